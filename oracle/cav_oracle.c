@@ -1,0 +1,354 @@
+/*
+ * cav_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * A plain-C CPU restatement of the reference's per-step hot path (mit-acl/gym-collision-avoidance,
+ * CollisionAvoidanceEnv.step / reset), used ONLY by tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs as the checker and the reported CPU baseline.  The product path
+ * (gym_collision_avoidance_b200 + libcavoid_sm100a.so) never links, loads or calls anything in oracle/.
+ *
+ * Parity pinning: the reference's own tests hold no golden vectors for this path, so this
+ * restatement is pinned against OUTPUTS OF THE REFERENCE ITSELF run in the build container:
+ *   - tests/golden/*.npz, minted by tools/make_golden.py from the unmodified Python reference
+ *     (tests/test_oracle_golden.py), and
+ *   - oracle/_ref/librvo2_ref.so, the unmodified reference RVO2 C++ (tests/test_oracle_rvo2.py, bit-exact).
+ *
+ * Each function cites the reference file:line it follows (paths relative to
+ * /root/reference/gym_collision_avoidance/envs/; R/ = policies/Python-RVO2/src/).
+ *
+ * Compiled with -ffp-contract=off: the reference is NumPy float64 (no FMA) and x86-64 g++ without -mfma.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "cavoid.h"
+
+#define CAVO_MAX_AGENTS 64
+
+static int g_threads = 0; /* 0 = OpenMP default */
+int cavo_get_max_threads(void);
+static int g_faithful_dostep = 0;
+
+/* ------------------------------------------------------------------------------------------------------------
+ * ORCA / RVO2 in float32 (R/Agent.cpp:287-366 lines, :417-421 solve, :424-448 neighbours, :470-475 update,
+ * :477-630 LP1/LP2/LP3; R/Vector2.h:95-126,285-328 arithmetic; R/Definitions.h:52 RVO_EPSILON).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct {
+    float px, py, dx, dy;
+} orca_line_t;
+#define RVO_EPS 0.00001f
+
+static inline float o_det(float ax, float ay, float bx, float by) { return ax * by - ay * bx; } /* Vector2.h:313-316 */
+static inline float o_dot(float ax, float ay, float bx, float by) { return ax * bx + ay * by; } /* Vector2.h:95-98 */
+
+/* R/Agent.cpp:477-548 */
+static int orca_lp1(const orca_line_t *lines, int lineNo, float radius, float ox, float oy, int directionOpt,
+                    float *rx, float *ry) {
+    const orca_line_t *L = &lines[lineNo];
+    const float dotProduct = o_dot(L->px, L->py, L->dx, L->dy);
+    const float discriminant = dotProduct * dotProduct + radius * radius - o_dot(L->px, L->py, L->px, L->py);
+    if (discriminant < 0.0f) return 0;
+    const float sqrtDiscriminant = sqrtf(discriminant);
+    float tLeft = -dotProduct - sqrtDiscriminant;
+    float tRight = -dotProduct + sqrtDiscriminant;
+    for (int i = 0; i < lineNo; ++i) {
+        const float denominator = o_det(L->dx, L->dy, lines[i].dx, lines[i].dy);
+        const float numerator = o_det(lines[i].dx, lines[i].dy, L->px - lines[i].px, L->py - lines[i].py);
+        if (fabsf(denominator) <= RVO_EPS) {
+            if (numerator < 0.0f) return 0;
+            continue;
+        }
+        const float t = numerator / denominator;
+        if (denominator >= 0.0f) {
+            tRight = (t < tRight) ? t : tRight; /* std::min(tRight, t) */
+        } else {
+            tLeft = (tLeft < t) ? t : tLeft; /* std::max(tLeft, t) */
+        }
+        if (tLeft > tRight) return 0;
+    }
+    if (directionOpt) {
+        if (o_dot(ox, oy, L->dx, L->dy) > 0.0f) {
+            *rx = L->px + tRight * L->dx;
+            *ry = L->py + tRight * L->dy;
+        } else {
+            *rx = L->px + tLeft * L->dx;
+            *ry = L->py + tLeft * L->dy;
+        }
+    } else {
+        const float t = o_dot(L->dx, L->dy, ox - L->px, oy - L->py);
+        if (t < tLeft) {
+            *rx = L->px + tLeft * L->dx;
+            *ry = L->py + tLeft * L->dy;
+        } else if (t > tRight) {
+            *rx = L->px + tRight * L->dx;
+            *ry = L->py + tRight * L->dy;
+        } else {
+            *rx = L->px + t * L->dx;
+            *ry = L->py + t * L->dy;
+        }
+    }
+    return 1;
+}
+
+/* R/Agent.cpp:550-581 */
+static int orca_lp2(const orca_line_t *lines, int n, float radius, float ox, float oy, int directionOpt, float *rx,
+                    float *ry) {
+    if (directionOpt) {
+        *rx = ox * radius;
+        *ry = oy * radius;
+    } else if (o_dot(ox, oy, ox, oy) > radius * radius) {
+        const float inv = 1.0f / sqrtf(o_dot(ox, oy, ox, oy)); /* normalize: v / abs(v) = v * (1/abs) */
+        *rx = (ox * inv) * radius;
+        *ry = (oy * inv) * radius;
+    } else {
+        *rx = ox;
+        *ry = oy;
+    }
+    for (int i = 0; i < n; ++i) {
+        if (o_det(lines[i].dx, lines[i].dy, lines[i].px - *rx, lines[i].py - *ry) > 0.0f) {
+            const float tx = *rx, ty = *ry;
+            if (!orca_lp1(lines, i, radius, ox, oy, directionOpt, rx, ry)) {
+                *rx = tx;
+                *ry = ty;
+                return i;
+            }
+        }
+    }
+    return n;
+}
+
+/* R/Agent.cpp:583-630 (numObstLines == 0 on this path: RVOPolicy never adds obstacles) */
+static void orca_lp3(const orca_line_t *lines, int n, int beginLine, float radius, float *rx, float *ry) {
+    float distance = 0.0f;
+    orca_line_t proj[CAVO_MAX_AGENTS];
+    for (int i = beginLine; i < n; ++i) {
+        if (o_det(lines[i].dx, lines[i].dy, lines[i].px - *rx, lines[i].py - *ry) > distance) {
+            int np = 0;
+            for (int j = 0; j < i; ++j) {
+                orca_line_t ln;
+                const float determinant = o_det(lines[i].dx, lines[i].dy, lines[j].dx, lines[j].dy);
+                if (fabsf(determinant) <= RVO_EPS) {
+                    if (o_dot(lines[i].dx, lines[i].dy, lines[j].dx, lines[j].dy) > 0.0f) continue;
+                    ln.px = 0.5f * (lines[i].px + lines[j].px);
+                    ln.py = 0.5f * (lines[i].py + lines[j].py);
+                } else {
+                    const float s = o_det(lines[j].dx, lines[j].dy, lines[i].px - lines[j].px, lines[i].py - lines[j].py) /
+                                    determinant;
+                    ln.px = lines[i].px + s * lines[i].dx;
+                    ln.py = lines[i].py + s * lines[i].dy;
+                }
+                const float ddx = lines[j].dx - lines[i].dx, ddy = lines[j].dy - lines[i].dy;
+                const float inv = 1.0f / sqrtf(o_dot(ddx, ddy, ddx, ddy));
+                ln.dx = ddx * inv;
+                ln.dy = ddy * inv;
+                proj[np++] = ln;
+            }
+            const float tx = *rx, ty = *ry;
+            if (orca_lp2(proj, np, radius, -lines[i].dy, lines[i].dx, 1, rx, ry) < np) {
+                *rx = tx;
+                *ry = ty;
+            }
+            distance = o_det(lines[i].dx, lines[i].dy, lines[i].px - *rx, lines[i].py - *ry);
+        }
+    }
+}
+
+/* One ego solve: neighbours (R/Agent.cpp:44-56,424-448; insertion in agent-index order = single kd-tree leaf,
+ * R/KdTree.cpp:266-271, exact for N <= 10; for N > 10 the kd-tree only changes the order of EXACT float
+ * distance ties), ORCA lines (R/Agent.cpp:295-366), LP2 then LP3 (:417-421).
+ * pos/vel [n][2] float32, rad [n] (already scaled), returns newVelocity. */
+void cavo_orca_solve(int n, int ego, const float *pos, const float *vel, const float *rad, float maxSpeed,
+                     float prefx, float prefy, float timeHorizon, float timeStep, float collab,
+                     float neighborDist, int maxNeighbors, float *out_vx, float *out_vy, orca_line_t *out_lines,
+                     int *out_nlines) {
+    int nb_idx[CAVO_MAX_AGENTS];
+    float nb_d[CAVO_MAX_AGENTS];
+    int nn = 0;
+    if (maxNeighbors > 0) {
+        float rangeSq = neighborDist * neighborDist;
+        for (int j = 0; j < n; ++j) {
+            if (j == ego) continue;
+            const float dx = pos[2 * ego] - pos[2 * j], dy = pos[2 * ego + 1] - pos[2 * j + 1];
+            const float distSq = o_dot(dx, dy, dx, dy);
+            if (distSq < rangeSq) {
+                if (nn < maxNeighbors) ++nn;
+                int i = nn - 1;
+                while (i != 0 && distSq < nb_d[i - 1]) {
+                    nb_d[i] = nb_d[i - 1];
+                    nb_idx[i] = nb_idx[i - 1];
+                    --i;
+                }
+                nb_d[i] = distSq;
+                nb_idx[i] = j;
+                if (nn == maxNeighbors) rangeSq = nb_d[nn - 1];
+            }
+        }
+    }
+    orca_line_t lines[CAVO_MAX_AGENTS];
+    int nl = 0;
+    const float invTimeHorizon = 1.0f / timeHorizon;
+    const float vx = vel[2 * ego], vy = vel[2 * ego + 1];
+    if (collab > 0.0f) {
+        for (int k = 0; k < nn; ++k) {
+            const int o = nb_idx[k];
+            const float rpx = pos[2 * o] - pos[2 * ego], rpy = pos[2 * o + 1] - pos[2 * ego + 1];
+            const float rvx = vx - vel[2 * o], rvy = vy - vel[2 * o + 1];
+            const float distSq = o_dot(rpx, rpy, rpx, rpy);
+            const float combinedRadius = rad[ego] + rad[o];
+            const float combinedRadiusSq = combinedRadius * combinedRadius;
+            orca_line_t ln;
+            float ux, uy;
+            if (distSq > combinedRadiusSq) {
+                const float wx = rvx - invTimeHorizon * rpx, wy = rvy - invTimeHorizon * rpy;
+                const float wLengthSq = o_dot(wx, wy, wx, wy);
+                const float dotProduct1 = o_dot(wx, wy, rpx, rpy);
+                if (dotProduct1 < 0.0f && dotProduct1 * dotProduct1 > combinedRadiusSq * wLengthSq) {
+                    const float wLength = sqrtf(wLengthSq);
+                    const float inv = 1.0f / wLength;
+                    const float uwx = wx * inv, uwy = wy * inv;
+                    ln.dx = uwy;
+                    ln.dy = -uwx;
+                    const float s = combinedRadius * invTimeHorizon - wLength;
+                    ux = s * uwx;
+                    uy = s * uwy;
+                } else {
+                    const float leg = sqrtf(distSq - combinedRadiusSq);
+                    const float inv = 1.0f / distSq;
+                    if (o_det(rpx, rpy, wx, wy) > 0.0f) {
+                        ln.dx = (rpx * leg - rpy * combinedRadius) * inv;
+                        ln.dy = (rpx * combinedRadius + rpy * leg) * inv;
+                    } else {
+                        ln.dx = (-(rpx * leg + rpy * combinedRadius)) * inv;
+                        ln.dy = (-(-rpx * combinedRadius + rpy * leg)) * inv;
+                    }
+                    const float dotProduct2 = o_dot(rvx, rvy, ln.dx, ln.dy);
+                    ux = dotProduct2 * ln.dx - rvx;
+                    uy = dotProduct2 * ln.dy - rvy;
+                }
+            } else {
+                const float invTimeStep = 1.0f / timeStep;
+                const float wx = rvx - invTimeStep * rpx, wy = rvy - invTimeStep * rpy;
+                const float wLength = sqrtf(o_dot(wx, wy, wx, wy));
+                const float inv = 1.0f / wLength;
+                const float uwx = wx * inv, uwy = wy * inv;
+                ln.dx = uwy;
+                ln.dy = -uwx;
+                const float s = combinedRadius * invTimeStep - wLength;
+                ux = s * uwx;
+                uy = s * uwy;
+            }
+            ln.px = vx + collab * ux;
+            ln.py = vy + collab * uy;
+            lines[nl++] = ln;
+        }
+    }
+    float rx, ry;
+    const int fail = orca_lp2(lines, nl, maxSpeed, prefx, prefy, 0, &rx, &ry);
+    if (fail < nl) orca_lp3(lines, nl, fail, maxSpeed, &rx, &ry);
+    *out_vx = rx;
+    *out_vy = ry;
+    if (out_lines) memcpy(out_lines, lines, sizeof(orca_line_t) * (size_t)nl);
+    if (out_nlines) *out_nlines = nl;
+}
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Map + laserscan, float64 geometry in both precisions (Map.py:6-64, LaserScanSensor.py:24-101).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct {
+    int rows, cols;
+    double origin0, origin1, cell;
+} cavo_map_t;
+
+static cavo_map_t cavo_map_dims(const cav_config_t *c) {
+    cavo_map_t m;
+    m.cell = c->map_grid_cell_size;
+    m.rows = (int)(c->map_x_width / m.cell); /* Map.py:13 dims */
+    m.cols = (int)(c->map_y_width / m.cell);
+    m.origin0 = (c->map_x_width / 2.) / m.cell; /* Map.py:23 */
+    m.origin1 = (c->map_y_width / 2.) / m.cell;
+    return m;
+}
+/* Map.py:26-32 */
+static int cavo_world_to_cell(const cavo_map_t *m, double px, double py, int *gx, int *gy) {
+    const double fx = floor(m->origin0 - py / m->cell);
+    const double fy = floor(m->origin1 + px / m->cell);
+    if (!(fx >= 0 && fy >= 0 && fx < m->rows && fy < m->cols)) {
+        *gx = -1;
+        *gy = -1;
+        return 0;
+    }
+    *gx = (int)fx;
+    *gy = (int)fy;
+    return 1;
+}
+
+#define REAL double
+#define SFX(n) n##_f64
+#define R_SIN sin
+#define R_COS cos
+#define R_ATAN2 atan2
+#define R_SQRT sqrt
+#define R_FABS fabs
+#define R_FMOD fmod
+#define R_RINT rint
+#include "cav_oracle_impl.h"
+#undef REAL
+#undef SFX
+#undef R_SIN
+#undef R_COS
+#undef R_ATAN2
+#undef R_SQRT
+#undef R_FABS
+#undef R_FMOD
+#undef R_RINT
+
+#define REAL float
+#define SFX(n) n##_f32
+#define R_SIN sinf
+#define R_COS cosf
+#define R_ATAN2 atan2f
+#define R_SQRT sqrtf
+#define R_FABS fabsf
+#define R_FMOD fmodf
+#define R_RINT rintf
+#include "cav_oracle_impl.h"
+
+/* ---------------------------------------------------------------------------------------------------------- */
+void cavo_set_threads(int n) { g_threads = n; }
+int cavo_get_max_threads(void) {
+#ifdef _OPENMP
+    return g_threads > 0 ? g_threads : omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+/* When non-zero, RVO agents redo the reference's full N-agent doStep per ego (RVOPolicy.py:93 ->
+ * R/RVOSimulator.cpp:163-183): N solves of which only the ego's is used.  Results are identical; only the
+ * CPU cost changes.  Used to report a "faithful" CPU baseline next to the efficient one. */
+void cavo_set_faithful_dostep(int on) { g_faithful_dostep = on; }
+
+#define DISPATCH(fn, ...) (cfg->precision == CAV_F64 ? fn##_f64(__VA_ARGS__) : fn##_f32(__VA_ARGS__))
+
+int cavo_policy(const cav_config_t *cfg, const cav_buffers_t *b, const float *ext) { return DISPATCH(policy, cfg, b, ext); }
+int cavo_dynamics(const cav_config_t *cfg, const cav_buffers_t *b, double dt) { return DISPATCH(dynamics, cfg, b, dt); }
+int cavo_pairwise_obs(const cav_config_t *cfg, const cav_buffers_t *b) { return DISPATCH(pairwise_obs, cfg, b); }
+int cavo_laserscan(const cav_config_t *cfg, const cav_buffers_t *b) { return DISPATCH(laserscan, cfg, b); }
+int cavo_reset(const cav_config_t *cfg, const cav_buffers_t *b, const uint8_t *mask, const cav_scenario_bank_t *bank,
+               const int32_t *scenario_idx, int accumulate_stats) {
+    return DISPATCH(reset, cfg, b, mask, bank, scenario_idx, accumulate_stats);
+}
+/* CollisionAvoidanceEnv.step, collision_avoidance_env.py:156-234 */
+int cavo_step(const cav_config_t *cfg, const cav_buffers_t *b, const float *ext, double dt) {
+    if (dt <= 0) dt = cfg->dt;
+    int rc;
+    if ((rc = cavo_policy(cfg, b, ext))) return rc;
+    if ((rc = cavo_dynamics(cfg, b, dt))) return rc;
+    if ((rc = cavo_pairwise_obs(cfg, b))) return rc;
+    if (cfg->obs_offset[CAV_OBS_LASERSCAN] >= 0)
+        if ((rc = cavo_laserscan(cfg, b))) return rc;
+    return 0;
+}
