@@ -1,0 +1,359 @@
+// cav_abi.cu -- the C ABI of libcavoid_sm100a.so (include/cavoid.h): handle management, config validation and
+// flattening, and the entry points that enqueue the sm_100a kernels on the caller's stream.  Nothing here
+// allocates device memory, copies host<->device or synchronises: every buffer is borrowed from the caller.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "cav_kernels.h"
+
+using namespace cav;
+
+struct cav_handle_s {
+    uint32_t magic;
+    cav_config_t cfg;
+    cav_buffers_t bufs;
+    bool bound;
+    int device;
+    int sm_count;
+    KParams<float> pf;
+    KParams<double> pd;
+    ObsPlan plan;
+    LaserParams lp;
+    ResetParams rp;
+    bool has_laser;
+    int launches;
+    char err[512];
+};
+
+#define CAV_MAGIC 0xCA70D001u
+
+static thread_local char g_err[512] = "";
+
+static int fail(cav_handle_t h, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (h) {
+        strncpy(h->err, buf, sizeof(h->err) - 1);
+        h->err[sizeof(h->err) - 1] = 0;
+    }
+    strncpy(g_err, buf, sizeof(g_err) - 1);
+    g_err[sizeof(g_err) - 1] = 0;
+    return code;
+}
+
+static bool valid(cav_handle_t h) { return h && h->magic == CAV_MAGIC; }
+
+template <typename T>
+static void fill_params(const cav_config_t &c, KParams<T> &p) {
+    p.E = c.num_envs;
+    p.N = c.num_agents;
+    p.dt = (T)c.dt;
+    p.near_goal_thr = (T)c.near_goal_threshold;
+    p.max_heading_change = (T)c.max_heading_change;
+    p.reward_at_goal = (T)c.reward_at_goal;
+    p.reward_coll_agent = (T)c.reward_collision_with_agent;
+    p.reward_coll_wall = (T)c.reward_collision_with_wall;
+    p.reward_time_step = (T)c.reward_time_step;
+    p.reward_wiggly = (T)c.reward_wiggly_behavior;
+    p.wiggly_thr = (T)c.wiggly_behavior_threshold;
+    p.getting_close = (T)c.getting_close_range;
+    // env.py:589-599: clip bounds = min / max of the possible reward values
+    const T vals[5] = {p.reward_at_goal, p.reward_coll_agent, p.reward_time_step, p.reward_coll_wall, p.reward_wiggly};
+    p.reward_min = vals[0];
+    p.reward_max = vals[0];
+    for (int k = 1; k < 5; ++k) {
+        if (vals[k] < p.reward_min) p.reward_min = vals[k];
+        if (vals[k] > p.reward_max) p.reward_max = vals[k];
+    }
+    p.sensing_horizon = (T)c.sensing_horizon;
+    p.K = c.max_num_other_agents_observed;
+    p.sorting = c.agent_sorting_method;
+    p.game_over_mode = c.game_over_mode;
+    p.rvo_inv_time_horizon_num = (float)c.rvo_time_horizon;
+    p.rvo_time_step = (float)c.dt;  // PyRVOSimulator(timeStep=Config.DT), RVOPolicy.py:13,25
+    p.rvo_collab = (float)c.rvo_collab_coeff;
+    p.rvo_neighbor_dist = (float)c.rvo_neighbor_dist;
+    p.rvo_max_delta_heading = (T)c.rvo_max_delta_heading;
+    p.rvo_radius_scale = (T)c.rvo_radius_scale;
+    p.rvo_inv_dt = (T)1 / (T)c.dt;  // 1/self.dt, RVOPolicy.py:105
+    p.rvo_max_neighbors = c.rvo_max_neighbors;
+    p.store_history = c.store_history;
+    p.history_len = c.history_len;
+    p.obs_len = c.obs_len;
+}
+
+static int state_len(const cav_config_t &c, int s) {
+    switch (s) {
+        case CAV_OBS_OTHER_AGENTS_STATES: return 7 * c.max_num_other_agents_observed;
+        case CAV_OBS_OTHER_AGENT_STATES: return 7;
+        case CAV_OBS_LASERSCAN: return c.laserscan_num_past * c.laserscan_length;
+        default: return 1;
+    }
+}
+
+static int build_plan(const cav_config_t &c, ObsPlan &pl) {
+    memset(&pl, 0, sizeof(pl));
+    for (int s = 0; s < CAV_OBS_NUM_STATES; ++s) pl.c_state[s] = -1;
+    pl.oas7_goff = c.obs_offset[CAV_OBS_OTHER_AGENT_STATES];
+    // states staged through shared memory by the pairwise+obs kernel, in ascending global offset
+    int order[CAV_OBS_NUM_STATES], no = 0;
+    for (int s = 0; s < CAV_OBS_NUM_STATES; ++s) {
+        if (c.obs_offset[s] < 0) continue;
+        if (c.obs_offset[s] + state_len(c, s) > c.obs_len) return -1;
+        if (s == CAV_OBS_OTHER_AGENT_STATES || s == CAV_OBS_LASERSCAN) continue;
+        order[no++] = s;
+    }
+    for (int i = 1; i < no; ++i)
+        for (int j = i; j > 0 && c.obs_offset[order[j]] < c.obs_offset[order[j - 1]]; --j) {
+            const int t = order[j];
+            order[j] = order[j - 1];
+            order[j - 1] = t;
+        }
+    int coff = 0;
+    for (int i = 0; i < no; ++i) {
+        const int s = order[i], go = c.obs_offset[s], ln = state_len(c, s);
+        if (i > 0 && go < c.obs_offset[order[i - 1]] + state_len(c, order[i - 1])) return -1;  // overlap
+        pl.c_state[s] = coff;
+        if (pl.nseg > 0 && pl.goff[pl.nseg - 1] + pl.len[pl.nseg - 1] == go) {
+            pl.len[pl.nseg - 1] += ln;
+        } else {
+            if (pl.nseg >= CAV_MAX_OBS_SEG) return -1;
+            pl.goff[pl.nseg] = go;
+            pl.coff[pl.nseg] = coff;
+            pl.len[pl.nseg] = ln;
+            pl.nseg++;
+        }
+        coff += ln;
+    }
+    pl.compact_len = coff > 0 ? coff : 1;
+    return 0;
+}
+
+extern "C" {
+
+int cav_abi_version(void) { return CAV_ABI_VERSION; }
+
+int cav_create(const cav_config_t *cfg, cav_handle_t *out) {
+    if (!cfg || !out) return fail(nullptr, CAV_ERR_NULL_POINTER, "cav_create: null argument");
+    *out = nullptr;
+    if (cfg->struct_size != (int32_t)sizeof(cav_config_t))
+        return fail(nullptr, CAV_ERR_BAD_CONFIG, "cav_create: struct_size %d != %zu", cfg->struct_size,
+                    sizeof(cav_config_t));
+    if (cfg->precision != CAV_F32 && cfg->precision != CAV_F64)
+        return fail(nullptr, CAV_ERR_BAD_CONFIG, "cav_create: bad precision %d", cfg->precision);
+    if (cfg->num_envs < 1) return fail(nullptr, CAV_ERR_BAD_CONFIG, "cav_create: num_envs %d < 1", cfg->num_envs);
+    if (cfg->num_agents < 1 || cfg->num_agents > CAV_MAX_AGENTS)
+        return fail(nullptr, CAV_ERR_BAD_CONFIG, "cav_create: num_agents %d outside [1, %d]", cfg->num_agents,
+                    CAV_MAX_AGENTS);
+    if (!(cfg->dt > 0.0)) return fail(nullptr, CAV_ERR_BAD_CONFIG, "cav_create: dt must be > 0");
+    if (cfg->max_num_other_agents_observed < 0 || cfg->obs_len < 1)
+        return fail(nullptr, CAV_ERR_BAD_CONFIG, "cav_create: bad observation sizes");
+    if (cfg->agent_sorting_method != CAV_SORT_CLOSEST_FIRST && cfg->agent_sorting_method != CAV_SORT_CLOSEST_LAST)
+        return fail(nullptr, CAV_ERR_UNSUPPORTED,
+                    "cav_create: agent_sorting_method %d has no device implementation (closest_first / closest_last)",
+                    cfg->agent_sorting_method);
+    if (cfg->game_over_mode < 0 || cfg->game_over_mode > 2)
+        return fail(nullptr, CAV_ERR_BAD_CONFIG, "cav_create: bad game_over_mode");
+    if (cfg->rvo_collab_coeff < 0.0)
+        return fail(nullptr, CAV_ERR_UNSUPPORTED, "cav_create: anti-collaborative RVO (collab coeff < 0) is not built");
+    if (cfg->store_history && cfg->history_len < 1)
+        return fail(nullptr, CAV_ERR_BAD_CONFIG, "cav_create: store_history needs history_len >= 1");
+    cav_handle_s *h = new (std::nothrow) cav_handle_s;
+    if (!h) return fail(nullptr, CAV_ERR_BAD_CONFIG, "cav_create: out of host memory");
+    memset(h, 0, sizeof(*h));
+    h->magic = CAV_MAGIC;
+    h->cfg = *cfg;
+    if (build_plan(*cfg, h->plan) != 0) {
+        delete h;
+        return fail(nullptr, CAV_ERR_BAD_CONFIG, "cav_create: observation offsets overlap or exceed obs_len");
+    }
+    h->has_laser = cfg->obs_offset[CAV_OBS_LASERSCAN] >= 0;
+    if (h->has_laser) {
+        if (!cfg->use_static_map) {
+            delete h;
+            return fail(nullptr, CAV_ERR_BAD_CONFIG, "cav_create: laserscan needs use_static_map "
+                                                      "(LaserScanSensor.py:25-27)");
+        }
+        LaserParams &lp = h->lp;
+        lp.E = cfg->num_envs;
+        lp.N = cfg->num_agents;
+        lp.B = cfg->laserscan_length;
+        lp.P = cfg->laserscan_num_past;
+        lp.obs_len = cfg->obs_len;
+        lp.obs_off = cfg->obs_offset[CAV_OBS_LASERSCAN];
+        lp.cell = cfg->map_grid_cell_size;
+        lp.inv_cell = 1.0 / lp.cell;
+        lp.rows = (int)(cfg->map_x_width / lp.cell);  // Map.py:13
+        lp.cols = (int)(cfg->map_y_width / lp.cell);
+        lp.wpr = (lp.cols + 31) / 32;
+        lp.origin0 = (cfg->map_x_width / 2.) / lp.cell;  // Map.py:23
+        lp.origin1 = (cfg->map_y_width / 2.) / lp.cell;
+        lp.min_angle = cfg->laser_min_angle;
+        lp.max_angle = cfg->laser_max_angle;
+        lp.ang_step = lp.B > 1 ? (lp.max_angle - lp.min_angle) / (double)(lp.B - 1) : 0.0;
+        lp.min_range = cfg->laser_min_range;
+        lp.max_range = cfg->laser_max_range;
+        lp.range_res = cfg->laser_range_resolution;
+        lp.nr = (int)ceil((lp.max_range - lp.min_range) / lp.range_res);  // len(np.arange(min, max, res))
+        if (lp.B < 1 || lp.P < 1 || lp.rows < 1 || lp.cols < 1 || lp.nr < 1 || (size_t)lp.rows * lp.wpr * 4 > 200 * 1024) {
+            delete h;
+            return fail(nullptr, CAV_ERR_BAD_CONFIG, "cav_create: bad laserscan / map geometry");
+        }
+    }
+    h->rp.E = cfg->num_envs;
+    h->rp.N = cfg->num_agents;
+    h->rp.obs_len = cfg->obs_len;
+    h->rp.dt = cfg->dt;
+    h->rp.near_goal_threshold = cfg->near_goal_threshold;
+    h->rp.max_time_ratio = cfg->max_time_ratio;
+    fill_params<float>(*cfg, h->pf);
+    fill_params<double>(*cfg, h->pd);
+    cudaError_t ce = cudaGetDevice(&h->device);
+    if (ce == cudaSuccess) ce = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device);
+    if (ce != cudaSuccess) {
+        const int rc = fail(nullptr, CAV_ERR_CUDA, "cav_create: %s", cudaGetErrorString(ce));
+        delete h;
+        return rc;
+    }
+    *out = h;
+    return CAV_OK;
+}
+
+size_t cav_real_bytes(cav_handle_t h) { return valid(h) ? (h->cfg.precision == CAV_F64 ? 8 : 4) : 0; }
+
+size_t cav_workspace_bytes(cav_handle_t h) {
+    (void)h;
+    return 0;
+}
+
+int cav_bind(cav_handle_t h, const cav_buffers_t *bufs) {
+    if (!valid(h)) return fail(nullptr, CAV_ERR_BAD_HANDLE, "cav_bind: bad handle");
+    if (!bufs) return fail(h, CAV_ERR_NULL_POINTER, "cav_bind: null buffers");
+    const struct {
+        const void *p;
+        const char *name;
+        bool vec;
+    } req[] = {{bufs->pv, "pv", true},         {bufs->goal, "goal", true},       {bufs->ht, "ht", true},
+               {bufs->ego, "ego", true},       {bufs->flags, "flags", false},    {bufs->kinds, "kinds", false},
+               {bufs->step_num, "step_num", false}, {bufs->actions, "actions", false},
+               {bufs->reward, "reward", false}, {bufs->done, "done", false},     {bufs->game_over, "game_over", false},
+               {bufs->obs, "obs", false}};
+    for (const auto &r : req) {
+        if (!r.p) return fail(h, CAV_ERR_NULL_POINTER, "cav_bind: %s is NULL", r.name);
+        if (r.vec && ((uintptr_t)r.p & 15u)) return fail(h, CAV_ERR_MISALIGNED, "cav_bind: %s not 16-byte aligned", r.name);
+    }
+    if (((uintptr_t)bufs->actions & 7u)) return fail(h, CAV_ERR_MISALIGNED, "cav_bind: actions not 8-byte aligned");
+    const void *optvec[] = {bufs->aux0, bufs->past_actions, bufs->past_vel};
+    for (const void *p : optvec)
+        if (p && ((uintptr_t)p & 15u)) return fail(h, CAV_ERR_MISALIGNED, "cav_bind: aux column not 16-byte aligned");
+    if (h->has_laser && !bufs->laser_count) return fail(h, CAV_ERR_NULL_POINTER, "cav_bind: laser_count is NULL");
+    if (h->cfg.store_history && !bufs->history) return fail(h, CAV_ERR_NULL_POINTER, "cav_bind: history is NULL");
+    h->bufs = *bufs;
+    h->bound = true;
+    return CAV_OK;
+}
+
+#define CAV_CHECK_READY(h, name)                                                    \
+    if (!valid(h)) return fail(nullptr, CAV_ERR_BAD_HANDLE, name ": bad handle");   \
+    if (!(h)->bound) return fail(h, CAV_ERR_NOT_BOUND, name ": cav_bind has not been called")
+
+#define CAV_CUDA(h, name, expr)                                                                \
+    do {                                                                                       \
+        cudaError_t ce_ = (expr);                                                              \
+        if (ce_ != cudaSuccess) return fail(h, CAV_ERR_CUDA, name ": %s", cudaGetErrorString(ce_)); \
+        (h)->launches++;                                                                       \
+    } while (0)
+
+static int do_policy_move(cav_handle_t h, const float *ext, int phases, double dt, cudaStream_t st) {
+    if (h->cfg.precision == CAV_F64)
+        CAV_CUDA(h, "policy_move", run_policy_move<double>(h->bufs, h->pd, ext, phases, dt, h->sm_count, st));
+    else
+        CAV_CUDA(h, "policy_move", run_policy_move<float>(h->bufs, h->pf, ext, phases, dt, h->sm_count, st));
+    return CAV_OK;
+}
+static int do_pairwise_obs(cav_handle_t h, const uint8_t *mask, int obs_only, cudaStream_t st) {
+    if (h->cfg.precision == CAV_F64)
+        CAV_CUDA(h, "pairwise_obs", run_pairwise_obs<double>(h->bufs, h->pd, h->plan, mask, obs_only, h->sm_count, st));
+    else
+        CAV_CUDA(h, "pairwise_obs", run_pairwise_obs<float>(h->bufs, h->pf, h->plan, mask, obs_only, h->sm_count, st));
+    return CAV_OK;
+}
+static int do_laser(cav_handle_t h, const uint8_t *mask, cudaStream_t st) {
+    if (h->cfg.precision == CAV_F64)
+        CAV_CUDA(h, "laserscan", run_laserscan<double>(h->bufs, h->lp, mask, h->sm_count, st));
+    else
+        CAV_CUDA(h, "laserscan", run_laserscan<float>(h->bufs, h->lp, mask, h->sm_count, st));
+    return CAV_OK;
+}
+
+int cav_reset(cav_handle_t h, const uint8_t *env_mask, const cav_scenario_bank_t *bank, const int32_t *scenario_idx,
+              int accumulate_stats, cav_stream_t stream) {
+    CAV_CHECK_READY(h, "cav_reset");
+    if (!bank || !bank->rows) return fail(h, CAV_ERR_NULL_POINTER, "cav_reset: scenario bank is NULL");
+    if (bank->num_scenarios < 1) return fail(h, CAV_ERR_BAD_CONFIG, "cav_reset: empty scenario bank");
+    cudaStream_t st = (cudaStream_t)stream;
+    h->launches = 0;
+    if (h->cfg.precision == CAV_F64)
+        CAV_CUDA(h, "reset", run_reset<double>(h->bufs, h->rp, env_mask, *bank, scenario_idx, accumulate_stats, st));
+    else
+        CAV_CUDA(h, "reset", run_reset<float>(h->bufs, h->rp, env_mask, *bank, scenario_idx, accumulate_stats, st));
+    int rc = do_pairwise_obs(h, env_mask, 1, st);  // reset returns self._get_obs() (env.py:282)
+    if (rc) return rc;
+    if (h->has_laser) rc = do_laser(h, env_mask, st);
+    return rc;
+}
+
+int cav_step(cav_handle_t h, const float *ext_actions, double dt, cav_stream_t stream) {
+    CAV_CHECK_READY(h, "cav_step");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!(dt > 0.0)) dt = h->cfg.dt;
+    h->launches = 0;
+    int rc = do_policy_move(h, ext_actions, 3, dt, st);
+    if (rc) return rc;
+    rc = do_pairwise_obs(h, nullptr, 0, st);
+    if (rc) return rc;
+    if (h->has_laser) rc = do_laser(h, nullptr, st);
+    return rc;
+}
+
+int cav_k_policy(cav_handle_t h, const float *ext_actions, cav_stream_t stream) {
+    CAV_CHECK_READY(h, "cav_k_policy");
+    h->launches = 0;
+    return do_policy_move(h, ext_actions, 1, h->cfg.dt, (cudaStream_t)stream);
+}
+int cav_k_dynamics(cav_handle_t h, double dt, cav_stream_t stream) {
+    CAV_CHECK_READY(h, "cav_k_dynamics");
+    if (!(dt > 0.0)) dt = h->cfg.dt;
+    h->launches = 0;
+    return do_policy_move(h, nullptr, 2, dt, (cudaStream_t)stream);
+}
+int cav_k_pairwise_obs(cav_handle_t h, cav_stream_t stream) {
+    CAV_CHECK_READY(h, "cav_k_pairwise_obs");
+    h->launches = 0;
+    return do_pairwise_obs(h, nullptr, 0, (cudaStream_t)stream);
+}
+int cav_k_laserscan(cav_handle_t h, cav_stream_t stream) {
+    CAV_CHECK_READY(h, "cav_k_laserscan");
+    if (!h->has_laser) return fail(h, CAV_ERR_BAD_CONFIG, "cav_k_laserscan: laserscan is not in the observation");
+    h->launches = 0;
+    return do_laser(h, nullptr, (cudaStream_t)stream);
+}
+
+int cav_last_launch_count(cav_handle_t h) { return valid(h) ? h->launches : 0; }
+
+const char *cav_last_error(cav_handle_t h) { return valid(h) ? h->err : g_err; }
+
+int cav_destroy(cav_handle_t h) {
+    if (!valid(h)) return fail(nullptr, CAV_ERR_BAD_HANDLE, "cav_destroy: bad handle");
+    h->magic = 0;
+    delete h;
+    return CAV_OK;
+}
+
+}  // extern "C"

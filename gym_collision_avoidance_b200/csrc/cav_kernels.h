@@ -1,0 +1,39 @@
+// cav_kernels.h -- internal launcher interface between the C-ABI layer (cav_abi.cu) and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "cav_common.cuh"
+
+namespace cav {
+
+// G lanes per agent, SL neighbours per lane, GPE groups per env, EPB envs per CTA, CTA size
+void launch_geometry(int N, int &G, int &SL, int &GPE, int &EPB, int &threads);
+
+// phases: 1 = policy (action selection), 2 = move, 3 = both (fused)
+template <typename T>
+cudaError_t run_policy_move(const cav_buffers_t &bufs, const KParams<T> &p, const float *ext, int phases, double dt,
+                            int sm_count, cudaStream_t st);
+template <typename T>
+cudaError_t run_pairwise_obs(const cav_buffers_t &bufs, const KParams<T> &p, const ObsPlan &plan,
+                             const uint8_t *env_mask, int obs_only, int sm_count, cudaStream_t st);
+
+struct LaserParams {
+    int E, N, B, P, obs_len, obs_off;
+    int rows, cols, wpr, nr;
+    double origin0, origin1, cell, inv_cell;
+    double min_angle, max_angle, ang_step, min_range, max_range, range_res;
+};
+template <typename T>
+cudaError_t run_laserscan(const cav_buffers_t &bufs, const LaserParams &lp, const uint8_t *env_mask, int sm_count,
+                          cudaStream_t st);
+
+struct ResetParams {
+    int E, N, obs_len;
+    double dt, near_goal_threshold, max_time_ratio;
+};
+template <typename T>
+cudaError_t run_reset(const cav_buffers_t &bufs, const ResetParams &rp, const uint8_t *env_mask,
+                      const cav_scenario_bank_t &bank, const int32_t *scenario_idx, int accumulate_stats,
+                      cudaStream_t st);
+
+}  // namespace cav

@@ -1,0 +1,181 @@
+// cav_laser.cu -- LaserScanSensor raycast for libcavoid_sm100a.so (sm_100a).
+//
+// Replaces, per environment and step: Map.add_agents_to_map (reference Map.py:46-64: copy the static map and paint
+// every agent's disc) and, per agent, LaserScanSensor.sense (LaserScanSensor.py:49-101: 512 beams x 60 range
+// samples looked up in the 160x160 occupancy grid, ego disc masked out, "cumsum == 1" range pick, 3-deep history).
+//
+// Mapping: a CTA owns (environment, chunk of agents).  It rasterises the environment's occupancy grid into a
+// bit-packed shared-memory bitmap (rows x ceil(cols/32) words; 3.2 KB for 160x160) with shared-memory atomicOr,
+// then marches beams one thread per beam with bit tests out of shared memory and an early exit at the second hit.
+// Geometry is float64 in both precisions (positions / heading are promoted): grid-cell decisions then match the
+// reference's float64 cells except where a sample lies within 1e-9 cells of a cell border (exact division path).
+// The observation's laserscan segment doubles as the sensor's measurement_history (rows shift down in place).
+#include "cav_kernels.h"
+
+namespace cav {
+
+struct LaserPtrs {
+    const void *pv, *goal, *ht;
+    const int32_t *num_active;
+    void *obs;
+    uint32_t *laser_count;
+    const uint32_t *static_map_bits;
+};
+
+// Map.world_coordinates_to_map_indices (Map.py:26-32): gx = floor(origin0 - y/cell), gy = floor(origin1 + x/cell).
+// y*inv_cell replaces the division unless the result is within 1e-9 of an integer, where the exact quotient decides.
+__device__ __forceinline__ double cell_coord(double origin, double v, double cell, double inv_cell, bool negate) {
+    const double a = v * inv_cell;
+    double c = negate ? (origin - a) : (origin + a);
+    if (fabs(c - rint(c)) < 1e-9 * fmax(1.0, fabs(c))) {
+        const double q = v / cell;
+        c = negate ? (origin - q) : (origin + q);
+    }
+    return floor(c);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_laserscan(LaserPtrs b, LaserParams lp, const uint8_t *__restrict__ env_mask,
+                                                     int APC, int chunks, int nwork) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t *s_map = reinterpret_cast<uint32_t *>(smem_raw);
+    const int map_words = lp.rows * lp.wpr;
+    double *s_px = reinterpret_cast<double *>(smem_raw + (((size_t)map_words * 4 + 15) & ~(size_t)15));
+    double *s_py = s_px + CAV_MAX_AGENTS;
+    double *s_hd = s_py + CAV_MAX_AGENTS;
+    double *s_rr2 = s_hd + CAV_MAX_AGENTS;
+    int *s_gx = reinterpret_cast<int *>(s_rr2 + CAV_MAX_AGENTS);
+    int *s_gy = s_gx + CAV_MAX_AGENTS;
+    int *s_in = s_gy + CAV_MAX_AGENTS;
+    uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_in + CAV_MAX_AGENTS);
+
+    const int tid = threadIdx.x;
+    const int N = lp.N;
+    const R4<T> *g_pv = reinterpret_cast<const R4<T> *>(b.pv);
+    const R4<T> *g_goal = reinterpret_cast<const R4<T> *>(b.goal);
+    const R4<T> *g_ht = reinterpret_cast<const R4<T> *>(b.ht);
+    T *g_obs = reinterpret_cast<T *>(b.obs);
+
+    for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+        const int e = w / chunks, chunk = w - e * chunks;
+        if (env_mask && !env_mask[e]) continue;  // block-uniform
+        const int n = b.num_active ? b.num_active[e] : N;
+        if (chunk * APC >= n) continue;
+        const size_t base = (size_t)e * N;
+        // ---- 1. static map + agent records ----
+        for (int k = tid; k < map_words; k += blockDim.x) s_map[k] = b.static_map_bits ? b.static_map_bits[k] : 0u;
+        if (tid < n) {
+            const R4<T> pv = ld4(g_pv + base + tid);
+            const double px = (double)pv.x, py = (double)pv.y;
+            s_px[tid] = px;
+            s_py[tid] = py;
+            s_hd[tid] = (double)ld4(g_ht + base + tid).x;
+            const double rc = (double)ld4(g_goal + base + tid).z / lp.cell;  // Map.py:55 (radius/grid_cell_size)**2
+            s_rr2[tid] = rc * rc;
+            const double fx = cell_coord(lp.origin0, py, lp.cell, lp.inv_cell, true);
+            const double fy = cell_coord(lp.origin1, px, lp.cell, lp.inv_cell, false);
+            const bool in = (fx >= 0.0 && fy >= 0.0 && fx < (double)lp.rows && fy < (double)lp.cols);
+            s_in[tid] = in ? 1 : 0;
+            s_gx[tid] = in ? (int)fx : -1;
+            s_gy[tid] = in ? (int)fy : -1;
+            s_cnt[tid] = b.laser_count[base + tid];
+        }
+        __syncthreads();
+        // ---- 2. paint discs (Map.py:46-64): cells with (col-gy)^2 + (row-gx)^2 < (r/cell)^2 ----
+        {
+            const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+            for (int a = warp; a < n; a += nwarps) {
+                if (!s_in[a]) continue;  // off-map agents paint nothing (Map.py:58-64)
+                const double rr2 = s_rr2[a];
+                double rcd = sqrt(rr2);
+                if (!(rcd < (double)(lp.rows + lp.cols))) rcd = (double)(lp.rows + lp.cols);
+                const int R = (int)rcd + 1;
+                const int gr = s_gx[a], gc = s_gy[a];
+                const int r0 = max(0, gr - R), r1 = min(lp.rows - 1, gr + R);
+                const int c0 = max(0, gc - R), c1 = min(lp.cols - 1, gc + R);
+                const int wbox = c1 - c0 + 1, cells = wbox * (r1 - r0 + 1);
+                for (int k = lane; k < cells; k += 32) {
+                    const int r = r0 + k / wbox, c = c0 + k % wbox;
+                    const double dc = (double)(c - gc), dr = (double)(r - gr);
+                    if (dc * dc + dr * dr < rr2) atomicOr(&s_map[r * lp.wpr + (c >> 5)], 1u << (c & 31));
+                }
+            }
+        }
+        __syncthreads();
+        // ---- 3. beams ----
+        const int a_end = min(n, (chunk + 1) * APC);
+        for (int h = chunk * APC; h < a_end; ++h) {
+            const double px = s_px[h], py = s_py[h], hd = s_hd[h], rr2 = s_rr2[h];
+            const int ego_in = s_in[h], cgx = s_gx[h], cgy = s_gy[h];
+            const uint32_t cnt = s_cnt[h];
+            T *o = g_obs + (base + h) * (size_t)lp.obs_len + lp.obs_off;
+            for (int bi = tid; bi < lp.B; bi += blockDim.x) {
+                double ang0 = (double)bi * lp.ang_step + lp.min_angle;  // np.linspace (LaserScanSensor.py:38)
+                if (bi == lp.B - 1) ang0 = lp.max_angle;
+                const double ang = ang0 + hd;  // :66
+                double sa, ca;
+                sincos(ang, &sa, &ca);
+                int cum = 0, kstar = -1;
+#pragma unroll 1
+                for (int k = 0; k < lp.nr; ++k) {
+                    const double rk = lp.min_range + (double)k * lp.range_res;  // np.arange (:39)
+                    const double x = px + rk * ca, y = py + rk * sa;            // :70-72
+                    const double fx = cell_coord(lp.origin0, y, lp.cell, lp.inv_cell, true);
+                    const double fy = cell_coord(lp.origin1, x, lp.cell, lp.inv_cell, false);
+                    int hit = 0;
+                    if (fx >= 0.0 && fy >= 0.0 && fx < (double)lp.rows && fy < (double)lp.cols) {
+                        const int gx = (int)fx, gy = (int)fy;
+                        hit = (s_map[gx * lp.wpr + (gy >> 5)] >> (gy & 31)) & 1u;
+                        if (hit && ego_in) {  // ego mask (:76-77)
+                            const double dc = (double)(gy - cgy), dr = (double)(gx - cgx);
+                            if (dc * dc + dr * dr < rr2) hit = 0;
+                        }
+                    }
+                    cum += hit;
+                    if (cum == 1) kstar = k;  // :78-82: the LAST index whose cumulative hit count is 1
+                    if (cum >= 2) break;
+                }
+                const double rng = kstar >= 0 ? lp.min_range + (double)kstar * lp.range_res : lp.max_range;
+                if (cnt == 0u) {  // first measurement fills every row (:84-85)
+                    for (int pp = 0; pp < lp.P; ++pp) o[(size_t)pp * lp.B + bi] = (T)rng;
+                } else {  // np.roll(history, 1, axis=0); row 0 = newest (:86-88)
+                    for (int pp = lp.P - 1; pp >= 1; --pp) o[(size_t)pp * lp.B + bi] = o[(size_t)(pp - 1) * lp.B + bi];
+                    o[bi] = (T)rng;
+                }
+            }
+        }
+        if (tid >= chunk * APC && tid < a_end) b.laser_count[base + tid] = s_cnt[tid] + 1u;
+        __syncthreads();
+    }
+}
+
+template <typename T>
+cudaError_t run_laserscan(const cav_buffers_t &bufs, const LaserParams &lp, const uint8_t *env_mask, int sm_count,
+                          cudaStream_t st) {
+    LaserPtrs p;
+    p.pv = bufs.pv;
+    p.goal = bufs.goal;
+    p.ht = bufs.ht;
+    p.num_active = bufs.num_active;
+    p.obs = bufs.obs;
+    p.laser_count = bufs.laser_count;
+    p.static_map_bits = bufs.static_map_bits;
+    const int APC = 4;
+    const int chunks = (lp.N + APC - 1) / APC;
+    const int nwork = lp.E * chunks;
+    const size_t smem = (((size_t)lp.rows * lp.wpr * 4 + 15) & ~(size_t)15) + CAV_MAX_AGENTS * (4 * 8 + 4 * 4) + 64;
+    auto kern = k_laserscan<T>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    const int grid = nwork < sm_count * 32 ? nwork : sm_count * 32;
+    kern<<<grid, 256, smem, st>>>(p, lp, env_mask, APC, chunks, nwork);
+    return cudaGetLastError();
+}
+
+template cudaError_t run_laserscan<float>(const cav_buffers_t &, const LaserParams &, const uint8_t *, int, cudaStream_t);
+template cudaError_t run_laserscan<double>(const cav_buffers_t &, const LaserParams &, const uint8_t *, int,
+                                           cudaStream_t);
+
+}  // namespace cav

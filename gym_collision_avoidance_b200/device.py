@@ -1,0 +1,173 @@
+"""Device-side containers and the handle wrapper over ``libcavoid_sm100a.so``.
+
+PyTorch is used only as the CUDA memory container / stream provider (``tensor.data_ptr()``,
+``torch.cuda.current_stream()``); every computation on the step path happens inside the library's sm_100a kernels.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import abi
+from .state import HostState, column_specs, make_bank
+
+_TORCH_KIND = {"f32": torch.float32, "u32": torch.int32, "i32": torch.int32, "u8": torch.uint8, "u64": torch.int64}
+_NP_VIEW = {"u32": np.uint32, "u64": np.uint64}
+
+
+class DeviceState(object):
+    """SoA state as torch CUDA tensors ([E, N, ...] env-major; see ``state.column_specs``)."""
+
+    def __init__(self, c, device):
+        self.c = c
+        self.device = torch.device(device)
+        self.real = torch.float64 if c.precision == abi.CAV_F64 else torch.float32
+        self.kinds_of = {}
+        self.t = {}
+        for name, (shape, kind) in column_specs(c).items():
+            dt = self.real if kind == "real" else _TORCH_KIND[kind]
+            self.t[name] = torch.zeros(shape, dtype=dt, device=self.device)
+            self.kinds_of[name] = kind
+        self.t["num_active"].fill_(c.num_agents)
+        self.static_map_bits = None
+
+    def __getattr__(self, k):
+        t = self.__dict__.get("t", {})
+        if k in t:
+            return t[k]
+        raise AttributeError(k)
+
+    def buffers(self):
+        b = abi.CavBuffers()
+        for n in abi.BUFFER_FIELDS:
+            a = self.t.get(n)
+            setattr(b, n, a.data_ptr() if a is not None else None)
+        if self.static_map_bits is not None:
+            b.static_map_bits = self.static_map_bits.data_ptr()
+        return b
+
+    def set_static_map(self, bits_u32):
+        """bits: uint32 array [rows * ceil(cols/32)] (row-major bitmap of Map.static_map)."""
+        a = np.ascontiguousarray(bits_u32, dtype=np.uint32).view(np.int32)
+        self.static_map_bits = torch.from_numpy(a.copy()).to(self.device)
+
+    def load_host(self, hs):
+        for name, arr in hs.arrays.items():
+            a = arr
+            if a.dtype == np.uint32:
+                a = a.view(np.int32)
+            elif a.dtype == np.uint64:
+                a = a.view(np.int64)
+            self.t[name].copy_(torch.from_numpy(np.ascontiguousarray(a)))
+        if hs.static_map_bits is not None:
+            self.set_static_map(hs.static_map_bits)
+
+    def to_host(self):
+        hs = HostState(self.c)
+        for name, t in self.t.items():
+            a = t.detach().cpu().numpy()
+            k = self.kinds_of[name]
+            if k in _NP_VIEW:
+                a = a.view(_NP_VIEW[k])
+            hs.arrays[name][...] = a
+        return hs
+
+
+class DeviceBank(object):
+    """Scenario bank resident in HBM (rows float64 [S, N, 8], optional kinds / num_active)."""
+
+    def __init__(self, rows, kinds=None, num_active=None, device="cuda"):
+        r, k, na = make_bank(rows, kinds, num_active)
+        self.rows = torch.from_numpy(r).to(device)
+        self.kinds = None if k is None else torch.from_numpy(k.view(np.int32).copy()).to(device)
+        self.num_active = None if na is None else torch.from_numpy(na).to(device)
+        self.num_scenarios = r.shape[0]
+
+    def struct(self):
+        s = abi.CavScenarioBank()
+        s.rows = self.rows.data_ptr()
+        s.kinds = self.kinds.data_ptr() if self.kinds is not None else None
+        s.num_active = self.num_active.data_ptr() if self.num_active is not None else None
+        s.num_scenarios = self.num_scenarios
+        return s
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+class Cavoid(object):
+    """One handle bound to one device + its SoA state.  Thin: every method is one C-ABI call."""
+
+    def __init__(self, cav_config, device="cuda:0", state=None):
+        self.L = abi.load_library()
+        self.c = cav_config
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise abi.CavoidError("the step path runs on CUDA only (no CPU fallback)")
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            rc = self.L.cav_create(ctypes.byref(self.c), ctypes.byref(self._h))
+        if rc != 0:
+            raise abi.CavoidError("cav_create failed (%s): %s" % (
+                abi.STATUS_NAMES.get(rc, rc), self.L.cav_last_error(None).decode()))
+        self.state = state if state is not None else DeviceState(self.c, self.device)
+        self.bind()
+        self.launches = 0
+
+    def bind(self):
+        b = self.state.buffers()
+        self._check(self.L.cav_bind(self._h, ctypes.byref(b)), "cav_bind")
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise abi.CavoidError("%s failed (%s): %s" % (what, abi.STATUS_NAMES.get(rc, rc),
+                                                          self.L.cav_last_error(self._h).decode()))
+
+    def _stream(self, stream):
+        s = stream if stream is not None else torch.cuda.current_stream(self.device)
+        return ctypes.c_void_p(s.cuda_stream)
+
+    def step(self, ext_actions=None, dt=0.0, stream=None):
+        self._check(self.L.cav_step(self._h, _ptr(ext_actions), float(dt), self._stream(stream)), "cav_step")
+        self.launches += self.L.cav_last_launch_count(self._h)
+
+    def reset(self, bank, env_mask=None, scenario_idx=None, accumulate_stats=False, stream=None):
+        bs = bank.struct()
+        self._check(self.L.cav_reset(self._h, _ptr(env_mask), ctypes.byref(bs), _ptr(scenario_idx),
+                                     int(accumulate_stats), self._stream(stream)), "cav_reset")
+        self.launches += self.L.cav_last_launch_count(self._h)
+
+    def k_policy(self, ext_actions=None, stream=None):
+        self._check(self.L.cav_k_policy(self._h, _ptr(ext_actions), self._stream(stream)), "cav_k_policy")
+        self.launches += self.L.cav_last_launch_count(self._h)
+
+    def k_dynamics(self, dt=0.0, stream=None):
+        self._check(self.L.cav_k_dynamics(self._h, float(dt), self._stream(stream)), "cav_k_dynamics")
+        self.launches += self.L.cav_last_launch_count(self._h)
+
+    def k_pairwise_obs(self, stream=None):
+        self._check(self.L.cav_k_pairwise_obs(self._h, self._stream(stream)), "cav_k_pairwise_obs")
+        self.launches += self.L.cav_last_launch_count(self._h)
+
+    def k_laserscan(self, stream=None):
+        self._check(self.L.cav_k_laserscan(self._h, self._stream(stream)), "cav_k_laserscan")
+        self.launches += self.L.cav_last_launch_count(self._h)
+
+    def stats(self):
+        raw = self.state.stats.detach().cpu().numpy().view(np.uint64)
+        out = {}
+        for i, name in enumerate(abi.STAT_NAMES):
+            out[name] = float(raw[i:i + 1].view(np.float64)[0]) if i in abi.STAT_IS_DOUBLE else int(raw[i])
+        return out
+
+    def close(self):
+        if self._h:
+            self.L.cav_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

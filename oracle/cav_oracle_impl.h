@@ -574,7 +574,8 @@ static void SFX(reset_env)(const cav_config_t *cfg, const cav_buffers_t *b, cons
         /* env.reset zeroes the observation dict before sensing (env.py:276-281) */
         memset((REAL *)b->obs + g * cfg->obs_len, 0, sizeof(REAL) * (size_t)cfg->obs_len);
     }
-    b->game_over[e] = 0;
+    /* game_over[e] is left untouched: the auto-reset caller still needs the finished step's flag
+     * (DummyVecEnv.step_wait returns done=True together with the reset observation, vec_env.py:120-128). */
 }
 
 static void SFX(accumulate_stats)(const cav_config_t *cfg, const cav_buffers_t *b, int e) {

@@ -94,8 +94,25 @@ def assert_close(name, got, want, rtol, atol, angle=False):
     return float(err.max()) if err.size else 0.0
 
 
-def compare_step(g, st, envs, ts, rtol, atol, check_aux=True, obs_rtol=None, obs_atol=None):
-    """Compare env e of `st` (after one step from golden state ts[e]) against golden state ts[e]+1."""
+class Tol(object):
+    """Per-quantity tolerances.  `pos`: positions / distances / times; `ang`: angles (compared modulo 2*pi);
+    `vel`: velocities, speeds and commanded actions; `laser_frac`: allowed fraction of differing laser beams."""
+
+    def __init__(self, rtol, atol, vel=None, ang=None, laser_frac=0.0):
+        self.pos = (rtol, atol)
+        self.vel = vel if vel is not None else (rtol, atol)
+        self.ang = ang if ang is not None else (rtol, atol)
+        self.laser_frac = laser_frac
+
+
+def _as_tol(rtol, atol):
+    return rtol if isinstance(rtol, Tol) else Tol(rtol, atol)
+
+
+def compare_step(g, st, envs, ts, rtol, atol=None, check_aux=True):
+    """Compare env e of `st` (after one step from golden state ts[e]) against golden state ts[e]+1.
+    Flags, done, game_over and step counters are compared exactly."""
+    tol = _as_tol(rtol, atol)
     z = g.z
     t1 = np.asarray(ts) + 1
     t0 = np.asarray(ts)
@@ -110,46 +127,99 @@ def compare_step(g, st, envs, ts, rtol, atol, check_aux=True, obs_rtol=None, obs
     assert np.array_equal(st.done[envs][:, :n], z["dones"][t0][:, :n]), "done mismatch"
     assert np.array_equal(st.game_over[envs].astype(bool), z["game_over"][t0]), "game_over mismatch"
     assert np.array_equal(st.step_num[envs][:, :n], z["st_step_num"][t1][:, :n]), "step_num mismatch"
-    for col in ("pv", "goal", "ht", "ego"):
-        got, want = st.arrays[col][envs][:, :n], z["st_" + col][t1][:, :n]
-        if col == "ht":
-            worst = max(worst, assert_close("ht.heading", got[..., 0], want[..., 0], rtol, atol, angle=True))
-            worst = max(worst, assert_close("ht.rest", got[..., 1:], want[..., 1:], rtol, atol))
-        elif col == "ego":
-            worst = max(worst, assert_close("ego.heading_ego", got[..., 1], want[..., 1], rtol, atol, angle=True))
-            worst = max(worst, assert_close("ego.dist", got[..., 0], want[..., 0], rtol, atol))
-            worst = max(worst, assert_close("ego.ref", got[..., 2:], want[..., 2:], rtol, atol))
-        else:
-            worst = max(worst, assert_close(col, got, want, rtol, atol))
-    worst = max(worst, assert_close("reward", st.reward[envs][:, :n], z["rewards"][t0][:, :n], rtol, atol))
+    G = lambda col: st.arrays[col][envs][:, :n]  # noqa: E731
+    W = lambda col: z["st_" + col][t1][:, :n]  # noqa: E731
+    worst = max(worst, assert_close("pos", G("pv")[..., :2], W("pv")[..., :2], *tol.pos))
+    worst = max(worst, assert_close("vel", G("pv")[..., 2:], W("pv")[..., 2:], *tol.vel))
+    worst = max(worst, assert_close("goal", G("goal"), W("goal"), *tol.pos))
+    worst = max(worst, assert_close("heading", G("ht")[..., 0], W("ht")[..., 0], *tol.ang, angle=True))
+    worst = max(worst, assert_close("time", G("ht")[..., 1:3], W("ht")[..., 1:3], *tol.pos))
+    worst = max(worst, assert_close("turning_dir", G("ht")[..., 3], W("ht")[..., 3], *tol.ang))
+    worst = max(worst, assert_close("dist_to_goal", G("ego")[..., 0], W("ego")[..., 0], *tol.pos))
+    worst = max(worst, assert_close("heading_ego", G("ego")[..., 1], W("ego")[..., 1], *tol.ang, angle=True))
+    worst = max(worst, assert_close("ref_prll", G("ego")[..., 2:], W("ego")[..., 2:], *tol.ang))
+    worst = max(worst, assert_close("reward", st.reward[envs][:, :n], z["rewards"][t0][:, :n], *tol.pos))
     live = (z["st_flags"][t0][:, :n] & abi.CAV_FLAG_DONE) == 0
     ga = st.actions[envs][:, :n].astype(np.float64)
     wa = z["actions"][t0][:, :n].astype(np.float64)
-    worst = max(worst, assert_close("actions.speed", np.where(live, ga[..., 0], 0), np.where(live, wa[..., 0], 0),
-                                    max(rtol, 2e-7), max(atol, 1e-7)))
+    f32 = (2e-7, 1e-7)
+    tv = (max(tol.vel[0], f32[0]), max(tol.vel[1], f32[1]))
+    ta = (max(tol.ang[0], f32[0]), max(tol.ang[1], f32[1]))
+    worst = max(worst, assert_close("actions.speed", np.where(live, ga[..., 0], 0), np.where(live, wa[..., 0], 0), *tv))
     worst = max(worst, assert_close("actions.dheading", np.where(live, ga[..., 1], 0), np.where(live, wa[..., 1], 0),
-                                    max(rtol, 2e-7), max(atol, 1e-7), angle=True))
-    ortol = rtol if obs_rtol is None else obs_rtol
-    oatol = atol if obs_atol is None else obs_atol
-    worst = max(worst, compare_obs(g, st.obs[envs], z["obs"][t1], ortol, oatol))
+                                    *ta, angle=True))
+    worst = max(worst, compare_obs(g, st.obs[envs], z["obs"][t1], tol))
     if check_aux and "aux0" in st.arrays:
-        for col in AUX_COLS:
-            worst = max(worst, assert_close(col, st.arrays[col][envs][:, :n], z["st_" + col][t1][:, :n], rtol, atol))
+        worst = max(worst, assert_close("aux.speed", G("aux0")[..., 0], W("aux0")[..., 0], *tv))
+        worst = max(worst, assert_close("aux.dheading", G("aux0")[..., 1], W("aux0")[..., 1], *ta, angle=True))
+        worst = max(worst, assert_close("aux.vel_ego", G("aux0")[..., 2:], W("aux0")[..., 2:], *tv))
+        worst = max(worst, assert_close("past_actions.speed", G("past_actions")[..., 0::2], W("past_actions")[..., 0::2], *tv))
+        worst = max(worst, assert_close("past_actions.dh", G("past_actions")[..., 1::2], W("past_actions")[..., 1::2], *ta))
+        worst = max(worst, assert_close("past_vel", G("past_vel"), W("past_vel"), *tv))
     return worst
 
 
-def compare_obs(g, got, want, rtol, atol):
-    """Packed observation compare; heading_ego_frame compared as an angle."""
+def compare_obs(g, got, want, rtol, atol=None):
+    """Packed observation compare.  Row layout of other_agents_states: [p_prll, p_orth, v_prll, v_orth, r, r+r,
+    dist] -> position / velocity tolerances per column; heading_ego_frame as an angle; laserscan beams must be
+    equal (they are multiples of the range resolution) except for `laser_frac` of them."""
+    tol = _as_tol(rtol, atol)
     cfg = g.py_config()
-    from gym_collision_avoidance_b200.envs.config import obs_layout
+    from gym_collision_avoidance_b200.envs.config import obs_layout, state_size
     off, total = obs_layout(cfg)
     got = np.asarray(got, np.float64)
     want = np.asarray(want, np.float64)
     worst = 0.0
-    mask = np.ones(total, bool)
-    if "heading_ego_frame" in off:
-        o = off["heading_ego_frame"]
-        worst = max(worst, assert_close("obs.heading_ego", got[..., o], want[..., o], rtol, atol, angle=True))
-        mask[o] = False
-    worst = max(worst, assert_close("obs", got[..., mask], want[..., mask], rtol, atol))
+    for s_, o in off.items():
+        ln = state_size(cfg, s_)
+        a, b = got[..., o:o + ln], want[..., o:o + ln]
+        if s_ == "heading_ego_frame":
+            worst = max(worst, assert_close("obs.heading_ego", a, b, *tol.ang, angle=True))
+        elif s_ in ("other_agents_states", "other_agent_states"):
+            a7, b7 = a.reshape(a.shape[:-1] + (-1, 7)), b.reshape(b.shape[:-1] + (-1, 7))
+            worst = max(worst, assert_close("obs.rows.pos", a7[..., [0, 1, 4, 5, 6]], b7[..., [0, 1, 4, 5, 6]], *tol.pos))
+            worst = max(worst, assert_close("obs.rows.vel", a7[..., [2, 3]], b7[..., [2, 3]], *tol.vel))
+        elif s_ == "laserscan":
+            bad = np.abs(a - b) > 1e-6
+            frac = bad.mean() if bad.size else 0.0
+            if frac > tol.laser_frac:
+                idx = np.argwhere(bad)[0]
+                raise AssertionError("obs.laserscan: %d/%d beams differ (%.4f > %.4f allowed); first at %s got %s "
+                                     "want %s" % (bad.sum(), bad.size, frac, tol.laser_frac, idx.tolist(),
+                                                  a[tuple(idx)], b[tuple(idx)]))
+        else:
+            worst = max(worst, assert_close("obs." + s_, a, b, *tol.pos))
+    return worst
+
+
+def compare_states(got, want, n, rtol, atol, cols=None):
+    """Full HostState vs HostState compare (same config): flags / counters exact, floats within tolerance."""
+    from gym_collision_avoidance_b200 import abi as _abi
+    cols = cols or tuple(k for k in want.arrays if k not in ("stats", "episode", "kinds", "num_active"))
+    worst = 0.0
+    for k in cols:
+        if k not in want.arrays:
+            continue
+        a, b = got.arrays[k], want.arrays[k]
+        if k in ("game_over",):
+            assert np.array_equal(a, b), "game_over mismatch"
+            continue
+        a, b = a[:, :n], b[:, :n]
+        if k == "flags":
+            if not np.array_equal(a & 0xff, b & 0xff):
+                bad = np.argwhere((a & 0xff) != (b & 0xff))[:5]
+                raise AssertionError("flags mismatch at %s: got %s want %s" % (bad.tolist(), a[tuple(bad[0])],
+                                                                                b[tuple(bad[0])]))
+        elif a.dtype.kind in "iu":
+            assert np.array_equal(a, b), "%s mismatch" % k
+        elif k == "actions":  # both sides keep the last live action for done agents
+            worst = max(worst, assert_close(k, a, b, max(rtol, 2e-7), max(atol, 1e-7)))
+        elif k == "ht":
+            worst = max(worst, assert_close("ht.heading", a[..., 0], b[..., 0], rtol, atol, angle=True))
+            worst = max(worst, assert_close("ht.rest", a[..., 1:], b[..., 1:], rtol, atol))
+        elif k == "ego":
+            worst = max(worst, assert_close("ego.heading", a[..., 1], b[..., 1], rtol, atol, angle=True))
+            worst = max(worst, assert_close("ego.rest", a[..., [0, 2, 3]], b[..., [0, 2, 3]], rtol, atol))
+        else:
+            worst = max(worst, assert_close(k, a, b, rtol, atol))
     return worst
