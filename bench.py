@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- agent-steps/sec of the vectorized collision-avoidance step on B200 (contract benchmark).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--envs E] [--agents A] [--policy RVO|noncoop] [--precision f64|f32] [--laser] [--history T]
+
+A "step" is one pass of the hot path over one batch: every agent of every environment selects an action (RVO/ORCA
+LP by default), moves, the pairwise collision / reward / sorted-neighbour observation / done pass runs, finished
+environments are reset from the device-resident scenario bank and observed (auto-reset).  Default workload:
+16384 envs x 10 agents, RVOPolicy, random-start / random-goal scenarios -- BASELINE.json configs[1]'s shape
+(10 agents, random goals, RVOPolicy) at the env count north_star's single-GPU target is quoted on (16384; pass
+--envs 4096 for configs[1] verbatim).  --gpus N (under torchrun) shards environments: every rank steps its own
+E environments (weak scaling), no data-path collective; one NCCL all-gather of the episode statistics at the end.
+
+Timing: W untimed warm-up steps; K timed steps, each bracketed by CUDA events on the launching stream, with a
+256 MiB memset + a 256 MiB read pass between steps to flush the 126 MB L2 (outside the event brackets); value =
+agent-steps / sum of event times, max over ranks; a barrier + synchronize brackets the whole timed loop.
+`e2e` is the same workload through VecCollisionAvoidanceEnv.step_host: pinned-host actions in, pinned-host
+observations / rewards / done flags out, every step (wall clock, includes the copies).
+`roofline` times the dominant fused pairwise+obs kernel alone (CUDA events around its launches, L2 flushed).
+`cpu_baseline` / `--impl reference`: the C restatement of the reference's step (oracle/, kind "port"; the Python
+reference cannot travel to the GPU box) on all host threads, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=16384, help="environments PER GPU")
+    ap.add_argument("--agents", type=int, default=10)
+    ap.add_argument("--policy", default="RVO", choices=["RVO", "noncoop"])
+    ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--laser", action="store_true", help="add LaserScanSensor 512 beams x 3 (BASELINE configs[3])")
+    ap.add_argument("--history", type=int, default=256, help="trajectory rows kept per agent (0 = off)")
+    ap.add_argument("--cpu-steps", type=int, default=0, help="cpu_baseline sample steps (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(a):
+    from gym_collision_avoidance_b200.envs.config import make_config
+    states = None
+    if a.laser:
+        states = ["is_learning", "num_other_agents", "dist_to_goal", "heading_ego_frame", "pref_speed", "radius",
+                  "other_agents_states", "laserscan"]
+    return make_config(a.agents, evaluate=True, use_static_map=a.laser, states_in_obs=states)
+
+
+def workload_name(a):
+    return "%d envs/GPU x %d agents, %sPolicy, UnicycleDynamics, random start/goal bank%s, sorted-neighbour obs, " \
+           "auto-reset, DT=0.1" % (a.envs, a.agents, "RVO" if a.policy == "RVO" else "NonCooperative",
+                                   " + LaserScanSensor 512x3" if a.laser else "")
+
+
+def scenario_bank(a, seed=1234):
+    from gym_collision_avoidance_b200.envs.scenarios import random_scenario_bank
+    return random_scenario_bank(1024, a.agents, seed=seed)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_baseline_run(a, steps, envs=None, threads=0, budget_s=15.0):
+    """Oracle (C port of the reference step) on the host cores; returns (agent_steps_per_s, cores, sample)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import cav_oracle
+    from gym_collision_avoidance_b200.envs.config import to_cav_config
+    from gym_collision_avoidance_b200.envs.vec_env import kinds_array
+    from gym_collision_avoidance_b200.state import HostBank, HostState
+    cores = len(os.sched_getaffinity(0))
+    E = envs or max(1024, 256 * cores)
+    if a.laser:
+        E = max(16, 2 * cores)
+    cfg = workload_config(a)
+    rows = scenario_bank(a)
+    c = to_cav_config(cfg, E, a.agents, precision=a.precision, history_len=a.history)
+    hs = HostState(c)
+    bank = HostBank(rows, kinds=kinds_array(rows.shape[0], a.agents, a.policy))
+    orc = cav_oracle.Oracle(c, threads=threads)
+    orc.reset(hs, bank)
+    for _ in range(3):  # warm-up (thread pool start, first touch)
+        orc.step(hs)
+        orc.reset(hs, bank, env_mask=hs.game_over.copy(), accumulate_stats=True)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        orc.step(hs)
+        orc.reset(hs, bank, env_mask=hs.game_over.copy(), accumulate_stats=True)
+    per = (time.perf_counter() - t0) / 3
+    if budget_s:  # bound the sample to about budget_s seconds of wall time
+        steps = int(max(3, min(steps, budget_s / max(per, 1e-6))))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        orc.step(hs)
+        orc.reset(hs, bank, env_mask=hs.game_over.copy(), accumulate_stats=True)
+    dt = time.perf_counter() - t0
+    used = cav_oracle.lib().cavo_get_max_threads() if threads == 0 else threads
+    return E * a.agents * steps / dt, used, "%d envs x %d agents x %d steps (C port of the reference step, OpenMP over " \
+        "envs, 1 ORCA solve per agent; the Python reference itself measured ~3e3 agent-steps/s/core, BASELINE.md)" % (
+            E, a.agents, steps), dt / steps
+
+
+def auto_cpu_steps(a):
+    if a.cpu_steps:
+        return a.cpu_steps
+    return 20 if a.laser else 2000
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active," \
+            "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+        except Exception:
+            pass
+    return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+
+
+def pairwise_obs_bytes(c):
+    """Algorithmic bytes per agent-step of the fused pairwise+obs kernel (state read
+    3 x real4 + flags, write obs + reward + done + flags), with `real` = 4 or 8 bytes."""
+    rb = 8 if c.precision == 1 else 4
+    K = c.max_num_other_agents_observed
+    read = 3 * 4 * rb + 4
+    write = rb * (6 + 7 * K) + rb + 1 + 4
+    return read + write
+
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from gym_collision_avoidance_b200.envs.vec_env import VecCollisionAvoidanceEnv
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    cfg = workload_config(a)
+    env = VecCollisionAvoidanceEnv(a.envs, cfg, a.agents, device=dev, precision=a.precision,
+                                   scenario_bank=scenario_bank(a, seed=1234 + rank), policies=a.policy,
+                                   history_len=a.history, use_cuda_graph=not a.no_graph)
+    env.reset()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush_rd = torch.empty(64 << 20, dtype=torch.float32, device=dev)  # 256 MiB
+
+    def l2_flush():
+        """Write a 256 MiB buffer (> 126 MB L2), then stream another 256 MiB through L2 with reads so the timed
+        kernels start from an L2 that holds neither their data nor a backlog of dirty flush lines."""
+        flush.zero_()
+        flush_rd.sum()
+    for _ in range(max(a.warmup, 3)):
+        env.step()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t_wall0 = time.perf_counter()
+    for s in range(a.steps):
+        l2_flush()  # outside the timed bracket
+        ev[s][0].record()
+        env.step()
+        ev[s][1].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if rank == 0 else None
+    dev_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
+    tmax = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dev_ms = float(tmax.item())
+    launches = env.launches_per_step * a.steps
+
+    # ---- roofline of the dominant kernel (fused pairwise+obs), timed alone ----
+    cav = env.cav
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(50)]
+    pm = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(50)]
+    for s in range(50):
+        l2_flush()
+        pm[s][0].record()
+        cav.k_policy()
+        cav.k_dynamics()
+        pm[s][1].record()
+        l2_flush()
+        kev[s][0].record()
+        cav.k_pairwise_obs()
+        kev[s][1].record()
+        cav.reset(env.bank, env_mask=env.state.game_over, accumulate_stats=True)
+    torch.cuda.synchronize()
+    k_ms = float(np.mean([e0.elapsed_time(e1) for e0, e1 in kev]))
+    pm_ms = float(np.mean([e0.elapsed_time(e1) for e0, e1 in pm]))
+    peak, peak_src = measured_peak()
+    bpa = pairwise_obs_bytes(env.c)
+    achieved = bpa * a.envs * a.agents / (k_ms * 1e-3) / 1e9
+
+    # ---- e2e through the public host-buffer API ----
+    h_act = np.zeros((a.envs, a.agents, 2), np.float32)
+    for _ in range(3):
+        env.step_host(h_act)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e2e_steps = max(10, min(a.steps, 50))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        env.step_host(h_act)
+    torch.cuda.synchronize()
+    e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_val = world * a.envs * a.agents * e2e_steps / float(e2e_t.item())
+
+    totals, per_rank = env.gather_episode_stats()  # the only collective (NCCL all-gather), not on the step path
+    out = None
+    if rank == 0:
+        value = world * a.envs * a.agents * a.steps / (dev_ms * 1e-3)
+        out = {
+            "metric": "agent-steps/sec", "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": a.steps,
+            "warmup": max(a.warmup, 3), "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": a.precision, "data": "synthetic",
+            "config": {"workload": workload_name(a), "envs_per_gpu": a.envs, "agents": a.agents, "policy": a.policy,
+                       "state_precision": a.precision, "orca_precision": "f32", "history_rows": a.history,
+                       "parallelism": "envs sharded x%d, no per-step collective" % world,
+                       "l2": "flushed between timed steps (256 MiB memset + 256 MiB read pass, outside the CUDA-event brackets)",
+                       "cuda_graph": not a.no_graph},
+            "wall_ms_per_step_incl_flush": t_wall / a.steps * 1e3,
+            "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": "agent-steps/s", "h2d_bytes_per_step": env.h2d_bytes_per_step,
+                    "d2h_bytes_per_step": env.d2h_bytes_per_step, "steps": e2e_steps},
+            "gpu_launches": launches,
+            "roofline": {"kernel": "k_pairwise_obs (fused pairwise collision+reward+sorted-neighbour obs+done)",
+                         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "bytes_per_agent_step": bpa,
+                         "kernel_ms": k_ms, "policy_move_kernel_ms": pm_ms},
+            "episode_stats": totals,
+        }
+        if not a.no_cpu_baseline:
+            v, cores, sample, _ = cpu_baseline_run(a, auto_cpu_steps(a))
+            out["cpu_baseline"] = {"value": v, "unit": "agent-steps/s", "cores": cores, "kind": "port",
+                                   "sample": sample}
+    env.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if out is not None:
+        print(json.dumps(out))
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(3, a.steps)
+    # warm-up is inside cpu_baseline_run (3 steps); each "step" is a bounded sample of the workload
+    # (max(1024, 256 x cores) envs instead of --envs), the run is capped at ~30 s of wall time
+    v, cores, sample, sec_per_step = cpu_baseline_run(a, steps, budget_s=30.0)
+    steps = int(round(float(sample.split(" x ")[2].split(" ")[0])))
+    out = {
+        "impl": "reference", "metric": "agent-steps/sec", "value": v, "unit": "agent-steps/s",
+        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": 3,
+        "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": a.precision, "data": "synthetic",
+        "config": {"workload": workload_name(a), "agents": a.agents, "policy": a.policy,
+                   "state_precision": a.precision},
+        "cpu_baseline": {"value": v, "unit": "agent-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

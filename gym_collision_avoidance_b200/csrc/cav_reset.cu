@@ -131,7 +131,6 @@ __global__ void __launch_bounds__(256) k_reset(ResetPtrs b, ResetParams rp, cons
             b.flags[gi] = 0u;
             b.step_num[gi] = 0;
             b.done[gi] = 0;
-            reinterpret_cast<T *>(b.reward)[gi] = (T)0;
             reinterpret_cast<float2 *>(b.actions)[gi] = make_float2(0.f, 0.f);
             const R4<T> z{(T)0, (T)0, (T)0, (T)0};
             if (b.aux0) st4(reinterpret_cast<R4<T> *>(b.aux0) + gi, z);

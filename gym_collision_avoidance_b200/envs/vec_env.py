@@ -1,0 +1,219 @@
+"""Vectorized multi-agent collision-avoidance environment on one B200.
+
+``VecCollisionAvoidanceEnv`` is the batched counterpart of the reference's ``DummyVecEnv`` over
+``CollisionAvoidanceEnv`` (reference ``envs/vec_env.py:86-159``: a serial Python loop over env instances with
+auto-reset on done, ``step_wait`` :120-128) with the observation already packed like
+``MultiagentDictToMultiagentArrayWrapper`` (``envs/wrappers.py:149-173``): ``[num_envs, num_agents, obs_len]`` in
+``Config.STATES_IN_OBS`` order.  One ``step`` is one CUDA-graph launch of the library's kernels
+(policy+move, pairwise+obs, [laserscan], masked reset of finished envs, their first observation); nothing on the
+step path runs in Python or on the CPU.
+"""
+import numpy as np
+import torch
+
+from .. import abi
+from ..device import Cavoid, DeviceBank
+from . import config as _config
+from .scenarios import random_scenario_bank
+
+POLICY_IDS = {"RVO": abi.CAV_POLICY_RVO, "noncoop": abi.CAV_POLICY_NONCOOP, "static": abi.CAV_POLICY_STATIC,
+              "external": abi.CAV_POLICY_EXTERNAL, "learning": abi.CAV_POLICY_LEARNING}
+DYNAMICS_IDS = {"unicycle": abi.CAV_DYN_UNICYCLE, "unicycle_max_turn_rate": abi.CAV_DYN_UNICYCLE_MAX_TURN_RATE,
+                "external": abi.CAV_DYN_EXTERNAL}
+
+
+def kinds_array(num_scenarios, num_agents, policies="RVO", dynamics="unicycle"):
+    """uint32 [S, N] kinds column from policy / dynamics names (one name, or one per agent slot)."""
+    pol = [policies] * num_agents if isinstance(policies, str) else list(policies)
+    dyn = [dynamics] * num_agents if isinstance(dynamics, str) else list(dynamics)
+    if len(pol) != num_agents or len(dyn) != num_agents:
+        raise ValueError("need one policy / dynamics name per agent slot")
+    for p in pol:
+        if p not in POLICY_IDS:
+            raise abi.CavoidError("policy %r has no device implementation (no CPU fallback)" % (p,))
+    row = np.array([abi.make_kind(POLICY_IDS[p], DYNAMICS_IDS[d]) for p, d in zip(pol, dyn)], np.uint32)
+    return np.tile(row[None], (num_scenarios, 1))
+
+
+class VecCollisionAvoidanceEnv(object):
+    """``num_envs`` independent environments of ``num_agents`` agent slots on one GPU.
+
+    Args mirror the reference where it has the notion: ``config`` is a reference-style ``Config`` object (ours or
+    the reference's own); ``policies`` / ``dynamics`` use the keys of the reference's ``policy_dict`` /
+    ``dynamics_dict`` (``test_cases.py:68-96``); ``scenario_bank`` holds "cadrl test case" rows
+    ``[px,py,gx,gy,pref_speed,radius(,heading)]`` (``test_cases.py:508``), env ``e`` playing scenario
+    ``(e + k*num_envs) mod S`` in its ``k``-th episode.
+    """
+
+    def __init__(self, num_envs, config=None, num_agents=None, device="cuda:0", precision="f64", scenario_bank=None,
+                 bank_kinds=None, bank_num_active=None, policies="RVO", dynamics="unicycle", auto_reset=True,
+                 use_cuda_graph=True, history_len=0, track_aux=False, seed=0, num_scenarios=None):
+        if config is None:
+            config = _config.make_config(num_agents or 10, evaluate=True)
+        self.config = config
+        self.num_envs = int(num_envs)
+        self.num_agents = int(num_agents if num_agents is not None else config.MAX_NUM_AGENTS_IN_ENVIRONMENT)
+        self.device = torch.device(device)
+        self.auto_reset = bool(auto_reset)
+        self.c = _config.to_cav_config(config, self.num_envs, self.num_agents, precision=precision,
+                                       history_len=history_len, track_aux=track_aux)
+        self.obs_offsets, self.obs_len = _config.obs_layout(config)
+        if scenario_bank is None:
+            S = num_scenarios or max(256, min(4096, self.num_envs))
+            scenario_bank = random_scenario_bank(S, self.num_agents, seed=seed)
+        scenario_bank = np.asarray(scenario_bank, dtype=np.float64)
+        S = scenario_bank.shape[0]
+        if bank_kinds is None:
+            bank_kinds = kinds_array(S, self.num_agents, policies, dynamics)
+        torch.cuda.set_device(self.device)
+        self.cav = Cavoid(self.c, self.device)
+        self.bank = DeviceBank(scenario_bank, kinds=bank_kinds, num_active=bank_num_active, device=self.device)
+        st = self.cav.state
+        self.state = st
+        self.ext_actions = torch.zeros((self.num_envs, self.num_agents, 2), dtype=torch.float32, device=self.device)
+        self.agent_dones = torch.zeros_like(st.done)  # which_agents_done of the step (kept across auto-reset)
+        # pinned host mirrors for the host-buffer API
+        self._h_actions = torch.zeros((self.num_envs, self.num_agents, 2), dtype=torch.float32).pin_memory()
+        # the host API hands observations / rewards out as float32, the dtype the reference's observation space
+        # declares (Config.STATE_INFO_DICT[...]['dtype'] = np.float32, config.py:93-170); device tensors keep `real`
+        self._d_obs32 = st.obs if st.obs.dtype == torch.float32 else torch.zeros_like(st.obs, dtype=torch.float32)
+        self._d_rew32 = (st.reward if st.reward.dtype == torch.float32
+                         else torch.zeros_like(st.reward, dtype=torch.float32))
+        self._h_obs = torch.zeros(tuple(st.obs.shape), dtype=torch.float32).pin_memory()
+        self._h_reward = torch.zeros(tuple(st.reward.shape), dtype=torch.float32).pin_memory()
+        self._h_game_over = torch.zeros(tuple(st.game_over.shape), dtype=torch.uint8).pin_memory()
+        self._h_agent_dones = torch.zeros(tuple(st.done.shape), dtype=torch.uint8).pin_memory()
+        self._graph = None
+        self._warm = False
+        self._use_graph = bool(use_cuda_graph)
+        self._stream = torch.cuda.Stream(device=self.device)
+        self.launches_per_step = 0
+        self.steps = 0
+
+    # ------------------------------------------------------------------------------------------------------
+    @property
+    def observation(self):
+        return self.state.obs
+
+    def reset(self):
+        """Reset every environment (reference ``reset`` -> ``_get_obs``); returns ``(obs, {})``."""
+        st = self.state
+        st.episode.zero_()
+        st.stats.zero_()
+        st.game_over.zero_()
+        self.cav.reset(self.bank)
+        self.agent_dones.zero_()
+        return st.obs, {}
+
+    def _enqueue_step(self):
+        """The per-step kernel sequence (captured once into a CUDA graph)."""
+        before = self.cav.launches
+        self.cav.step(self.ext_actions)
+        self.agent_dones.copy_(self.state.done)
+        if self.auto_reset:
+            # DummyVecEnv.step_wait (vec_env.py:124-125): finished envs are reset and return their first obs
+            self.cav.reset(self.bank, env_mask=self.state.game_over, accumulate_stats=True)
+        self.launches_per_step = self.cav.launches - before
+
+    def _launch(self):
+        if not self._use_graph:
+            self._enqueue_step()
+            return
+        if self._graph is None:
+            if not self._warm:
+                # the first step runs eagerly (lazy CUDA module loading must not happen during capture) ...
+                self._enqueue_step()
+                self._warm = True
+                return
+            # ... the second one is captured (capture records, it does not execute) and replayed from then on
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=self._stream):
+                self._enqueue_step()
+            self._graph = g
+        self._graph.replay()
+
+    def step(self, actions=None):
+        """One step for every environment.  ``actions``: ``[E, N, 2]`` float32 (device tensor, host tensor or
+        NumPy) holding ``[speed, delta_heading]`` (external policies) or the ``[0,1]^2`` learning action
+        (``LearningPolicy.py:30-32``) for the agents whose policy is external; ignored for the others.
+
+        Returns ``(obs, rewards, game_over, info)``, all device tensors owned by the env (overwritten by the next
+        step): obs ``[E,N,obs_len]``, rewards ``[E,N]``, game_over ``[E]`` uint8 (envs that finished this step and
+        whose obs is already their reset obs), info ``{"which_agents_done": [E,N] uint8}``.
+        """
+        if actions is not None:
+            if isinstance(actions, np.ndarray):
+                actions = torch.from_numpy(np.ascontiguousarray(actions, dtype=np.float32))
+            self.ext_actions.copy_(actions.reshape(self.ext_actions.shape), non_blocking=True)
+        self._launch()
+        self.steps += 1
+        st = self.state
+        return st.obs, st.reward, st.game_over, {"which_agents_done": self.agent_dones}
+
+    def step_host(self, actions=None):
+        """Host-buffer API: pinned-host actions in, pinned-host ``(obs, rewards, game_over, which_agents_done)``
+        out (float32 obs / rewards; host<->device copies on the current stream, then one synchronize)."""
+        if actions is not None:
+            self._h_actions.copy_(torch.as_tensor(actions, dtype=torch.float32).reshape(self._h_actions.shape))
+            self.ext_actions.copy_(self._h_actions, non_blocking=True)
+        self._launch()
+        self.steps += 1
+        st = self.state
+        if self._d_obs32 is not st.obs:
+            self._d_obs32.copy_(st.obs)
+            self._d_rew32.copy_(st.reward)
+        self._h_obs.copy_(self._d_obs32, non_blocking=True)
+        self._h_reward.copy_(self._d_rew32, non_blocking=True)
+        self._h_game_over.copy_(st.game_over, non_blocking=True)
+        self._h_agent_dones.copy_(self.agent_dones, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return self._h_obs, self._h_reward, self._h_game_over, self._h_agent_dones
+
+    @property
+    def h2d_bytes_per_step(self):
+        return self._h_actions.numel() * 4
+
+    @property
+    def d2h_bytes_per_step(self):
+        return (self._h_obs.numel() * self._h_obs.element_size() + self._h_reward.numel() * self._h_reward.element_size()
+                + self._h_game_over.numel() + self._h_agent_dones.numel())
+
+    # ------------------------------------------------------------------------------------------------------
+    def episode_stats(self):
+        """Per-rank end-of-episode aggregates accumulated on device (metric definitions: reference
+        ``experiments/src/env_utils.py:54-87``)."""
+        return self.cav.stats()
+
+    def gather_episode_stats(self):
+        """All-gather the per-rank statistics vectors (NCCL over NVLink when torch.distributed is initialised
+        with the nccl backend; gloo on CPU tensors in tests) and return (total dict, per-rank array).  This is the
+        ONLY collective of the framework and it is not on the per-step path."""
+        return gather_stats(self.cav.stats(), self.device)
+
+    def obs_slice(self, state_name):
+        o = self.obs_offsets[state_name]
+        return slice(o, o + _config.state_size(self.config, state_name))
+
+    def close(self):
+        self.cav.close()
+
+
+def stats_vector(stats):
+    return np.array([float(stats[n]) for n in abi.STAT_NAMES], dtype=np.float64)
+
+
+def gather_stats(stats, device=None):
+    """All-gather of the (tiny) per-rank episode-statistics vector; sums are the job totals."""
+    import torch.distributed as dist
+    v = stats_vector(stats)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return dict(zip(abi.STAT_NAMES, v.tolist())), v[None]
+    backend = dist.get_backend()
+    dev = torch.device(device) if (backend == "nccl" and device is not None) else torch.device("cpu")
+    t = torch.from_numpy(v).to(dev)
+    out = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t)
+    per_rank = torch.stack(out).cpu().numpy()
+    tot = per_rank.sum(axis=0)
+    return dict(zip(abi.STAT_NAMES, tot.tolist())), per_rank

@@ -538,7 +538,6 @@ static void SFX(reset_env)(const cav_config_t *cfg, const cav_buffers_t *b, cons
             b->flags[g] = 0;
             b->step_num[g] = 0;
             b->done[g] = 0;
-            ((REAL *)b->reward)[g] = 0;
             b->actions[2 * g] = b->actions[2 * g + 1] = 0;
             memset((REAL *)b->obs + g * cfg->obs_len, 0, sizeof(REAL) * (size_t)cfg->obs_len);
             continue;
@@ -564,7 +563,6 @@ static void SFX(reset_env)(const cav_config_t *cfg, const cav_buffers_t *b, cons
         b->flags[g] = 0;
         b->step_num[g] = 0;
         b->done[g] = 0;
-        ((REAL *)b->reward)[g] = 0;
         b->actions[2 * g] = b->actions[2 * g + 1] = 0;
         if (b->aux0) memset((SFX(r4) *)b->aux0 + g, 0, sizeof(SFX(r4)));
         if (b->past_actions) memset((SFX(r4) *)b->past_actions + g, 0, sizeof(SFX(r4)));

@@ -6,9 +6,10 @@ Tolerances (BASELINE.json north_star: 1e-5 relative, done / collision flags bit-
     north_star tolerance is claimed for.
   * CAV_F64 vs oracle f64 and CAV_F32 vs oracle f32 on the same injected state: flags EXACT; floats 1e-12 / 2e-6.
   * CAV_F32 (float4 columns) vs golden: flags EXACT on these fixtures; positions / distances / times 2e-5 relative;
-    angles 5e-5 rad; velocity-like values (velocities, commanded speed) 5e-4 absolute: the reference derives the
-    commanded speed as (float32 new position - position) / dt, so a float32-rounded position carries
-    ulp(pos)/dt ~ 1e-5..1e-4 m/s of noise through the ORCA solve; laser beams may differ where a
+    velocity-like values (velocities, commanded speed) 5e-4 absolute and angles 1e-3 rad: the reference derives the
+    commanded speed / heading from (float32 new position - position) / dt, so a float32-rounded position carries
+    ulp(pos)/dt ~ 1e-5..1e-4 m/s of noise through the ORCA solve, and the heading of a nearly
+    stopped agent is atan2 of that noisy displacement; laser beams may differ where a
     float32-rounded position moves a sample across a 0.1 m cell border (<= 0.5 % of beams).
 """
 import numpy as np
@@ -49,7 +50,7 @@ def test_step_teacher_forced_f32_vs_reference_golden(name):
     st = _inject_all(g, c)
     ext = np.ascontiguousarray(g.z["ext_actions"][:g.T], dtype=np.float32)
     out = GpuRunner(c).step(st, ext)
-    tol = common.Tol(2e-5, 2e-5, vel=(0.0, 5e-4), ang=(0.0, 5e-5), laser_frac=5e-3)
+    tol = common.Tol(2e-5, 2e-5, vel=(0.0, 5e-4), ang=(0.0, 1e-3), laser_frac=5e-3)
     common.compare_step(g, out, np.arange(g.T), np.arange(g.T), tol)
 
 

@@ -1,0 +1,194 @@
+"""-m gpu: CUDA path vs oracle on seeded synthetic banks across agent counts (every group width G / slots-per-lane
+SL the kernels instantiate), ragged environments, and size-independent properties at BASELINE.json's full sizes."""
+import numpy as np
+import pytest
+import torch
+
+import common
+from cav_oracle import Oracle
+from gym_collision_avoidance_b200 import abi
+from gym_collision_avoidance_b200.envs.config import make_config, to_cav_config
+from gym_collision_avoidance_b200.envs.scenarios import random_scenario_bank
+from gym_collision_avoidance_b200.envs.vec_env import kinds_array
+from gym_collision_avoidance_b200.state import HostBank, HostState
+
+pytestmark = pytest.mark.gpu
+
+
+def _bank(S, N, seed, policies="RVO", dense=False, num_active=None):
+    side = None
+    if dense:
+        side = 2.0 + 0.35 * N ** 0.5
+    rows = random_scenario_bank(S, N, seed=seed, side_length=side)
+    return HostBank(rows, kinds=kinds_array(S, N, policies), num_active=num_active)
+
+
+def _run_both(c, bank, steps, ext=None):
+    from gpu_common import GpuRunner, to_dev
+    hs = HostState(c)
+    orc = Oracle(c)
+    orc.reset(hs, bank)
+    r = GpuRunner(c)
+    r.cav.reset(r.bank(bank))
+    got = r.download()
+    common.compare_states(got, hs, c.num_agents, 1e-12, 1e-12)
+    mism = 0
+    for s in range(steps):
+        # teacher-forced: both sides step from the oracle's state
+        r.upload(hs)
+        orc.step(hs, ext)
+        r.cav.step(to_dev(ext))
+        got = r.download()
+        common.compare_states(got, hs, c.num_agents, 1e-9, 1e-9)
+    return mism
+
+
+@pytest.mark.parametrize("N", [2, 3, 4, 5, 8, 9, 10, 16, 17, 20, 32, 33, 34, 48, 64])
+def test_f64_vs_oracle_across_agent_counts(N):
+    """Covers G = 1, 2, 4, 8, 16, 32 and SL = 2; dense banks so collisions, LP3 fallbacks and done agents occur."""
+    E = 96 if N <= 20 else 24
+    c = to_cav_config(make_config(N, evaluate=True), E, N, precision="f64", track_aux=True)
+    bank = _bank(E, N, seed=100 + N, dense=True)
+    _run_both(c, bank, steps=12 if N <= 20 else 6)
+
+
+@pytest.mark.parametrize("N", [10, 20])
+def test_f32_vs_oracle_f32(N):
+    from gpu_common import GpuRunner
+    E = 128
+    c = to_cav_config(make_config(N, evaluate=True), E, N, precision="f32", track_aux=True)
+    bank = _bank(E, N, seed=7 + N, dense=True)
+    hs = HostState(c)
+    orc = Oracle(c)
+    orc.reset(hs, bank)
+    r = GpuRunner(c)
+    for s in range(10):
+        r.upload(hs)
+        orc.step(hs)
+        r.cav.step()
+        got = r.download()
+        common.compare_states(got, hs, N, 3e-6, 3e-6)
+
+
+def test_ragged_envs_and_mixed_policies():
+    """Environments with fewer agents than slots (num_active), mixed policies incl. external/learning actions."""
+    from gpu_common import GpuRunner, to_dev
+    N, E = 8, 64
+    cfg = make_config(N, evaluate=False)
+    c = to_cav_config(cfg, E, N, precision="f64", track_aux=True)
+    rng = np.random.RandomState(5)
+    na = rng.randint(2, N + 1, size=E).astype(np.int32)
+    pols = ["learning", "RVO", "noncoop", "static", "external", "RVO", "noncoop", "RVO"]
+    bank = _bank(E, N, seed=9, policies=pols, dense=True, num_active=na)
+    hs = HostState(c)
+    orc = Oracle(c)
+    orc.reset(hs, bank)
+    r = GpuRunner(c)
+    r.cav.reset(r.bank(bank))
+    common.compare_states(r.download(), hs, N, 1e-12, 1e-12)
+    assert np.array_equal(r.download().num_active, na)
+    for s in range(15):
+        ext = rng.uniform(0.1, 0.9, size=(E, N, 2)).astype(np.float32)
+        r.upload(hs)
+        orc.step(hs, ext)
+        r.cav.step(to_dev(ext))
+        common.compare_states(r.download(), hs, N, 1e-9, 1e-9)
+
+
+def test_masked_reset_and_episode_stats_match_oracle():
+    from gpu_common import GpuRunner, to_dev
+    N, E = 6, 256
+    c = to_cav_config(make_config(N, evaluate=True), E, N, precision="f64")
+    bank = _bank(64, N, seed=21, policies="noncoop", dense=True)
+    hs = HostState(c)
+    orc = Oracle(c)
+    orc.reset(hs, bank)
+    r = GpuRunner(c)
+    db = r.bank(bank)
+    r.cav.reset(db)
+    for s in range(60):
+        orc.step(hs)
+        mask = hs.game_over.copy()
+        orc.reset(hs, bank, env_mask=mask, accumulate_stats=True)
+        r.cav.step()
+        r.cav.reset(db, env_mask=r.cav.state.game_over, accumulate_stats=True)
+    got = r.download()
+    assert np.array_equal(got.episode, hs.episode)
+    assert int(hs.stats[abi.CAV_STAT_EPISODES]) > 50
+    for k in range(9):
+        assert int(got.stats[k]) == int(hs.stats[k]), (abi.STAT_NAMES[k], got.stats[k], hs.stats[k])
+    for k in (9, 10):
+        a, b = got.stats[k:k + 1].view(np.float64)[0], hs.stats[k:k + 1].view(np.float64)[0]
+        assert abs(a - b) <= 1e-6 * max(1.0, abs(b))
+    # free-running for 60 steps from identical resets: flags identical, floats tight (float64 state)
+    common.compare_states(got, hs, N, 1e-6, 1e-6, cols=("pv", "ht", "flags", "step_num", "obs"))
+
+
+@pytest.mark.parametrize("E,N,policy,prec", [(32768, 10, "noncoop", "f32"), (16384, 10, "RVO", "f64")])
+def test_full_size_properties(E, N, policy, prec):
+    """BASELINE configs[1]/[2] sizes: size-independent properties of one step.
+    (1) determinism, (2) env-permutation invariance, (3) kinematics: pos' = pos + vel'*dt for agents that moved,
+    (4) done agents do not move, (5) neighbour rows sorted by (round(dist,2), p_orth) then zero rows,
+    (6) collision flag <=> some neighbour gap <= 0, (7) game_over <=> all agents done."""
+    from gym_collision_avoidance_b200.device import Cavoid, DeviceBank
+    cfg = make_config(N, evaluate=True)
+    c = to_cav_config(cfg, E, N, precision=prec)
+    rows = random_scenario_bank(512, N, seed=77)
+    kinds = kinds_array(512, N, policy)
+    cav = Cavoid(c, "cuda:0")
+    bank = DeviceBank(rows, kinds=kinds, device="cuda:0")
+    cav.reset(bank)
+    for _ in range(25):
+        cav.step()
+    torch.cuda.synchronize()
+    before = {k: v.clone() for k, v in cav.state.t.items()}
+    cav.step()
+    torch.cuda.synchronize()
+    after = {k: v.clone() for k, v in cav.state.t.items()}
+    # (1) determinism
+    for k, v in before.items():
+        cav.state.t[k].copy_(v)
+    cav.step()
+    torch.cuda.synchronize()
+    for k in ("pv", "ht", "ego", "flags", "obs", "reward", "done", "game_over", "actions"):
+        assert torch.equal(cav.state.t[k], after[k]), k
+    # (2) permutation of environments commutes with the step
+    perm = torch.randperm(E, device="cuda:0")
+    for k, v in before.items():
+        if v.shape[:1] == (E,):
+            cav.state.t[k].copy_(v[perm])
+    cav.step()
+    torch.cuda.synchronize()
+    for k in ("pv", "ht", "flags", "obs", "reward", "game_over"):
+        assert torch.equal(cav.state.t[k], after[k][perm]), k
+    # (3)(4) kinematics
+    dt = c.dt
+    pv0, pv1 = before["pv"].double(), after["pv"].double()
+    was_done = (before["flags"] & abi.CAV_FLAG_DONE) != 0
+    moved = ~was_done
+    err = (pv1[..., :2] - (pv0[..., :2] + pv1[..., 2:] * dt)).abs().max(dim=-1).values
+    tol = 1e-12 if prec == "f64" else 2e-6
+    assert float(err[moved].max()) <= tol * 20
+    assert torch.equal(pv1[..., :2][was_done], pv0[..., :2][was_done])
+    assert float(pv1[..., 2:][was_done].abs().max()) == 0.0
+    # (5) sortedness of the neighbour rows
+    K = N - 1
+    obs = after["obs"].double()
+    rows7 = obs[..., 6:6 + 7 * K].reshape(E, N, K, 7)
+    nobs = obs[..., 1].long()
+    assert int(nobs.min()) == K and int(nobs.max()) == K
+    key = torch.round(rows7[..., 6] * 100.0)
+    d = key[..., 1:] - key[..., :-1]
+    assert bool((d >= 0).all())
+    tie = d == 0
+    assert bool((rows7[..., 1][..., 1:][tie] >= rows7[..., 1][..., :-1][tie]).all())
+    # (6) collisions: COLLIDED_AGENT bit <=> min gap <= 0 (gap = dist_2_other of the closest row, unrounded min)
+    mind = after["min_dist"].double()
+    collided = (after["flags"] & abi.CAV_FLAG_COLLIDED_AGENT) != 0
+    assert torch.equal(collided, mind <= 0)
+    assert float((rows7[..., 6].min(dim=-1).values - mind).abs().max()) <= (1e-12 if prec == "f64" else 1e-5)
+    # (7) game over
+    done = (after["flags"] & abi.CAV_FLAG_DONE) != 0
+    assert torch.equal(after["game_over"].bool(), done.all(dim=1))
+    assert torch.equal(after["done"].bool(), done)
+    cav.close()

@@ -1,0 +1,98 @@
+"""-m gpu: the public vectorized API (CUDA-graph step with auto-reset, host-buffer step) and C-ABI error paths."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+import common
+from cav_oracle import Oracle
+from gym_collision_avoidance_b200 import abi
+from gym_collision_avoidance_b200.envs.config import make_config, to_cav_config
+from gym_collision_avoidance_b200.envs.scenarios import random_scenario_bank
+from gym_collision_avoidance_b200.envs.vec_env import VecCollisionAvoidanceEnv, kinds_array
+from gym_collision_avoidance_b200.state import HostBank, HostState
+
+pytestmark = pytest.mark.gpu
+
+
+def test_vec_env_graph_equals_eager_and_oracle():
+    N, E = 10, 512
+    rows = random_scenario_bank(128, N, seed=3)
+    cfg = make_config(N, evaluate=True)
+    envs = [VecCollisionAvoidanceEnv(E, cfg, N, precision="f64", scenario_bank=rows, policies="RVO",
+                                     use_cuda_graph=g, history_len=64) for g in (True, False)]
+    c = envs[0].c
+    hs = HostState(c)
+    orc = Oracle(c)
+    bank = HostBank(rows, kinds=kinds_array(128, N, "RVO"))
+    orc.reset(hs, bank)
+    for e in envs:
+        obs, info = e.reset()
+        assert obs.shape == (E, N, 69) and info == {}
+    for s in range(40):
+        outs = [e.step() for e in envs]
+        orc.step(hs)
+        go = hs.game_over.copy()
+        rew = hs.reward.copy()
+        orc.reset(hs, bank, env_mask=go, accumulate_stats=True)
+        torch.cuda.synchronize()
+        for k in range(4):
+            a = outs[0][k] if k < 3 else outs[0][3]["which_agents_done"]
+            b = outs[1][k] if k < 3 else outs[1][3]["which_agents_done"]
+            assert torch.equal(a, b), (s, k)
+        assert np.array_equal(outs[0][2].cpu().numpy(), go)
+        common.assert_close("reward", outs[0][1].cpu().numpy(), rew, 1e-6, 1e-6)
+    got = envs[0].state.to_host()
+    common.compare_states(got, hs, N, 1e-6, 1e-6, cols=("pv", "ht", "flags", "step_num", "obs", "episode"))
+    st = envs[0].episode_stats()
+    assert st["episodes"] == int(hs.stats[abi.CAV_STAT_EPISODES])
+    tot, per_rank = envs[0].gather_episode_stats()
+    assert tot["episodes"] == st["episodes"] and per_rank.shape == (1, len(abi.STAT_NAMES))
+    for e in envs:
+        e.close()
+
+
+def test_step_host_roundtrip_external_actions():
+    N, E = 4, 64
+    cfg = make_config(N, evaluate=False)
+    rows = random_scenario_bank(32, N, seed=5)
+    env = VecCollisionAvoidanceEnv(E, cfg, N, precision="f32", scenario_bank=rows, auto_reset=False,
+                                   policies=["external", "noncoop", "RVO", "learning"])
+    env.reset()
+    act = np.zeros((E, N, 2), np.float32)
+    act[:, 0] = [0.7, 0.1]
+    act[:, 3] = [0.5, 0.5]
+    p0 = env.state.pv.clone()
+    obs, rew, go, adone = env.step_host(act)
+    assert obs.is_pinned() and obs.shape == (E, N, env.obs_len)
+    assert env.h2d_bytes_per_step == E * N * 2 * 4
+    assert env.d2h_bytes_per_step == obs.numel() * 4 + E * N * 4 + E + E * N
+    assert obs.dtype == torch.float32
+    a = env.state.actions.cpu().numpy()
+    assert np.allclose(a[:, 0], [0.7, 0.1])
+    pref = env.state.goal[:, 3, 3].cpu().numpy()
+    assert np.allclose(a[:, 3, 0], 0.5 * pref, rtol=1e-6) and np.allclose(a[:, 3, 1], 0.0, atol=1e-6)
+    moved = (env.state.pv[:, 0, :2] - p0[:, 0, :2]).norm(dim=-1).cpu().numpy()
+    assert np.allclose(moved, 0.7 * cfg.DT, rtol=1e-5)
+    assert np.allclose(obs.numpy(), env.state.obs.cpu().numpy())
+    env.close()
+
+
+def test_abi_error_paths_on_device():
+    L = abi.load_library()
+    c = to_cav_config(make_config(4), 8, 4)
+    h = ctypes.c_void_p()
+    assert L.cav_create(ctypes.byref(c), ctypes.byref(h)) == 0
+    assert L.cav_step(h, None, 0.0, None) == -4  # CAV_ERR_NOT_BOUND
+    assert b"cav_bind" in L.cav_last_error(h)
+    b = abi.CavBuffers()
+    assert L.cav_bind(h, ctypes.byref(b)) == -2  # CAV_ERR_NULL_POINTER
+    t = torch.zeros(1024, dtype=torch.float64, device="cuda:0")
+    for name in abi.BUFFER_FIELDS:
+        setattr(b, name, t.data_ptr())
+    b.pv = t.data_ptr() + 8
+    assert L.cav_bind(h, ctypes.byref(b)) == -3  # CAV_ERR_MISALIGNED
+    assert b"pv" in L.cav_last_error(h)
+    assert L.cav_k_laserscan(h, None) in (-4, -1)
+    assert L.cav_destroy(h) == 0
