@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -24,6 +25,7 @@ struct cav_handle_s {
     LaserParams lp;
     ResetParams rp;
     bool has_laser;
+    bool use_tpa;  // one-thread-per-agent kernels (small N) instead of the sub-warp-group kernels
     int launches;
     char err[512];
 };
@@ -214,6 +216,16 @@ int cav_create(const cav_config_t *cfg, cav_handle_t *out) {
     h->rp.max_time_ratio = cfg->max_time_ratio;
     fill_params<float>(*cfg, h->pf);
     fill_params<double>(*cfg, h->pd);
+    {
+        // mapping: thread-per-agent up to CAV_TPA_MAX_N agents (default 24, measured crossover),
+        // sub-warp groups with warp-shuffle bitonic sorts above.  CAV_TPA_MAX_N=0 forces the group kernels.
+        int tpa_max = 24;
+        if (const char *ev = getenv("CAV_TPA_MAX_N")) tpa_max = atoi(ev);
+        if (tpa_max > 25) tpa_max = 25;  // the sorted-neighbour list is packed 5 bits x 24 in two registers
+        h->use_tpa = cfg->num_agents <= tpa_max &&
+                     tpa_smem_bytes(cfg->num_agents, cfg->precision == CAV_F64, h->plan,
+                                    cfg->max_num_other_agents_observed) <= 200 * 1024;
+    }
     cudaError_t ce = cudaGetDevice(&h->device);
     if (ce == cudaSuccess) ce = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device);
     if (ce != cudaSuccess) {
@@ -271,6 +283,13 @@ int cav_bind(cav_handle_t h, const cav_buffers_t *bufs) {
     } while (0)
 
 static int do_policy_move(cav_handle_t h, const float *ext, int phases, double dt, cudaStream_t st) {
+    if (h->use_tpa) {
+        if (h->cfg.precision == CAV_F64)
+            CAV_CUDA(h, "policy_move_tpa", run_policy_move_tpa<double>(h->bufs, h->pd, ext, phases, dt, h->sm_count, st));
+        else
+            CAV_CUDA(h, "policy_move_tpa", run_policy_move_tpa<float>(h->bufs, h->pf, ext, phases, dt, h->sm_count, st));
+        return CAV_OK;
+    }
     if (h->cfg.precision == CAV_F64)
         CAV_CUDA(h, "policy_move", run_policy_move<double>(h->bufs, h->pd, ext, phases, dt, h->sm_count, st));
     else
@@ -278,6 +297,15 @@ static int do_policy_move(cav_handle_t h, const float *ext, int phases, double d
     return CAV_OK;
 }
 static int do_pairwise_obs(cav_handle_t h, const uint8_t *mask, int obs_only, cudaStream_t st) {
+    if (h->use_tpa) {
+        if (h->cfg.precision == CAV_F64)
+            CAV_CUDA(h, "pairwise_obs_tpa",
+                     run_pairwise_obs_tpa<double>(h->bufs, h->pd, h->plan, mask, obs_only, h->sm_count, st));
+        else
+            CAV_CUDA(h, "pairwise_obs_tpa",
+                     run_pairwise_obs_tpa<float>(h->bufs, h->pf, h->plan, mask, obs_only, h->sm_count, st));
+        return CAV_OK;
+    }
     if (h->cfg.precision == CAV_F64)
         CAV_CUDA(h, "pairwise_obs", run_pairwise_obs<double>(h->bufs, h->pd, h->plan, mask, obs_only, h->sm_count, st));
     else

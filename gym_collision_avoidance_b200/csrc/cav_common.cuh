@@ -125,6 +125,17 @@ __device__ __forceinline__ void update_ego(const R4<T> &pv, const R4<T> &goal, T
     ego.w = pry;
 }
 
+// One trajectory row (Agent.to_vector, agent.py:275-289): 11 global + 3 ego values, written with 7 vector stores
+// (double2 for float64 rows: 112-byte rows are 16-byte aligned; float2 for float32 rows: 56-byte rows, 8-byte aligned).
+__device__ __forceinline__ void store_history_row(double *row, const double (&v)[CAV_HISTORY_ROW]) {
+#pragma unroll
+    for (int k = 0; k < CAV_HISTORY_ROW / 2; ++k) reinterpret_cast<double2 *>(row)[k] = make_double2(v[2 * k], v[2 * k + 1]);
+}
+__device__ __forceinline__ void store_history_row(float *row, const float (&v)[CAV_HISTORY_ROW]) {
+#pragma unroll
+    for (int k = 0; k < CAV_HISTORY_ROW / 2; ++k) reinterpret_cast<float2 *>(row)[k] = make_float2(v[2 * k], v[2 * k + 1]);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // sub-warp groups: G consecutive lanes (G in {1,2,4,8,16,32}) cooperate on one agent.
 // ---------------------------------------------------------------------------------------------------------

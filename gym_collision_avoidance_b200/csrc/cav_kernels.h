@@ -17,6 +17,15 @@ template <typename T>
 cudaError_t run_pairwise_obs(const cav_buffers_t &bufs, const KParams<T> &p, const ObsPlan &plan,
                              const uint8_t *env_mask, int obs_only, int sm_count, cudaStream_t st);
 
+// one-thread-per-agent variants (cav_tpa.cu), used for small N
+template <typename T>
+cudaError_t run_policy_move_tpa(const cav_buffers_t &bufs, const KParams<T> &p, const float *ext, int phases, double dt,
+                                int sm_count, cudaStream_t st);
+template <typename T>
+cudaError_t run_pairwise_obs_tpa(const cav_buffers_t &bufs, const KParams<T> &p, const ObsPlan &plan,
+                                 const uint8_t *env_mask, int obs_only, int sm_count, cudaStream_t st);
+size_t tpa_smem_bytes(int N, int precision_f64, const ObsPlan &plan, int K);
+
 struct LaserParams {
     int E, N, B, P, obs_len, obs_off;
     int rows, cols, wpr, nr;

@@ -275,20 +275,9 @@ __global__ void __launch_bounds__(512) k_policy_move(DevBuffers b, KParams<T> p,
                     const int sn = b.step_num[gi];
                     if (p.store_history && b.history && sn < p.history_len) {  // agent.py:257-260,275-289
                         T *row = reinterpret_cast<T *>(b.history) + ((size_t)gi * p.history_len + sn) * CAV_HISTORY_ROW;
-                        row[0] = ht.z;
-                        row[1] = pv.x;
-                        row[2] = pv.y;
-                        row[3] = gl.x;
-                        row[4] = gl.y;
-                        row[5] = gl.z;
-                        row[6] = gl.w;
-                        row[7] = pv.z;
-                        row[8] = pv.w;
-                        row[9] = (dyn != CAV_DYN_EXTERNAL) ? a0 : speed_out;
-                        row[10] = ht.x;
-                        row[11] = ht.z;
-                        row[12] = ego.x;
-                        row[13] = ego.y;
+                        const T v[CAV_HISTORY_ROW] = {ht.z, pv.x, pv.y, gl.x, gl.y, gl.z, gl.w, pv.z, pv.w,
+                                                      (dyn != CAV_DYN_EXTERNAL) ? a0 : speed_out, ht.x, ht.z, ego.x, ego.y};
+                        store_history_row(row, v);
                     }
                     // _check_if_at_goal, agent.py:150-153
                     const T ex = pv.x - gl.x, ey = pv.y - gl.y;

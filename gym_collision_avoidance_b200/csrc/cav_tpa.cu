@@ -1,0 +1,729 @@
+// cav_tpa.cu -- one-thread-per-agent ("TPA") variants of the two per-step kernels for small agent counts.
+//
+//   k_policy_move_tpa   reference collision_avoidance_env.py:304-327 (_take_action): RVOPolicy.py:50-122 + RVO2
+//                       Agent.cpp:287-630, NonCooperativePolicy.py:21, StaticPolicy.py:21-22, ExternalPolicy.py:14-16,
+//                       LearningPolicy.py:30-32, then Agent.take_action (agent.py:192-241)
+//   k_pairwise_obs_tpa  env.py:394-512 (collisions + rewards), OtherAgentsStatesSensor.sense
+//                       (OtherAgentsStatesSensor.py:58-144) + get_observation_dict (agent.py:323-327),
+//                       _check_which_agents_done (env.py:514-553)
+//
+// Why a second mapping: with N = 10 the sub-warp-group kernels (cav_step.cu) keep 9 of 16 lanes busy, replicate
+// every per-agent scalar 16x and pay ~10 shuffle stages per sort; ncu showed them issue-bound at ~1000 warp
+// instructions per agent pair (profiles/r01a_*).  Here a thread owns an agent and walks its N-1 neighbours out of
+// the shared-memory copy of its environment's agent block; per-thread scratch (sort keys, ORCA lines, centre
+// distances) lives in shared memory laid out [slot][thread] (conflict-free).  The packed observation is
+// transposed through a small per-warp shared-memory arena in chunks of three neighbour rows, so that global
+// stores are runs of >= 21 consecutive reals per agent instead of one real per 276-byte stride.
+// Arithmetic (expression order, -fmad=false, IEEE sqrt/div) is identical to the group kernels and the oracle.
+#include "cav_kernels.h"
+#include "cav_orca_tpa.cuh"
+
+namespace cav {
+
+enum { PH_POLICY = 1, PH_MOVE = 2 };
+
+struct TpaBuffers {
+    void *pv, *goal, *ht, *ego;
+    uint32_t *flags;
+    uint32_t *kinds;
+    int32_t *step_num;
+    const int32_t *num_active;
+    float *actions;
+    void *reward, *min_dist;
+    uint8_t *done, *game_over;
+    void *obs;
+    void *history, *aux0, *past_actions, *past_vel;
+};
+
+static inline TpaBuffers make_tpa(const cav_buffers_t &b) {
+    TpaBuffers d;
+    d.pv = b.pv;
+    d.goal = b.goal;
+    d.ht = b.ht;
+    d.ego = b.ego;
+    d.flags = b.flags;
+    d.kinds = b.kinds;
+    d.step_num = b.step_num;
+    d.num_active = b.num_active;
+    d.actions = b.actions;
+    d.reward = b.reward;
+    d.min_dist = b.min_dist;
+    d.done = b.done;
+    d.game_over = b.game_over;
+    d.obs = b.obs;
+    d.history = b.history;
+    d.aux0 = b.aux0;
+    d.past_actions = b.past_actions;
+    d.past_vel = b.past_vel;
+    return d;
+}
+
+__host__ __device__ __forceinline__ size_t a16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+// =============================================================================================================
+// kernel A (TPA): policy + move
+// =============================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(128) k_policy_move_tpa(TpaBuffers b, KParams<T> p, const float *__restrict__ ext,
+                                                           int phases, T dt, int EPB, int ntiles) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int N = p.N;
+    const int cap = EPB * N;
+    const int nt = blockDim.x;
+    unsigned char *sp = smem_raw;
+    float4 *s_f4 = reinterpret_cast<float4 *>(sp);
+    sp += a16(sizeof(float4) * cap);
+    float4 *s_lines = reinterpret_cast<float4 *>(sp);
+    sp += a16(sizeof(float4) * (size_t)(N - 1) * nt);
+    unsigned long long *s_keys = reinterpret_cast<unsigned long long *>(sp);
+    sp += a16(sizeof(unsigned long long) * (size_t)(N - 1) * nt);
+    float *s_frad = reinterpret_cast<float *>(sp);
+    sp += a16(sizeof(float) * cap);
+    int *s_n = reinterpret_cast<int *>(sp);
+
+    const int tid = threadIdx.x;
+    R4<T> *g_pv = reinterpret_cast<R4<T> *>(b.pv);
+    R4<T> *g_goal = reinterpret_cast<R4<T> *>(b.goal);
+    R4<T> *g_ht = reinterpret_cast<R4<T> *>(b.ht);
+    R4<T> *g_ego = reinterpret_cast<R4<T> *>(b.ego);
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int e0 = tile * EPB;
+        const int ne = min(EPB, p.E - e0);
+        const int count = ne * N;
+        const size_t base = (size_t)e0 * N;
+        const bool have = tid < count;
+        const size_t gi = base + tid;
+        R4<T> pv{}, gl{}, ht{};
+        uint32_t f = 0, kind = 0;
+        if (have) {
+            pv = ld4(g_pv + gi);
+            gl = ld4(g_goal + gi);
+            ht = ld4(g_ht + gi);
+            f = b.flags[gi];
+            kind = b.kinds[gi];
+            // what RVOPolicy.py:57-74 pushes into the float32 simulator
+            s_f4[tid] = make_float4((float)pv.x, (float)pv.y, (float)pv.z, (float)pv.w);
+            s_frad[tid] = (float)(p.rvo_radius_scale * gl.z);
+        }
+        if (tid < ne) s_n[tid] = b.num_active ? b.num_active[e0 + tid] : N;
+        __syncthreads();
+
+        const int el = tid / N, a = tid - el * N;
+        if (have && a < s_n[el]) {
+            const int n = s_n[el];
+            const int eb = el * N;
+            float2 act = make_float2(0.f, 0.f);
+            bool have_act = false;
+            // ---- action selection (env.py:310-323) ----
+            if ((phases & PH_POLICY) && !(f & CAV_FLAG_DONE)) {
+                const uint32_t pol = CAV_KIND_POLICY(kind);
+                T a0 = (T)0, a1 = (T)0;
+                if (pol == CAV_POLICY_RVO) {
+                    const T gx = gl.x - pv.x, gy = gl.y - pv.y;  // RVOPolicy.py:66
+                    const T nrm = M<T>::sqrt_(gx * gx + gy * gy);
+                    const T sc = gl.w / nrm;  // :67
+                    const float prefx = (float)(sc * gx), prefy = (float)(sc * gy);
+                    float nvx, nvy;
+                    orca_tpa(n, a, s_f4 + eb, s_frad + eb, prefx, prefy, (float)gl.w, p.rvo_inv_time_horizon_num,
+                             p.rvo_time_step, p.rvo_collab, p.rvo_neighbor_dist, p.rvo_max_neighbors, s_keys + tid, nt,
+                             SmemLines{s_lines + tid, nt}, nvx, nvy);
+                    // Agent::update (Agent.cpp:470-475) in float, then RVOPolicy.py:96-111 in `real`
+                    const float4 me = s_f4[tid];
+                    const float npx = me.x + nvx * p.rvo_time_step, npy = me.y + nvy * p.rvo_time_step;
+                    const T dpx = (T)npx - pv.x, dpy = (T)npy - pv.y;
+                    const T ang1 = M<T>::atan2_(dpy, dpx);
+                    const T new_heading = pymod<T>(ang1 - (T)0, two_pi<T>());
+                    T dh = wrap<T>(new_heading - ht.x);
+                    T spd = p.rvo_inv_dt * M<T>::sqrt_(dpx * dpx + dpy * dpy);
+                    if (M<T>::abs_(dh) > p.rvo_max_delta_heading) {
+                        dh = sign<T>(dh) * p.rvo_max_delta_heading;
+                        spd = (T)0;
+                    }
+                    a0 = spd;
+                    a1 = dh;
+                } else if (pol == CAV_POLICY_NONCOOP) {  // NonCooperativePolicy.py:21
+                    a0 = gl.w;
+                    a1 = -ld4(g_ego + gi).y;
+                } else if (pol == CAV_POLICY_STATIC) {  // StaticPolicy.py:21-22: goal := pos
+                    gl.x = pv.x;
+                    gl.y = pv.y;
+                    st4(g_goal + gi, gl);
+                } else if (pol == CAV_POLICY_EXTERNAL) {  // ExternalPolicy.py:14-16
+                    const float2 x = ext ? reinterpret_cast<const float2 *>(ext)[gi] : make_float2(0.f, 0.f);
+                    a0 = (T)x.x;
+                    a1 = (T)x.y;
+                } else {  // CAV_POLICY_LEARNING, LearningPolicy.py:30-32
+                    const float2 x = ext ? reinterpret_cast<const float2 *>(ext)[gi] : make_float2(0.f, 0.f);
+                    a1 = p.max_heading_change * ((T)2. * (T)x.y - (T)1.);
+                    a0 = gl.w * (T)x.x;
+                }
+                act = make_float2((float)a0, (float)a1);  // float32 store, env.py:305-307
+                have_act = true;
+                reinterpret_cast<float2 *>(b.actions)[gi] = act;
+            }
+            // ---- move (Agent.take_action, agent.py:192-241) ----
+            if (phases & PH_MOVE) {
+                if (f & (CAV_FLAG_AT_GOAL | CAV_FLAG_RAN_OUT_OF_TIME | CAV_FLAG_IN_COLLISION)) {  // agent.py:202-209
+                    if (f & CAV_FLAG_AT_GOAL) f |= CAV_FLAG_WAS_AT_GOAL_ALREADY;
+                    if (f & CAV_FLAG_IN_COLLISION) f |= CAV_FLAG_WAS_IN_COLLISION_ALREADY;
+                    pv.z = (T)0;
+                    pv.w = (T)0;
+                    st4(g_pv + gi, pv);
+                    b.flags[gi] = f;
+                    if (b.past_vel) {
+                        R4<T> *pvel = reinterpret_cast<R4<T> *>(b.past_vel) + gi;
+                        R4<T> q = ld4(pvel);
+                        q.z = q.x;
+                        q.w = q.y;
+                        q.x = (T)0;
+                        q.y = (T)0;
+                        st4(pvel, q);
+                    }
+                } else {
+                    if (!have_act) act = reinterpret_cast<const float2 *>(b.actions)[gi];
+                    const T a0 = (T)act.x;
+                    T a1 = (T)act.y;
+                    const uint32_t dyn = CAV_KIND_DYNAMICS(kind);
+                    if (b.past_actions) {  // agent.py:212-213
+                        R4<T> *pa = reinterpret_cast<R4<T> *>(b.past_actions) + gi;
+                        R4<T> q = ld4(pa);
+                        q.z = q.x;
+                        q.w = q.y;
+                        q.x = a0;
+                        q.y = a1;
+                        st4(pa, q);
+                    }
+                    T speed_out = (T)0, dhead_out = (T)0;
+                    if (b.aux0) {
+                        const R4<T> q = ld4(reinterpret_cast<R4<T> *>(b.aux0) + gi);
+                        speed_out = q.x;
+                        dhead_out = q.y;
+                    }
+                    if (dyn != CAV_DYN_EXTERNAL) {
+                        if (dyn == CAV_DYN_UNICYCLE_MAX_TURN_RATE) {  // UnicycleDynamicsMaxTurnRate.py:30-32
+                            T tr = a1 / dt;
+                            tr = tr < (T)-3.0 ? (T)-3.0 : (tr > (T)3.0 ? (T)3.0 : tr);
+                            a1 = tr * dt;
+                        }
+                        const T heading = ht.x;
+                        const T sel = wrap<T>(a1 + heading);  // UnicycleDynamics.py:28
+                        const T c = M<T>::cos_(sel), s = M<T>::sin_(sel);
+                        const T dx = a0 * c * dt, dy = a0 * s * dt;  // :30-31
+                        pv.x += dx;
+                        pv.y += dy;
+                        pv.z = a0 * c;  // :34-35
+                        pv.w = a0 * s;
+                        speed_out = a0;
+                        dhead_out = wrap<T>(sel - heading);  // :37-38
+                        ht.x = sel;
+                        if (dyn == CAV_DYN_UNICYCLE) {  // turning_dir, :42-47
+                            T td = ht.w;
+                            if (M<T>::abs_(td) < (T)1e-5) {
+                                td = (T)0.11 * sign<T>(sel);
+                            } else if (td * sel < (T)0) {
+                                T v = -td + sel;
+                                v = v < pi<T>() ? v : pi<T>();
+                                v = v > -pi<T>() ? v : -pi<T>();
+                                td = v;
+                            } else {
+                                T m = M<T>::abs_(td) - (T)0.1;
+                                m = m > (T)0 ? m : (T)0.0;
+                                td = sign<T>(td) * m;
+                            }
+                            ht.w = td;
+                        }
+                    }
+                    R4<T> ego;
+                    T vex, vey;
+                    update_ego<T>(pv, gl, ht.x, ego, vex, vey);  // agent.py:227
+                    if (b.aux0) st4(reinterpret_cast<R4<T> *>(b.aux0) + gi, R4<T>{speed_out, dhead_out, vex, vey});
+                    const int sn = b.step_num[gi];
+                    if (p.store_history && b.history && sn < p.history_len) {  // agent.py:257-260,275-289
+                        T *row = reinterpret_cast<T *>(b.history) + ((size_t)gi * p.history_len + sn) * CAV_HISTORY_ROW;
+                        const T v[CAV_HISTORY_ROW] = {ht.z, pv.x, pv.y, gl.x, gl.y, gl.z, gl.w, pv.z, pv.w,
+                                                      (dyn != CAV_DYN_EXTERNAL) ? a0 : speed_out, ht.x, ht.z, ego.x, ego.y};
+                        store_history_row(row, v);
+                    }
+                    // _check_if_at_goal, agent.py:150-153
+                    const T ex = pv.x - gl.x, ey = pv.y - gl.y;
+                    if (ex * ex + ey * ey <= p.near_goal_thr * p.near_goal_thr) f |= CAV_FLAG_AT_GOAL;
+                    else f &= ~CAV_FLAG_AT_GOAL;
+                    if (b.past_vel) {
+                        R4<T> *pvel = reinterpret_cast<R4<T> *>(b.past_vel) + gi;
+                        R4<T> q = ld4(pvel);
+                        q.z = q.x;
+                        q.w = q.y;
+                        q.x = pv.z;
+                        q.y = pv.w;
+                        st4(pvel, q);
+                    }
+                    ht.y -= dt;  // agent.py:235-239
+                    ht.z += dt;
+                    b.step_num[gi] = sn + 1;
+                    if (ht.y <= (T)0) f |= CAV_FLAG_RAN_OUT_OF_TIME;
+                    st4(g_pv + gi, pv);
+                    st4(g_ht + gi, ht);
+                    st4(g_ego + gi, ego);
+                    b.flags[gi] = f;
+                }
+            }
+        }
+        __syncthreads();  // shared memory is re-staged by the next tile
+    }
+}
+
+// =============================================================================================================
+// kernel B (TPA): pairwise collisions + rewards + sorted-neighbour observation + done
+// =============================================================================================================
+// Neighbour ordering key, one 64-bit word per neighbour:  [ kint | p_orth (order-preserving bits) | agent index ].
+//   kint = rint(dist_2_other * 100): ordering by round(dist_2_other, 2) == ordering by kint (NumPy rounds as
+//   rint(x*100)/100, OtherAgentsStatesSensor.py:103), biased and clamped into KB bits.
+//   float32 state: 26 + 32 + 6 bits -- exact.   float64 state: 24 + top 34 bits of p_orth + 6 bits; keys whose kint
+//   fields are equal are re-compared exactly (kint as a real, full p_orth, index) by a bounded bubble pass, so the
+//   final order is exactly the reference's stable two-key sort also for clamped / truncated fields.
+__device__ __forceinline__ int obs_gmap(const ObsPlan &plan, int c) {  // compact offset -> offset in the obs vector
+    if (plan.nseg == 1) return plan.goff[0] + c - plan.coff[0];
+    int g = 0;
+    for (int sgi = 0; sgi < plan.nseg; ++sgi)
+        if (c >= plan.coff[sgi]) g = plan.goff[sgi] + c - plan.coff[sgi];
+    return g;
+}
+
+// output chunk width (reals): one store instruction writes 32/CW agents x CW consecutive reals
+template <typename T>
+struct TpaChunk;
+template <>
+struct TpaChunk<float> {
+    static constexpr int CW = 32;
+};
+template <>
+struct TpaChunk<double> {
+    static constexpr int CW = 16;
+};
+
+template <typename T>
+struct KeyCodec;
+template <>
+struct KeyCodec<float> {
+    static constexpr int KB = 26;
+    static constexpr int PB = 32;
+    static __device__ __forceinline__ unsigned long long po_bits(float po) {
+        unsigned u = __float_as_uint(po);
+        u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+        return (unsigned long long)u;
+    }
+};
+template <>
+struct KeyCodec<double> {
+    static constexpr int KB = 24;
+    static constexpr int PB = 34;
+    static __device__ __forceinline__ unsigned long long po_bits(double po) {
+        unsigned long long u = (unsigned long long)__double_as_longlong(po);
+        u = (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
+        return u >> 30;
+    }
+};
+
+template <typename T>
+__device__ __forceinline__ unsigned long long make_key(T kint_d, T po, int o, bool descending_kr) {
+    constexpr int KB = KeyCodec<T>::KB, PB = KeyCodec<T>::PB;
+    const T kmax = (T)(1 << (KB - 1));
+    T kc = kint_d < -kmax ? -kmax : (kint_d > kmax - (T)1 ? kmax - (T)1 : kint_d);
+    if (!(kc == kc)) kc = kmax - (T)1;  // NaN sorts last
+    unsigned long long kb = (unsigned long long)((long long)kc + (long long)(1 << (KB - 1)));
+    if (descending_kr) kb = ((1ull << KB) - 1ull) - kb;
+    return (kb << (PB + 6)) | (KeyCodec<T>::po_bits(po) << 6) | (unsigned long long)o;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) k_pairwise_obs_tpa(TpaBuffers b, KParams<T> p, ObsPlan plan,
+                                                            const uint8_t *__restrict__ env_mask, int obs_only, int EPB,
+                                                            int ntiles, int region_bytes) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int N = p.N;
+    const int cap = EPB * N;
+    const int nt = blockDim.x;
+    const int nwarps = (nt + 31) >> 5;
+    unsigned char *sp = smem_raw;
+    R4<T> *s_pv = reinterpret_cast<R4<T> *>(sp);
+    sp += a16(sizeof(R4<T>) * cap);
+    T *s_rad = reinterpret_cast<T *>(sp);
+    sp += a16(sizeof(T) * cap);
+    T *s_dc = reinterpret_cast<T *>(sp);  // [N][nt] centre distance to agent o
+    sp += a16(sizeof(T) * (size_t)N * nt);
+    unsigned char *s_region = sp;  // [nwarps][region_bytes]: sort keys [slot][lane], later the output arena
+    sp += a16((size_t)nwarps * region_bytes);
+    uint8_t *s_done = reinterpret_cast<uint8_t *>(sp);  // [cap]
+    sp += a16((size_t)cap);
+    int *s_n = reinterpret_cast<int *>(sp);
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int wlanes = min(32, nt - (warp << 5));  // lanes that exist in this warp (the last warp may be partial)
+    const unsigned all_lanes = (wlanes == 32) ? 0xffffffffu : ((1u << wlanes) - 1u);
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(s_region + (size_t)warp * region_bytes) + lane;
+    T *arena = reinterpret_cast<T *>(s_region + (size_t)warp * region_bytes);
+    const R4<T> *g_pv = reinterpret_cast<const R4<T> *>(b.pv);
+    const R4<T> *g_goal = reinterpret_cast<const R4<T> *>(b.goal);
+    const R4<T> *g_ego = reinterpret_cast<const R4<T> *>(b.ego);
+    T *g_obs = reinterpret_cast<T *>(b.obs);
+    T *g_reward = reinterpret_cast<T *>(b.reward);
+    T *g_mind = reinterpret_cast<T *>(b.min_dist);
+    const int K = p.K;
+    const int CL = plan.compact_len;
+    const int c_oas = plan.c_state[CAV_OBS_OTHER_AGENTS_STATES];
+    const bool closest_last = (p.sorting == CAV_SORT_CLOSEST_LAST);
+    constexpr int KSHIFT = KeyCodec<T>::PB + 6;
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int e0 = tile * EPB;
+        const int ne = min(EPB, p.E - e0);
+        const int count = ne * N;
+        const size_t base = (size_t)e0 * N;
+        const bool have = tid < count;
+        const size_t gi = base + tid;
+        R4<T> pvh{}, glh{}, egh{};
+        uint32_t f = 0, kind = 0;
+        float adh = 0.f;
+        if (have) {
+            pvh = ld4(g_pv + gi);
+            glh = ld4(g_goal + gi);
+            egh = ld4(g_ego + gi);
+            f = b.flags[gi];
+            kind = b.kinds[gi];
+            adh = b.actions[2 * gi + 1];
+            s_pv[tid] = pvh;
+            s_rad[tid] = glh.z;
+        }
+        if (tid < ne) {
+            int n = b.num_active ? b.num_active[e0 + tid] : N;
+            if (env_mask && !env_mask[e0 + tid]) n = -1;  // env not selected
+            s_n[tid] = n;
+        }
+        __syncthreads();
+
+        const int el = have ? tid / N : 0, h = tid - el * N;
+        const int n = have ? s_n[el] : -1;
+        const bool active = have && h < n;
+        const int eb = el * N;
+        int nc = 0;
+        unsigned long long order0 = 0ull, order1 = 0ull;  // sorted neighbour indices, 5 bits each (12 per word)
+        const T prx = egh.z, pry = egh.w;
+        const T orx = -pry, ory = prx;  // ref_orth, agent.py:347
+        if (active) {
+            T md = M<T>::inf();
+            bool coll = false;
+#pragma unroll 1
+            for (int o = 0; o < n; ++o) {
+                if (o == h) continue;
+                const R4<T> pvo = s_pv[eb + o];
+                const T ro = s_rad[eb + o];
+                const T rx = pvo.x - pvh.x, ry = pvo.y - pvh.y;
+                const T dc = M<T>::sqrt_(rx * rx + ry * ry);  // util.l2norm == util.vec2_l2_norm
+                const T cr = glh.z + ro;                       // env.py:481
+                md = min_keep(md, dc - cr);                    // :482-487
+                coll = coll || (dc <= cr);                     // :490
+                s_dc[o * nt + tid] = dc;
+                if (dc > p.sensing_horizon) continue;  // OtherAgentsStatesSensor.py:90
+                const T d2o = dc - glh.z - ro;         // :87
+                const T po = (rx * orx + ry * ory) + (T)0;  // +0: -0.0 and +0.0 compare equal in the reference
+                const unsigned long long key = make_key<T>(M<T>::rint_(d2o * (T)100), po, o, false);
+                int i = nc;
+#pragma unroll 1
+                while (i > 0) {  // insertion, ascending
+                    const unsigned long long prev = keys[(i - 1) * 32];
+                    if (prev < key) break;
+                    keys[i * 32] = prev;
+                    --i;
+                }
+                keys[i * 32] = key;
+                ++nc;
+            }
+            // exact re-comparison inside runs of equal kint (see KeyCodec): bounded bubble passes
+#pragma unroll 1
+            for (int pass = 0; pass < nc; ++pass) {
+                bool swapped = false;
+#pragma unroll 1
+                for (int r = 0; r + 1 < nc; ++r) {
+                    const unsigned long long ka = keys[r * 32], kb = keys[(r + 1) * 32];
+                    if ((ka >> KSHIFT) != (kb >> KSHIFT)) continue;
+                    const int oa = (int)(ka & 63ull), ob = (int)(kb & 63ull);
+                    const R4<T> pa = s_pv[eb + oa], pb = s_pv[eb + ob];
+                    const T kia = M<T>::rint_((s_dc[oa * nt + tid] - glh.z - s_rad[eb + oa]) * (T)100);
+                    const T kib = M<T>::rint_((s_dc[ob * nt + tid] - glh.z - s_rad[eb + ob]) * (T)100);
+                    const T poa = (pa.x - pvh.x) * orx + (pa.y - pvh.y) * ory;
+                    const T pob = (pb.x - pvh.x) * orx + (pb.y - pvh.y) * ory;
+                    const bool b_first = (kib < kia) || (kib == kia && (pob < poa || (pob == poa && ob < oa)));
+                    if (b_first) {
+                        keys[r * 32] = kb;
+                        keys[(r + 1) * 32] = ka;
+                        swapped = true;
+                    }
+                }
+                if (!swapped) break;
+            }
+            if (nc > K) nc = K;  // :39
+            if (closest_last) {
+                // re-sort the clipped list by (-kr, po), stable (:42-44): flip the kint field, insertion again
+#pragma unroll 1
+                for (int j = 0; j < nc; ++j) {
+                    unsigned long long key = keys[j * 32];
+                    const unsigned long long kb = ((1ull << KeyCodec<T>::KB) - 1ull) - (key >> KSHIFT);
+                    key = (kb << KSHIFT) | (key & ((1ull << KSHIFT) - 1ull));
+                    int i = j;
+#pragma unroll 1
+                    while (i > 0) {
+                        const unsigned long long prev = keys[(i - 1) * 32];
+                        if (prev < key) break;
+                        keys[i * 32] = prev;
+                        --i;
+                    }
+                    keys[i * 32] = key;
+                }
+#pragma unroll 1
+                for (int pass = 0; pass < nc; ++pass) {
+                    bool swapped = false;
+#pragma unroll 1
+                    for (int r = 0; r + 1 < nc; ++r) {
+                        const unsigned long long ka = keys[r * 32], kb = keys[(r + 1) * 32];
+                        if ((ka >> KSHIFT) != (kb >> KSHIFT)) continue;
+                        const int oa = (int)(ka & 63ull), ob = (int)(kb & 63ull);
+                        const R4<T> pa = s_pv[eb + oa], pb = s_pv[eb + ob];
+                        const T kia = M<T>::rint_((s_dc[oa * nt + tid] - glh.z - s_rad[eb + oa]) * (T)100);
+                        const T kib = M<T>::rint_((s_dc[ob * nt + tid] - glh.z - s_rad[eb + ob]) * (T)100);
+                        const T poa = (pa.x - pvh.x) * orx + (pa.y - pvh.y) * ory;
+                        const T pob = (pb.x - pvh.x) * orx + (pb.y - pvh.y) * ory;
+                        // descending kr; ties keep the order of the first (closest-first) sort, i.e. (po, index)
+                        const bool b_first = (kib > kia) || (kib == kia && (pob < poa || (pob == poa && ob < oa)));
+                        if (b_first) {
+                            keys[r * 32] = kb;
+                            keys[(r + 1) * 32] = ka;
+                            swapped = true;
+                        }
+                    }
+                    if (!swapped) break;
+                }
+            }
+#pragma unroll 1
+            for (int r = 0; r < nc; ++r) {
+                const unsigned long long o = keys[r * 32] & 31ull;
+                if (r < 12) order0 |= o << (5 * r);
+                else order1 |= o << (5 * (r - 12));
+            }
+            // ---- collisions + reward (env.py:394-456) ----
+            if (!obs_only) {
+                f &= ~(uint32_t)(CAV_FLAG_COLLIDED_AGENT | CAV_FLAG_COLLIDED_WALL);
+                if (coll) f |= CAV_FLAG_COLLIDED_AGENT;
+                T r = p.reward_time_step;
+                if (f & CAV_FLAG_AT_GOAL) {
+                    if (!(f & CAV_FLAG_WAS_AT_GOAL_ALREADY)) r = p.reward_at_goal;
+                } else if (!(f & CAV_FLAG_WAS_IN_COLLISION_ALREADY)) {
+                    if (coll) {
+                        r = p.reward_coll_agent;
+                        f |= CAV_FLAG_IN_COLLISION;
+                    } else {
+                        if (md <= p.getting_close) r = (T)-0.1 - md / (T)2.0;
+                        if (M<T>::abs_((T)adh) > p.wiggly_thr) r += p.reward_wiggly;
+                    }
+                }
+                r = r < p.reward_min ? p.reward_min : (r > p.reward_max ? p.reward_max : r);  // np.clip
+                g_reward[gi] = r;
+                if (g_mind) g_mind[gi] = md;
+                // done (env.py:514-536)
+                const bool d = (f & (CAV_FLAG_AT_GOAL | CAV_FLAG_RAN_OUT_OF_TIME | CAV_FLAG_IN_COLLISION)) != 0;
+                f = d ? (f | CAV_FLAG_DONE) : (f & ~(uint32_t)CAV_FLAG_DONE);
+                b.flags[gi] = f;
+                b.done[gi] = d ? 1 : 0;
+                s_done[tid] = d ? 1 : 0;
+            }
+        }
+        // ---- packed observation, transposed through the per-warp arena (aliases the sort keys) ----
+        // Chunk c covers compact elements [CW*c, CW*(c+1)): every lane deposits its own slice in arena row `lane`
+        // (stride CW+1: conflict-free both ways), then the warp stores agent-major: CW consecutive lanes write CW
+        // consecutive reals of one agent (one 128/256-byte run per agent and chunk).
+        const unsigned vmask = __ballot_sync(0xffffffffu, active);
+        if (vmask != 0u) {  // warp-uniform
+            __syncwarp();   // every lane is done with its keys before the arena overwrites them
+            constexpr int CW = TpaChunk<T>::CW;
+            constexpr int AST = CW + 1;
+            T *gwarp = g_obs + (base + (size_t)(warp << 5)) * (size_t)p.obs_len;
+            const int nchunks = (CL + CW - 1) / CW;
+            const int sub = lane / CW, kk = lane - sub * CW;
+#pragma unroll 1
+            for (int c = 0; c < nchunks; ++c) {
+                const int c0 = c * CW;
+                const int c1 = min(CL, c0 + CW);
+                if (active) {
+                    T *my = arena + lane * AST - c0;  // my[e] for compact element e in [c0, c1)
+                    // scalar states that fall into this chunk (agent.py:323-327)
+                    int cs;
+                    cs = plan.c_state[CAV_OBS_IS_LEARNING];
+                    if (cs >= c0 && cs < c1) my[cs] = (CAV_KIND_POLICY(kind) == CAV_POLICY_LEARNING) ? (T)1 : (T)0;
+                    cs = plan.c_state[CAV_OBS_NUM_OTHER_AGENTS];
+                    if (cs >= c0 && cs < c1) my[cs] = (T)nc;
+                    cs = plan.c_state[CAV_OBS_DIST_TO_GOAL];
+                    if (cs >= c0 && cs < c1) my[cs] = egh.x;
+                    cs = plan.c_state[CAV_OBS_HEADING_EGO_FRAME];
+                    if (cs >= c0 && cs < c1) my[cs] = egh.y;
+                    cs = plan.c_state[CAV_OBS_PREF_SPEED];
+                    if (cs >= c0 && cs < c1) my[cs] = glh.w;
+                    cs = plan.c_state[CAV_OBS_RADIUS];
+                    if (cs >= c0 && cs < c1) my[cs] = glh.z;
+                    if (c_oas >= 0 && K > 0 && c1 > c_oas && c0 < c_oas + 7 * K) {
+                        const int r_lo = (c0 > c_oas) ? (c0 - c_oas) / 7 : 0;
+                        const int r_hi = min(K - 1, (c1 - 1 - c_oas) / 7);
+#pragma unroll 1
+                        for (int r = r_lo; r <= r_hi; ++r) {
+                            T row[7];
+                            if (r < nc) {
+                                const int o = (int)(((r < 12) ? (order0 >> (5 * r)) : (order1 >> (5 * (r - 12)))) & 31ull);
+                                const R4<T> pvo = s_pv[eb + o];
+                                const T ro = s_rad[eb + o];
+                                const T rx = pvo.x - pvh.x, ry = pvo.y - pvh.y;
+                                row[0] = rx * prx + ry * pry;
+                                row[1] = rx * orx + ry * ory;
+                                row[2] = pvo.z * prx + pvo.w * pry;
+                                row[3] = pvo.z * orx + pvo.w * ory;
+                                row[4] = ro;
+                                row[5] = glh.z + ro;
+                                row[6] = s_dc[o * nt + tid] - glh.z - ro;  // np.linalg.norm(..) - r - r (:125)
+                                if (r == 0 && plan.oas7_goff >= 0 && c_oas >= c0) {
+                                    // Agent.other_agent_states persists when nobody is observed: direct write
+                                    T *dst = g_obs + gi * (size_t)p.obs_len + plan.oas7_goff;
+#pragma unroll
+                                    for (int k = 0; k < 7; ++k) dst[k] = row[k];
+                                }
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < 7; ++k) row[k] = (T)0;  // zero rows (:108)
+                            }
+                            const int e0r = c_oas + 7 * r;
+#pragma unroll
+                            for (int k = 0; k < 7; ++k)
+                                if (e0r + k >= c0 && e0r + k < c1) my[e0r + k] = row[k];
+                        }
+                    }
+                }
+                __syncwarp();
+                if (c0 + kk < c1) {
+                    const int gk = obs_gmap(plan, c0 + kk);
+#pragma unroll 1
+                    for (int j = sub; j < wlanes; j += 32 / CW)
+                        if ((vmask >> j) & 1u) gwarp[j * p.obs_len + gk] = arena[j * AST + kk];
+                }
+                __syncwarp();
+            }
+        }
+        // ---- game_over (env.py:538-551) ----
+        if (!obs_only) {
+            __syncthreads();
+            if (tid < ne && s_n[tid] >= 0) {
+                const int nn = s_n[tid];
+                bool all_done = true, all_learning_done = true;
+                for (int a = 0; a < nn; ++a) {
+                    const bool d = s_done[tid * N + a] != 0;
+                    if (!d) {
+                        all_done = false;
+                        if (CAV_KIND_POLICY(b.kinds[base + (size_t)tid * N + a]) == CAV_POLICY_LEARNING)
+                            all_learning_done = false;
+                    }
+                }
+                bool go;
+                if (p.game_over_mode == CAV_GAME_OVER_ALL_DONE) go = all_done;
+                else if (p.game_over_mode == CAV_GAME_OVER_AGENT0) go = s_done[tid * N] != 0;
+                else go = all_learning_done;
+                b.game_over[e0 + tid] = go ? 1 : 0;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// =============================================================================================================
+// host-side launchers
+// =============================================================================================================
+void tpa_geometry(int N, int &EPB, int &threads) {
+    EPB = 128 / N;
+    if (EPB < 1) EPB = 1;
+    threads = ((EPB * N + 31) / 32) * 32;  // whole warps: the cooperative copy-out needs all 32 lanes to exist
+}
+
+// per-warp shared-memory region of kernel B: sort keys [N-1][32] (8 bytes each), later reused as the output arena
+// [32 lanes][CW + 1]
+template <typename T>
+int tpa_region_bytes(int N, const ObsPlan &, int) {
+    const size_t keys = (size_t)8 * (N > 1 ? N - 1 : 1) * 32;
+    const size_t arena = sizeof(T) * (size_t)32 * (TpaChunk<T>::CW + 1);
+    return (int)a16(keys > arena ? keys : arena);
+}
+
+template <typename T>
+size_t tpa_smem_policy_move(int N, int EPB, int nt) {
+    const int cap = EPB * N;
+    return a16(sizeof(float4) * cap) + a16(sizeof(float4) * (size_t)(N - 1) * nt) +
+           a16(sizeof(unsigned long long) * (size_t)(N - 1) * nt) + a16(sizeof(float) * cap) + a16(sizeof(int) * EPB) + 64;
+}
+template <typename T>
+size_t tpa_smem_pairwise_obs(int N, int EPB, int nt, int region_bytes) {
+    const int cap = EPB * N;
+    const int nwarps = (nt + 31) / 32;
+    return a16(sizeof(R4<T>) * cap) + a16(sizeof(T) * cap) + a16(sizeof(T) * (size_t)N * nt) +
+           a16((size_t)nwarps * region_bytes) + a16((size_t)cap) + a16(sizeof(int) * EPB) + 64;
+}
+
+template <typename T>
+cudaError_t run_policy_move_tpa(const cav_buffers_t &bufs, const KParams<T> &p, const float *ext, int phases, double dt,
+                                int sm_count, cudaStream_t st) {
+    int EPB, threads;
+    tpa_geometry(p.N, EPB, threads);
+    const int ntiles = (p.E + EPB - 1) / EPB;
+    const size_t smem = tpa_smem_policy_move<T>(p.N, EPB, threads);
+    auto kern = k_policy_move_tpa<T>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    const int grid = ntiles < sm_count * 16 ? ntiles : sm_count * 16;
+    kern<<<grid, threads, smem, st>>>(make_tpa(bufs), p, ext, phases, (T)dt, EPB, ntiles);
+    return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t run_pairwise_obs_tpa(const cav_buffers_t &bufs, const KParams<T> &p, const ObsPlan &plan,
+                                 const uint8_t *env_mask, int obs_only, int sm_count, cudaStream_t st) {
+    int EPB, threads;
+    tpa_geometry(p.N, EPB, threads);
+    const int ntiles = (p.E + EPB - 1) / EPB;
+    const int rb = tpa_region_bytes<T>(p.N, plan, p.K);
+    const size_t smem = tpa_smem_pairwise_obs<T>(p.N, EPB, threads, rb);
+    auto kern = k_pairwise_obs_tpa<T>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    const int grid = ntiles < sm_count * 16 ? ntiles : sm_count * 16;
+    kern<<<grid, threads, smem, st>>>(make_tpa(bufs), p, plan, env_mask, obs_only, EPB, ntiles, rb);
+    return cudaGetLastError();
+}
+
+size_t tpa_smem_bytes(int N, int precision_f64, const ObsPlan &plan, int K) {
+    int EPB, threads;
+    tpa_geometry(N, EPB, threads);
+    const size_t a = precision_f64 ? tpa_smem_policy_move<double>(N, EPB, threads) : tpa_smem_policy_move<float>(N, EPB, threads);
+    const size_t bb = precision_f64
+                          ? tpa_smem_pairwise_obs<double>(N, EPB, threads, tpa_region_bytes<double>(N, plan, K))
+                          : tpa_smem_pairwise_obs<float>(N, EPB, threads, tpa_region_bytes<float>(N, plan, K));
+    return a > bb ? a : bb;
+}
+
+template cudaError_t run_policy_move_tpa<float>(const cav_buffers_t &, const KParams<float> &, const float *, int,
+                                                double, int, cudaStream_t);
+template cudaError_t run_policy_move_tpa<double>(const cav_buffers_t &, const KParams<double> &, const float *, int,
+                                                 double, int, cudaStream_t);
+template cudaError_t run_pairwise_obs_tpa<float>(const cav_buffers_t &, const KParams<float> &, const ObsPlan &,
+                                                 const uint8_t *, int, int, cudaStream_t);
+template cudaError_t run_pairwise_obs_tpa<double>(const cav_buffers_t &, const KParams<double> &, const ObsPlan &,
+                                                  const uint8_t *, int, int, cudaStream_t);
+
+}  // namespace cav

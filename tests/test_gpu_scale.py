@@ -43,18 +43,26 @@ def _run_both(c, bank, steps, ext=None):
     return mism
 
 
-@pytest.mark.parametrize("N", [2, 3, 4, 5, 8, 9, 10, 16, 17, 20, 32, 33, 34, 48, 64])
-def test_f64_vs_oracle_across_agent_counts(N):
-    """Covers G = 1, 2, 4, 8, 16, 32 and SL = 2; dense banks so collisions, LP3 fallbacks and done agents occur."""
+@pytest.mark.parametrize("mapping", ["tpa", "group"])
+@pytest.mark.parametrize("N", [2, 3, 4, 5, 8, 9, 10, 16, 17, 20, 24, 25, 32, 33, 34, 48, 64])
+def test_f64_vs_oracle_across_agent_counts(N, mapping, monkeypatch):
+    """Both kernel families: one-thread-per-agent (N <= 24 by default; forced up to 32 here) and sub-warp groups
+    (G = 1, 2, 4, 8, 16, 32 lanes per agent, and SL = 2 neighbours per lane for N > 33).  Dense banks so that
+    collisions, LP3 fallbacks and done agents occur."""
+    if mapping == "tpa" and N > 25:
+        pytest.skip("thread-per-agent mapping is only built for N <= 25")
+    monkeypatch.setenv("CAV_TPA_MAX_N", "32" if mapping == "tpa" else "0")
     E = 96 if N <= 20 else 24
     c = to_cav_config(make_config(N, evaluate=True), E, N, precision="f64", track_aux=True)
     bank = _bank(E, N, seed=100 + N, dense=True)
     _run_both(c, bank, steps=12 if N <= 20 else 6)
 
 
+@pytest.mark.parametrize("mapping", ["tpa", "group"])
 @pytest.mark.parametrize("N", [10, 20])
-def test_f32_vs_oracle_f32(N):
+def test_f32_vs_oracle_f32(N, mapping, monkeypatch):
     from gpu_common import GpuRunner
+    monkeypatch.setenv("CAV_TPA_MAX_N", "32" if mapping == "tpa" else "0")
     E = 128
     c = to_cav_config(make_config(N, evaluate=True), E, N, precision="f32", track_aux=True)
     bank = _bank(E, N, seed=7 + N, dense=True)
@@ -70,9 +78,11 @@ def test_f32_vs_oracle_f32(N):
         common.compare_states(got, hs, N, 3e-6, 3e-6)
 
 
-def test_ragged_envs_and_mixed_policies():
+@pytest.mark.parametrize("mapping", ["tpa", "group"])
+def test_ragged_envs_and_mixed_policies(mapping, monkeypatch):
     """Environments with fewer agents than slots (num_active), mixed policies incl. external/learning actions."""
     from gpu_common import GpuRunner, to_dev
+    monkeypatch.setenv("CAV_TPA_MAX_N", "32" if mapping == "tpa" else "0")
     N, E = 8, 64
     cfg = make_config(N, evaluate=False)
     c = to_cav_config(cfg, E, N, precision="f64", track_aux=True)
