@@ -187,6 +187,15 @@ struct ObsPlan {
     int oas7_goff;               // global offset of the (7,) other_agent_states state, -1 when not observed
 };
 
+// Output chunks of the thread-per-agent pairwise+obs kernel: compact ranges [c0, c1) that never split a neighbour
+// row, each at most `cw` reals wide (host-built from the ObsPlan).
+#define CAV_MAX_CHUNKS 40
+struct ChunkPlan {
+    int n;
+    short c0[CAV_MAX_CHUNKS];
+    short c1[CAV_MAX_CHUNKS];
+};
+
 // Flat copy of the parts of cav_config_t the kernels need, already converted to `real` where it matters.
 template <typename T>
 struct KParams {

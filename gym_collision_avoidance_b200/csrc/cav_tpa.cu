@@ -339,7 +339,7 @@ __device__ __forceinline__ unsigned long long make_key(T kint_d, T po, int o, bo
 template <typename T>
 __global__ void __launch_bounds__(128) k_pairwise_obs_tpa(TpaBuffers b, KParams<T> p, ObsPlan plan,
                                                             const uint8_t *__restrict__ env_mask, int obs_only, int EPB,
-                                                            int ntiles, int region_bytes) {
+                                                            int ntiles, int region_bytes, ChunkPlan chunks) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = p.N;
     const int cap = EPB * N;
@@ -539,21 +539,21 @@ __global__ void __launch_bounds__(128) k_pairwise_obs_tpa(TpaBuffers b, KParams<
             }
         }
         // ---- packed observation, transposed through the per-warp arena (aliases the sort keys) ----
-        // Chunk c covers compact elements [CW*c, CW*(c+1)): every lane deposits its own slice in arena row `lane`
-        // (stride CW+1: conflict-free both ways), then the warp stores agent-major: CW consecutive lanes write CW
-        // consecutive reals of one agent (one 128/256-byte run per agent and chunk).
+        // Chunk c covers compact elements [c0, c1) (whole neighbour rows, at most CW reals): every lane deposits its
+        // own slice in arena row `lane` (stride CW+1: conflict-free both ways), then the warp stores agent-major:
+        // CW consecutive lanes write consecutive reals of one agent (one <= 128/256-byte run per agent and chunk).
         const unsigned vmask = __ballot_sync(0xffffffffu, active);
         if (vmask != 0u) {  // warp-uniform
             __syncwarp();   // every lane is done with its keys before the arena overwrites them
             constexpr int CW = TpaChunk<T>::CW;
             constexpr int AST = CW + 1;
+            constexpr int APL = 32 / CW;  // agents per store instruction
             T *gwarp = g_obs + (base + (size_t)(warp << 5)) * (size_t)p.obs_len;
-            const int nchunks = (CL + CW - 1) / CW;
             const int sub = lane / CW, kk = lane - sub * CW;
+            const bool all_active = (vmask == 0xffffffffu);
 #pragma unroll 1
-            for (int c = 0; c < nchunks; ++c) {
-                const int c0 = c * CW;
-                const int c1 = min(CL, c0 + CW);
+            for (int c = 0; c < chunks.n; ++c) {
+                const int c0 = chunks.c0[c], c1 = chunks.c1[c];
                 if (active) {
                     T *my = arena + lane * AST - c0;  // my[e] for compact element e in [c0, c1)
                     // scalar states that fall into this chunk (agent.py:323-327)
@@ -571,46 +571,66 @@ __global__ void __launch_bounds__(128) k_pairwise_obs_tpa(TpaBuffers b, KParams<
                     cs = plan.c_state[CAV_OBS_RADIUS];
                     if (cs >= c0 && cs < c1) my[cs] = glh.z;
                     if (c_oas >= 0 && K > 0 && c1 > c_oas && c0 < c_oas + 7 * K) {
-                        const int r_lo = (c0 > c_oas) ? (c0 - c_oas) / 7 : 0;
-                        const int r_hi = min(K - 1, (c1 - 1 - c_oas) / 7);
+                        const int r_lo = (c0 > c_oas) ? (c0 - c_oas + 6) / 7 : 0;     // first row starting in the chunk
+                        const int r_hi = min(K, (c1 - c_oas) / 7);                    // one past the last whole row
 #pragma unroll 1
-                        for (int r = r_lo; r <= r_hi; ++r) {
-                            T row[7];
+                        for (int r = r_lo; r < r_hi; ++r) {
+                            T *row = my + (c_oas + 7 * r);
                             if (r < nc) {
                                 const int o = (int)(((r < 12) ? (order0 >> (5 * r)) : (order1 >> (5 * (r - 12)))) & 31ull);
                                 const R4<T> pvo = s_pv[eb + o];
                                 const T ro = s_rad[eb + o];
                                 const T rx = pvo.x - pvh.x, ry = pvo.y - pvh.y;
-                                row[0] = rx * prx + ry * pry;
-                                row[1] = rx * orx + ry * ory;
-                                row[2] = pvo.z * prx + pvo.w * pry;
-                                row[3] = pvo.z * orx + pvo.w * ory;
+                                const T r0 = rx * prx + ry * pry, r1 = rx * orx + ry * ory;
+                                const T r2 = pvo.z * prx + pvo.w * pry, r3 = pvo.z * orx + pvo.w * ory;
+                                const T r5 = glh.z + ro;
+                                const T r6 = s_dc[o * nt + tid] - glh.z - ro;  // np.linalg.norm(..) - r - r (:125)
+                                row[0] = r0;
+                                row[1] = r1;
+                                row[2] = r2;
+                                row[3] = r3;
                                 row[4] = ro;
-                                row[5] = glh.z + ro;
-                                row[6] = s_dc[o * nt + tid] - glh.z - ro;  // np.linalg.norm(..) - r - r (:125)
-                                if (r == 0 && plan.oas7_goff >= 0 && c_oas >= c0) {
+                                row[5] = r5;
+                                row[6] = r6;
+                                if (r == 0 && plan.oas7_goff >= 0) {
                                     // Agent.other_agent_states persists when nobody is observed: direct write
                                     T *dst = g_obs + gi * (size_t)p.obs_len + plan.oas7_goff;
-#pragma unroll
-                                    for (int k = 0; k < 7; ++k) dst[k] = row[k];
+                                    dst[0] = r0;
+                                    dst[1] = r1;
+                                    dst[2] = r2;
+                                    dst[3] = r3;
+                                    dst[4] = ro;
+                                    dst[5] = r5;
+                                    dst[6] = r6;
                                 }
                             } else {
 #pragma unroll
                                 for (int k = 0; k < 7; ++k) row[k] = (T)0;  // zero rows (:108)
                             }
-                            const int e0r = c_oas + 7 * r;
-#pragma unroll
-                            for (int k = 0; k < 7; ++k)
-                                if (e0r + k >= c0 && e0r + k < c1) my[e0r + k] = row[k];
                         }
                     }
                 }
                 __syncwarp();
                 if (c0 + kk < c1) {
                     const int gk = obs_gmap(plan, c0 + kk);
+                    const T *src = arena + sub * AST + kk;
+                    T *dst = gwarp + sub * p.obs_len + gk;
+                    const int dstep = APL * p.obs_len;
+                    if (all_active) {
+#pragma unroll 4
+                        for (int j = sub; j < 32; j += APL) {
+                            *dst = *src;
+                            src += APL * AST;
+                            dst += dstep;
+                        }
+                    } else {
 #pragma unroll 1
-                    for (int j = sub; j < wlanes; j += 32 / CW)
-                        if ((vmask >> j) & 1u) gwarp[j * p.obs_len + gk] = arena[j * AST + kk];
+                        for (int j = sub; j < 32; j += APL) {
+                            if ((vmask >> j) & 1u) *dst = *src;
+                            src += APL * AST;
+                            dst += dstep;
+                        }
+                    }
                 }
                 __syncwarp();
             }
@@ -658,6 +678,30 @@ int tpa_region_bytes(int N, const ObsPlan &, int) {
     return (int)a16(keys > arena ? keys : arena);
 }
 
+// Row-aligned output chunks of at most cw reals over the compact observation vector [0, CL).
+static int build_chunks(const ObsPlan &plan, int K, int cw, ChunkPlan &cp) {
+    const int CL = plan.compact_len;
+    const int c_oas = plan.c_state[CAV_OBS_OTHER_AGENTS_STATES];
+    const int oas_end = (c_oas >= 0) ? c_oas + 7 * K : -1;
+    cp.n = 0;
+    int c = 0;
+    while (c < CL) {
+        int e = c + cw < CL ? c + cw : CL;
+        if (c_oas >= 0 && e > c_oas && e < oas_end) {
+            // do not split a row: pull the end back to the previous row boundary (rows are 7 <= cw wide)
+            const int rows = (e - c_oas) / 7;
+            const int aligned = c_oas + 7 * rows;
+            if (aligned > c) e = aligned;
+        }
+        if (cp.n >= CAV_MAX_CHUNKS) return -1;
+        cp.c0[cp.n] = (short)c;
+        cp.c1[cp.n] = (short)e;
+        cp.n++;
+        c = e;
+    }
+    return 0;
+}
+
 template <typename T>
 size_t tpa_smem_policy_move(int N, int EPB, int nt) {
     const int cap = EPB * N;
@@ -702,8 +746,10 @@ cudaError_t run_pairwise_obs_tpa(const cav_buffers_t &bufs, const KParams<T> &p,
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
+    ChunkPlan cp;
+    if (build_chunks(plan, p.K, TpaChunk<T>::CW, cp) != 0) return cudaErrorInvalidValue;
     const int grid = ntiles < sm_count * 16 ? ntiles : sm_count * 16;
-    kern<<<grid, threads, smem, st>>>(make_tpa(bufs), p, plan, env_mask, obs_only, EPB, ntiles, rb);
+    kern<<<grid, threads, smem, st>>>(make_tpa(bufs), p, plan, env_mask, obs_only, EPB, ntiles, rb, cp);
     return cudaGetLastError();
 }
 
