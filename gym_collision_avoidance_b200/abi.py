@@ -100,7 +100,8 @@ class CavScenarioBank(ctypes.Structure):
 # every symbol include/cavoid.h declares
 EXPORTED_SYMBOLS = [
     "cav_abi_version", "cav_create", "cav_real_bytes", "cav_workspace_bytes", "cav_bind", "cav_reset", "cav_step",
-    "cav_k_policy", "cav_k_dynamics", "cav_k_pairwise_obs", "cav_k_laserscan", "cav_last_launch_count",
+    "cav_k_policy", "cav_k_dynamics", "cav_k_pairwise_obs", "cav_k_laserscan", "cav_k_observe",
+    "cav_last_launch_count",
     "cav_last_error", "cav_destroy",
 ]
 
@@ -147,6 +148,8 @@ def load_library(path=None):
     L.cav_k_pairwise_obs.argtypes = [h, _vp]
     L.cav_k_laserscan.restype = ctypes.c_int
     L.cav_k_laserscan.argtypes = [h, _vp]
+    L.cav_k_observe.restype = ctypes.c_int
+    L.cav_k_observe.argtypes = [h, _vp, _vp]
     L.cav_last_launch_count.restype = ctypes.c_int
     L.cav_last_launch_count.argtypes = [h]
     L.cav_last_error.restype = ctypes.c_char_p

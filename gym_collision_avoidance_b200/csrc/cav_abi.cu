@@ -373,6 +373,15 @@ int cav_k_laserscan(cav_handle_t h, cav_stream_t stream) {
     return do_laser(h, nullptr, (cudaStream_t)stream);
 }
 
+int cav_k_observe(cav_handle_t h, const uint8_t *env_mask, cav_stream_t stream) {
+    CAV_CHECK_READY(h, "cav_k_observe");
+    h->launches = 0;
+    int rc = do_pairwise_obs(h, env_mask, 1, (cudaStream_t)stream);
+    if (rc) return rc;
+    if (h->has_laser) rc = do_laser(h, env_mask, (cudaStream_t)stream);
+    return rc;
+}
+
 int cav_last_launch_count(cav_handle_t h) { return valid(h) ? h->launches : 0; }
 
 const char *cav_last_error(cav_handle_t h) { return valid(h) ? h->err : g_err; }

@@ -154,6 +154,10 @@ class Cavoid(object):
         self._check(self.L.cav_k_laserscan(self._h, self._stream(stream)), "cav_k_laserscan")
         self.launches += self.L.cav_last_launch_count(self._h)
 
+    def k_observe(self, env_mask=None, stream=None):
+        self._check(self.L.cav_k_observe(self._h, _ptr(env_mask), self._stream(stream)), "cav_k_observe")
+        self.launches += self.L.cav_last_launch_count(self._h)
+
     def stats(self):
         raw = self.state.stats.detach().cpu().numpy().view(np.uint64)
         out = {}

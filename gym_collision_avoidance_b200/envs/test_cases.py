@@ -1,0 +1,128 @@
+"""Scenario builders returning ``list[Agent]`` with the reference's names and registries
+(reference ``envs/test_cases.py:68-96,144-175,212-253,495-590,900-911``)."""
+import os
+import pickle
+
+import numpy as np
+
+from .agent import Agent
+from .dynamics.ExternalDynamics import ExternalDynamics
+from .dynamics.UnicycleDynamics import UnicycleDynamics
+from .dynamics.UnicycleDynamicsMaxTurnRate import UnicycleDynamicsMaxTurnRate
+from .policies.ExternalPolicy import ExternalPolicy
+from .policies.LearningPolicy import LearningPolicy
+from .policies.NonCooperativePolicy import NonCooperativePolicy
+from .policies.RVOPolicy import RVOPolicy
+from .policies.StaticPolicy import StaticPolicy
+from .scenarios import _circle_case, _rand_case, _swap_case
+from .sensors.LaserScanSensor import LaserScanSensor
+from .sensors.OtherAgentsStatesSensor import OtherAgentsStatesSensor
+
+policy_dict = {"RVO": RVOPolicy, "noncoop": NonCooperativePolicy, "external": ExternalPolicy,
+               "learning": LearningPolicy, "static": StaticPolicy}
+sensor_dict = {"other_agents_states": OtherAgentsStatesSensor, "laserscan": LaserScanSensor}
+dynamics_dict = {"unicycle": UnicycleDynamics, "external": ExternalDynamics,
+                 "unicycle_max_turn_rate": UnicycleDynamicsMaxTurnRate}
+
+
+def _config():
+    from . import Config
+    return Config
+
+
+def get_testcase_two_agents(policies=("learning", "RVO")):
+    """Reference ``test_cases.py:144-175``: head-on swap (-3,-3)<->(3,3), r 0.5, pref speed 1."""
+    gx = gy = 3
+    return [Agent(-gx, -gy, gx, gy, 0.5, 1.0, 0.0, policy_dict[policies[0]], UnicycleDynamics,
+                  [OtherAgentsStatesSensor], 0),
+            Agent(gx, gy, -gx, -gy, 0.5, 1.0, np.pi, policy_dict[policies[1]], UnicycleDynamics,
+                  [OtherAgentsStatesSensor], 1)]
+
+
+def cadrl_test_case_to_agents(test_case, policies="RVO", policy_distr=None, agents_dynamics="unicycle",
+                              agents_sensors=("other_agents_states",), policy_to_ensure=None, prev_agents=None):
+    """Reference ``test_cases.py:495-590``: rows ``[px,py,gx,gy,pref_speed,radius]`` -> Agents."""
+    test_case = np.asarray(test_case)
+    n = test_case.shape[0]
+    if isinstance(policies, str):
+        plist = [policies] * n
+    elif policy_distr is None:
+        plist = list(policies)
+    else:
+        plist = list(np.random.choice(policies, n, p=policy_distr))
+        if policy_to_ensure is not None and policy_to_ensure not in plist:
+            plist[np.random.randint(n)] = policy_to_ensure
+    C = _config()
+    agents = []
+    for i, row in enumerate(test_case):
+        px, py, gx, gy, pref_speed, radius = row[:6]
+        if C.EVALUATE_MODE:
+            heading = np.arctan2(gy - py, gx - px)
+        else:
+            heading = np.random.uniform(-np.pi, np.pi)
+        if prev_agents is not None and plist[i] == prev_agents[i].policy.str:
+            prev_agents[i].reset(px=px, py=py, gx=gx, gy=gy, pref_speed=pref_speed, radius=radius, heading=heading)
+            agents.append(prev_agents[i])
+        else:
+            agents.append(Agent(px, py, gx, gy, radius, pref_speed, heading, policy_dict[plist[i]],
+                                dynamics_dict[agents_dynamics], [sensor_dict[s] for s in agents_sensors], i))
+    return agents
+
+
+def generate_rand_test_case_multi(num_agents, side_length, speed_bnds, radius_bnds):
+    """Reference ``gen_rand_testcases.py:111-142`` (15 % swap / 15 % circle / 70 % random), NumPy global RNG."""
+    rng = np.random
+    u = rng.rand()
+    if u < 0.15:
+        return _swap_case(rng, num_agents, side_length, speed_bnds, radius_bnds)
+    if u < 0.3:
+        return _circle_case(rng, num_agents, side_length, speed_bnds, radius_bnds)
+    return _rand_case(rng, num_agents, side_length, speed_bnds, radius_bnds)
+
+
+def get_testcase_random(num_agents=None, side_length=4, speed_bnds=(0.5, 2.0), radius_bnds=(0.2, 0.8),
+                        policies="learning", policy_distr=None, agents_dynamics="unicycle",
+                        agents_sensors=("other_agents_states",), policy_to_ensure=None, prev_agents=None):
+    """Reference ``test_cases.py:212-253``."""
+    C = _config()
+    if num_agents is None:
+        num_agents = np.random.randint(2, C.MAX_NUM_AGENTS_IN_ENVIRONMENT + 1)
+    if isinstance(side_length, list):
+        for comp in side_length:
+            if comp["num_agents"][0] <= num_agents < comp["num_agents"][1]:
+                side_length = np.random.uniform(comp["side_length"][0], comp["side_length"][1])
+    tc = generate_rand_test_case_multi(num_agents, float(side_length), list(speed_bnds), list(radius_bnds))
+    return cadrl_test_case_to_agents(tc, policies=policies, policy_distr=policy_distr,
+                                     agents_dynamics=agents_dynamics, agents_sensors=agents_sensors,
+                                     policy_to_ensure=policy_to_ensure, prev_agents=prev_agents)
+
+
+def gen_circle_test_case(num_agents, radius):
+    """Reference ``test_cases.py:900-911``."""
+    tc = np.zeros((num_agents, 6))
+    for i in range(num_agents):
+        tc[i, 4], tc[i, 5] = 1.0, 0.5
+        th0 = (2 * np.pi / num_agents) * i
+        th1 = th0 + np.pi
+        tc[i, 0], tc[i, 1] = radius * np.cos(th0), radius * np.sin(th0)
+        tc[i, 2], tc[i, 3] = radius * np.cos(th1), radius * np.sin(th1)
+    return tc
+
+
+def preset_testCases(num_agents, test_case_dir=None, num_test_cases=500):
+    """Loads a reference fixture file ``{N}_agents_500_cases.p`` (list of (N,6) arrays; reference
+    ``test_cases.py:593-625``).  The fixture files are the reference's data and are not bundled: pass the
+    directory that holds them (``.../gym_collision_avoidance/envs/test_cases``) or set ``CAV_TEST_CASE_DIR``."""
+    d = test_case_dir or os.environ.get("CAV_TEST_CASE_DIR")
+    if d is None:
+        raise FileNotFoundError("set CAV_TEST_CASE_DIR to the reference's envs/test_cases directory")
+    with open(os.path.join(d, "%d_agents_%d_cases.p" % (num_agents, num_test_cases)), "rb") as f:
+        return pickle.load(f, encoding="latin1")
+
+
+def full_test_suite(num_agents, test_case_index, policies="learning", agents_dynamics="unicycle", agents_sensors=(),
+                    prev_agents=None, test_case_dir=None):
+    """Reference ``test_cases.py:332-355``."""
+    tc = preset_testCases(num_agents, test_case_dir)[test_case_index]
+    return cadrl_test_case_to_agents(tc, policies=policies, agents_dynamics=agents_dynamics,
+                                     agents_sensors=agents_sensors, prev_agents=prev_agents)

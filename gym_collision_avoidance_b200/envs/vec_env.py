@@ -199,6 +199,15 @@ class VecCollisionAvoidanceEnv(object):
         self.cav.close()
 
 
+def shard_envs(total_envs, rank, world_size):
+    """Contiguous block of environments owned by `rank`: returns (first_env, num_envs).  Whole
+    environments only -- an environment's agents never straddle GPUs."""
+    base, rem = divmod(int(total_envs), int(world_size))
+    n = base + (1 if rank < rem else 0)
+    first = rank * base + min(rank, rem)
+    return first, n
+
+
 def stats_vector(stats):
     return np.array([float(stats[n]) for n in abi.STAT_NAMES], dtype=np.float64)
 

@@ -264,11 +264,14 @@ int cav_step(cav_handle_t h, const float *ext_actions, double dt, cav_stream_t s
  *   cav_k_pairwise_obs: env.py:394-512 collisions+rewards, OtherAgentsStatesSensor.sense
  *                       (OtherAgentsStatesSensor.py:58-144), get_observation_dict (agent.py:323-327),
  *                       _check_which_agents_done (env.py:514-553)
- *   cav_k_laserscan   : Map.add_agents_to_map (Map.py:46-50) + LaserScanSensor.sense (LaserScanSensor.py:49-101) */
+ *   cav_k_laserscan   : Map.add_agents_to_map (Map.py:46-50) + LaserScanSensor.sense (LaserScanSensor.py:49-101)
+ *   cav_k_observe     : env.py:555-575 _get_obs alone (sensors + packing, no rewards / flags), for the envs selected
+ *                       by env_mask (NULL = all): what reset() returns for externally injected agent states */
 int cav_k_policy(cav_handle_t h, const float *ext_actions, cav_stream_t stream);
 int cav_k_dynamics(cav_handle_t h, double dt, cav_stream_t stream);
 int cav_k_pairwise_obs(cav_handle_t h, cav_stream_t stream);
 int cav_k_laserscan(cav_handle_t h, cav_stream_t stream);
+int cav_k_observe(cav_handle_t h, const uint8_t *env_mask, cav_stream_t stream);
 
 /* Number of kernels the last cav_step / cav_reset call on this handle enqueued (for launch accounting). */
 int cav_last_launch_count(cav_handle_t h);

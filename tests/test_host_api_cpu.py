@@ -1,0 +1,95 @@
+"""CPU tests of the host-side mirror of the reference's plugin surface (no GPU): Agent initialisation arithmetic
+against the golden reset states, registries, Map bitmap packing, observation dict <-> packed array."""
+import numpy as np
+import pytest
+
+import common
+from gym_collision_avoidance_b200 import abi
+from gym_collision_avoidance_b200.envs import config as cfgmod
+from gym_collision_avoidance_b200 import envs as envs_pkg
+
+
+@pytest.fixture()
+def eval_config():
+    old = envs_pkg.Config
+    cfg = envs_pkg.set_config(cfgmod.make_config(10, evaluate=True))
+    yield cfg
+    envs_pkg.set_config(old)
+
+
+def test_agent_reset_matches_reference_golden(eval_config):
+    from gym_collision_avoidance_b200.envs import test_cases as tc
+    g = common.Golden("rvo10_c0")
+    rows = np.zeros((10, 6))
+    rows[:, 0:2] = g.z["st_pv"][0][:, 0:2]
+    rows[:, 2:4] = g.z["st_goal"][0][:, 0:2]
+    rows[:, 4] = g.z["st_goal"][0][:, 3]
+    rows[:, 5] = g.z["st_goal"][0][:, 2]
+    agents = tc.cadrl_test_case_to_agents(rows, policies="RVO")
+    for i, a in enumerate(agents):
+        assert a.policy.str == "RVO" and type(a.policy).kernel_id == abi.CAV_POLICY_RVO
+        assert not a.policy.is_external and not a.policy.is_still_learning
+        np.testing.assert_allclose(a.heading_global_frame, g.z["st_ht"][0][i, 0], rtol=0, atol=1e-15)
+        np.testing.assert_allclose(a.time_remaining_to_reach_goal, g.z["st_ht"][0][i, 1], rtol=1e-14)
+        np.testing.assert_allclose([a.dist_to_goal, a.heading_ego_frame], g.z["st_ego"][0][i, :2], rtol=1e-14, atol=1e-15)
+        np.testing.assert_allclose(a.ref_prll, g.z["st_ego"][0][i, 2:], rtol=1e-14)
+        assert a.global_state_history.shape == (int(1.2 * a.time_remaining_to_reach_goal / 0.1), 11)
+        assert (a.t, a.step_num, a.is_done, a.is_at_goal) == (0.0, 0, False, False)
+
+
+def test_registries_and_plugin_flags(eval_config):
+    from gym_collision_avoidance_b200.envs import test_cases as tc
+    assert set(tc.policy_dict) >= {"RVO", "noncoop", "static", "external", "learning"}
+    assert set(tc.sensor_dict) == {"other_agents_states", "laserscan"}
+    assert set(tc.dynamics_dict) >= {"unicycle", "external"}
+    lp = tc.policy_dict["learning"]()
+    assert lp.is_external and lp.is_still_learning and lp.str == "learning"
+
+    class A(object):
+        max_heading_change, pref_speed = np.pi / 3, 1.5
+    np.testing.assert_allclose(lp.external_action_to_action(A(), [0.5, 0.75]), [0.75, np.pi / 6])
+    ep = tc.policy_dict["external"]()
+    assert ep.is_external and not ep.is_still_learning and ep.find_next_action(None, None, 0) is None
+    a, b = tc.get_testcase_two_agents(["RVO", "noncoop"])
+    assert (a.pos_global_frame == [-3, -3]).all() and (b.goal_global_frame == [-3, -3]).all()
+    assert b.heading_global_frame == np.pi and isinstance(b.heading_global_frame, np.float64)
+    s = tc.sensor_dict["other_agents_states"]()
+    s.set_args({"max_num_other_agents_observed": 3})
+    assert s.max_num_other_agents_observed == 3 and s.name == "other_agents_states"
+    c = tc.gen_circle_test_case(8, 5.0)
+    np.testing.assert_allclose(c[:, 0:2], -c[:, 2:4], atol=1e-12)
+
+
+def test_map_bits_and_obs_packing():
+    from gym_collision_avoidance_b200.envs.Map import Map
+    from gym_collision_avoidance_b200.envs.wrappers import dict_to_packed, packed_to_dict
+    sm = np.zeros((160, 160), bool)
+    sm[3, 0] = sm[3, 31] = sm[3, 32] = sm[159, 159] = True
+    m = Map(16, 16, 0.1, static_map=sm)
+    bits = m.bits().reshape(160, 5)
+    assert bits[3, 0] == (1 | (1 << 31)) and bits[3, 1] == 1 and bits[159, 4] == (1 << 31) and bits.sum() == bits[3].sum() + bits[159, 4]
+    idx, inside = m.world_coordinates_to_map_indices([0.05, 0.05])
+    assert inside and tuple(idx) == (79, 80)
+    cfg = cfgmod.make_config(4)
+    packed = np.arange(4 * 27, dtype=np.float64).reshape(4, 27)
+    d = packed_to_dict(cfg, packed)
+    assert d[2]["other_agents_states"].shape == (3, 7) and d[1]["dist_to_goal"] == packed[1, 2]
+    np.testing.assert_array_equal(dict_to_packed(cfg, d), packed)
+
+
+def test_config_singleton_env_vars(tmp_path, monkeypatch):
+    import importlib
+    p = tmp_path / "mycfg.py"
+    p.write_text("from gym_collision_avoidance_b200.envs.config import EvaluateConfig\n"
+                 "class Mine(EvaluateConfig):\n    def __init__(self):\n        self.MAX_NUM_AGENTS_IN_ENVIRONMENT = 7\n"
+                 "        EvaluateConfig.__init__(self)\n        self.DT = 0.05\n")
+    monkeypatch.setenv("GYM_CONFIG_PATH", str(p))
+    monkeypatch.setenv("GYM_CONFIG_CLASS", "Mine")
+    mod = importlib.reload(envs_pkg)
+    try:
+        assert mod.Config.MAX_NUM_AGENTS_IN_ENVIRONMENT == 7 and mod.Config.DT == 0.05
+        assert mod.Config.MAX_NUM_OTHER_AGENTS_OBSERVED == 6 and mod.Config.EVALUATE_MODE
+    finally:
+        monkeypatch.delenv("GYM_CONFIG_PATH")
+        monkeypatch.delenv("GYM_CONFIG_CLASS")
+        importlib.reload(envs_pkg)
