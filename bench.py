@@ -90,6 +90,8 @@ def cpu_baseline_run(a, steps, envs=None, threads=0, budget_s=15.0):
     c = to_cav_config(cfg, E, a.agents, precision=a.precision, history_len=a.history)
     hs = HostState(c)
     bank = HostBank(rows, kinds=kinds_array(rows.shape[0], a.agents, a.policy))
+    if threads == 0:
+        threads = cores  # explicit: torchrun exports OMP_NUM_THREADS=1
     orc = cav_oracle.Oracle(c, threads=threads)
     orc.reset(hs, bank)
     for _ in range(3):  # warm-up (thread pool start, first touch)
@@ -197,6 +199,7 @@ def run_ours(a):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)

@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(256) k_laserscan(LaserPtrs b, LaserParams lp, 
     const R4<T> *g_goal = reinterpret_cast<const R4<T> *>(b.goal);
     const R4<T> *g_ht = reinterpret_cast<const R4<T> *>(b.ht);
     T *g_obs = reinterpret_cast<T *>(b.obs);
+    const bool has_static = b.static_map_bits != nullptr;
 
     for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
         const int e = w / chunks, chunk = w - e * chunks;
@@ -116,8 +117,42 @@ __global__ void __launch_bounds__(256) k_laserscan(LaserPtrs b, LaserParams lp, 
                 double sa, ca;
                 sincos(ang, &sa, &ca);
                 int cum = 0, kstar = -1;
+                // Which samples can hit at all?  A sample can only land in a cell painted for agent o if it lies
+                // within R_o = r_o + sqrt(2)*cell (+eps) of o's centre (the sample and the centre are each anywhere
+                // inside their cells), so with an empty static map only the samples inside the union of the ray's
+                // intersections with those inflated discs need the exact cell test; everything else is a miss.
+                int k_lo = 0, k_hi = lp.nr - 1;
+                if (!has_static) {
+                    double tmin = 1e300, tmax = -1e300;
 #pragma unroll 1
-                for (int k = 0; k < lp.nr; ++k) {
+                    for (int o = 0; o < n; ++o) {
+                        if (o == h || !s_in[o]) continue;
+                        const double ox = s_px[o] - px, oy = s_py[o] - py;
+                        const double R = sqrt(s_rr2[o]) * lp.cell + 1.4143 * lp.cell + 1e-6;
+                        const double tca = ox * ca + oy * sa;
+                        const double d2 = (ox * ox + oy * oy) - tca * tca;
+                        const double R2 = R * R;
+                        if (d2 > R2) continue;
+                        const double thc = sqrt(R2 - d2);
+                        const double t1 = tca + thc;
+                        if (t1 < 0.0) continue;
+                        const double t0 = tca - thc;
+                        tmin = fmin(tmin, t0);
+                        tmax = fmax(tmax, t1);
+                    }
+                    if (tmax < tmin) {
+                        k_lo = 1;
+                        k_hi = 0;  // the beam cannot hit anything
+                    } else {
+                        const double inv_res = 1.0 / lp.range_res;
+                        const double a = floor((tmin - lp.min_range) * inv_res) - 1.0;
+                        const double bnd = ceil((tmax - lp.min_range) * inv_res) + 1.0;
+                        k_lo = a > 0.0 ? (int)a : 0;
+                        k_hi = bnd < (double)(lp.nr - 1) ? (int)bnd : lp.nr - 1;
+                    }
+                }
+#pragma unroll 1
+                for (int k = k_lo; k <= k_hi; ++k) {
                     const double rk = lp.min_range + (double)k * lp.range_res;  // np.arange (:39)
                     const double x = px + rk * ca, y = py + rk * sa;            // :70-72
                     const double fx = cell_coord(lp.origin0, y, lp.cell, lp.inv_cell, true);
@@ -135,6 +170,8 @@ __global__ void __launch_bounds__(256) k_laserscan(LaserPtrs b, LaserParams lp, 
                     if (cum == 1) kstar = k;  // :78-82: the LAST index whose cumulative hit count is 1
                     if (cum >= 2) break;
                 }
+                // a single hit inside the window keeps cumsum == 1 up to the last range sample (:78-82)
+                if (cum == 1) kstar = lp.nr - 1;
                 const double rng = kstar >= 0 ? lp.min_range + (double)kstar * lp.range_res : lp.max_range;
                 if (cnt == 0u) {  // first measurement fills every row (:84-85)
                     for (int pp = 0; pp < lp.P; ++pp) o[(size_t)pp * lp.B + bi] = (T)rng;

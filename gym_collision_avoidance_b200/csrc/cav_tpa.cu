@@ -299,7 +299,7 @@ struct TpaChunk<float> {
 };
 template <>
 struct TpaChunk<double> {
-    static constexpr int CW = 16;
+    static constexpr int CW = 16;  // measured at 16384 x 10, f64: CW 16 -> 50 us, 8 -> 64 us, 32 -> 60 us
 };
 
 template <typename T>

@@ -202,3 +202,49 @@ def test_full_size_properties(E, N, policy, prec):
     assert torch.equal(after["game_over"].bool(), done.all(dim=1))
     assert torch.equal(after["done"].bool(), done)
     cav.close()
+
+
+LASER_STATES = ["is_learning", "num_other_agents", "dist_to_goal", "heading_ego_frame", "pref_speed", "radius",
+                "other_agents_states", "laserscan"]
+
+
+@pytest.mark.parametrize("static_map", [False, True])
+@pytest.mark.parametrize("N,prec", [(20, "f64"), (7, "f32"), (40, "f64")])
+def test_laserscan_vs_oracle_random_scenes(N, prec, static_map):
+    """LaserScanSensor raycast (empty static map: ray-disc culled march; non-empty static map: full march + static
+    bits) == oracle, beam for beam, over several steps (history roll included); agents partly off the 16 m map."""
+    from gpu_common import GpuRunner
+    E = 24
+    cfg = make_config(N, evaluate=True, use_static_map=True, states_in_obs=LASER_STATES)
+    c = to_cav_config(cfg, E, N, precision=prec)
+    rows = random_scenario_bank(E, N, seed=50 + N, side_length=7.5)
+    rows[:, :, 5] = np.random.RandomState(N).uniform(0.15, 0.9, size=(E, N))
+    bank = HostBank(rows, kinds=kinds_array(E, N, "noncoop"))
+    hs = HostState(c)
+    if static_map:
+        rng = np.random.RandomState(3)
+        sm = np.zeros((160, 160), bool)
+        for _ in range(12):
+            r0, c0 = rng.randint(0, 150, 2)
+            sm[r0:r0 + rng.randint(1, 12), c0:c0 + rng.randint(1, 12)] = True
+        from gym_collision_avoidance_b200.envs.Map import Map
+        hs.static_map_bits = Map(16, 16, 0.1, static_map=sm).bits()
+    orc = Oracle(c)
+    orc.reset(hs, bank)
+    r = GpuRunner(c)
+    if static_map:
+        r.cav.state.set_static_map(hs.static_map_bits)
+        r.cav.bind()
+    r.cav.reset(r.bank(bank))
+    got = r.download()
+    o = c.obs_offset[abi.CAV_OBS_LASERSCAN]
+    assert np.array_equal(got.obs[..., o:], hs.obs[..., o:])
+    assert (hs.obs[..., o:] < 6.0).mean() > 0.02  # the scenes do produce hits
+    for s in range(5):
+        r.upload(hs)
+        orc.step(hs)
+        r.cav.step()
+        got = r.download()
+        assert np.array_equal(got.laser_count, hs.laser_count)
+        bad = got.obs[..., o:] != hs.obs[..., o:]
+        assert bad.mean() <= (0.0 if prec == "f64" else 0.0), (s, int(bad.sum()))
