@@ -181,6 +181,15 @@ def measured_peak():
     return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
 
 
+def measured_traffic(a):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture, or None."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+        return d.get("%s_%dx%d_%s" % (a.precision, a.envs, a.agents, a.policy))
+    except Exception:
+        return None
+
+
 def pairwise_obs_bytes(c):
     """Algorithmic bytes per agent-step of the fused pairwise+obs kernel (state read
     3 x real4 + flags, write obs + reward + done + flags), with `real` = 4 or 8 bytes."""
@@ -303,7 +312,7 @@ def run_ours(a):
             "gpu_launches": launches,
             "roofline": {"kernel": "k_pairwise_obs (fused pairwise collision+reward+sorted-neighbour obs+done)",
                          "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "bytes_per_agent_step": bpa,
+                         "traffic": measured_traffic(a), "peak_source": peak_src, "bytes_per_agent_step": bpa,
                          "kernel_ms": k_ms, "policy_move_kernel_ms": pm_ms},
             "episode_stats": totals,
         }
