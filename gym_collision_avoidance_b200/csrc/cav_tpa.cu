@@ -15,6 +15,8 @@
 // transposed through a small per-warp shared-memory arena in chunks of three neighbour rows, so that global
 // stores are runs of >= 21 consecutive reals per agent instead of one real per 276-byte stride.
 // Arithmetic (expression order, -fmad=false, IEEE sqrt/div) is identical to the group kernels and the oracle.
+#include <cstdlib>
+
 #include "cav_kernels.h"
 #include "cav_orca_tpa.cuh"
 
@@ -664,7 +666,9 @@ __global__ void __launch_bounds__(128) k_pairwise_obs_tpa(TpaBuffers b, KParams<
 // host-side launchers
 // =============================================================================================================
 void tpa_geometry(int N, int &EPB, int &threads) {
-    EPB = 128 / N;
+    int target = 128;
+    if (const char *ev = getenv("CAV_TPA_THREADS")) target = atoi(ev);
+    EPB = target / N;
     if (EPB < 1) EPB = 1;
     threads = ((EPB * N + 31) / 32) * 32;  // whole warps: the cooperative copy-out needs all 32 lanes to exist
 }
