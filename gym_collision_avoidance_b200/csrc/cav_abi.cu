@@ -296,20 +296,38 @@ static int do_policy_move(cav_handle_t h, const float *ext, int phases, double d
         CAV_CUDA(h, "policy_move", run_policy_move<float>(h->bufs, h->pf, ext, phases, dt, h->sm_count, st));
     return CAV_OK;
 }
+static WallMap wall_map(cav_handle_t h) {
+    WallMap wm;
+    memset(&wm, 0, sizeof(wm));
+    const cav_config_t &c = h->cfg;
+    if (c.use_static_map && h->bufs.static_map_bits && c.map_grid_cell_size > 0.0) {
+        wm.bits = h->bufs.static_map_bits;
+        wm.cell = c.map_grid_cell_size;
+        wm.inv_cell = 1.0 / wm.cell;
+        wm.rows = (int)(c.map_x_width / wm.cell);
+        wm.cols = (int)(c.map_y_width / wm.cell);
+        wm.wpr = (wm.cols + 31) / 32;
+        wm.origin0 = (c.map_x_width / 2.) / wm.cell;
+        wm.origin1 = (c.map_y_width / 2.) / wm.cell;
+    }
+    return wm;
+}
+
 static int do_pairwise_obs(cav_handle_t h, const uint8_t *mask, int obs_only, cudaStream_t st) {
+    const WallMap wm = wall_map(h);
     if (h->use_tpa) {
         if (h->cfg.precision == CAV_F64)
             CAV_CUDA(h, "pairwise_obs_tpa",
-                     run_pairwise_obs_tpa<double>(h->bufs, h->pd, h->plan, mask, obs_only, h->sm_count, st));
+                     run_pairwise_obs_tpa<double>(h->bufs, h->pd, h->plan, wm, mask, obs_only, h->sm_count, st));
         else
             CAV_CUDA(h, "pairwise_obs_tpa",
-                     run_pairwise_obs_tpa<float>(h->bufs, h->pf, h->plan, mask, obs_only, h->sm_count, st));
+                     run_pairwise_obs_tpa<float>(h->bufs, h->pf, h->plan, wm, mask, obs_only, h->sm_count, st));
         return CAV_OK;
     }
     if (h->cfg.precision == CAV_F64)
-        CAV_CUDA(h, "pairwise_obs", run_pairwise_obs<double>(h->bufs, h->pd, h->plan, mask, obs_only, h->sm_count, st));
+        CAV_CUDA(h, "pairwise_obs", run_pairwise_obs<double>(h->bufs, h->pd, h->plan, wm, mask, obs_only, h->sm_count, st));
     else
-        CAV_CUDA(h, "pairwise_obs", run_pairwise_obs<float>(h->bufs, h->pf, h->plan, mask, obs_only, h->sm_count, st));
+        CAV_CUDA(h, "pairwise_obs", run_pairwise_obs<float>(h->bufs, h->pf, h->plan, wm, mask, obs_only, h->sm_count, st));
     return CAV_OK;
 }
 static int do_laser(cav_handle_t h, const uint8_t *mask, cudaStream_t st) {

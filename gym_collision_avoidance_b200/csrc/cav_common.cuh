@@ -176,6 +176,49 @@ __device__ __forceinline__ T max_keep(T cur, T v) {
     return (cur < v) ? v : cur;
 }
 
+// Static-map geometry for the wall-collision test (env.py:494-506, Map.py:26-32,52-56); bits == nullptr disables it.
+struct WallMap {
+    const uint32_t *bits;  // row-major bitmap of Map.static_map, rows x wpr words
+    int rows, cols, wpr;
+    double origin0, origin1, cell, inv_cell;
+};
+
+// Map.world_coordinates_to_map_indices: floor(origin -/+ v/cell); v*inv_cell replaces the division unless the result
+// is within 1e-9 of an integer, where the exact quotient decides.
+__device__ __forceinline__ double cell_coord(double origin, double v, double cell, double inv_cell, bool negate) {
+    const double a = v * inv_cell;
+    double c = negate ? (origin - a) : (origin + a);
+    if (fabs(c - rint(c)) < 1e-9 * fmax(1.0, fabs(c))) {
+        const double q = v / cell;
+        c = negate ? (origin - q) : (origin + q);
+    }
+    return floor(c);
+}
+
+// collision_with_wall[i] (env.py:494-506): the agent's centre cell is inside the map and some static cell lies under
+// its disc mask (col-gy)^2 + (row-gx)^2 < (radius/cell)^2.  Cells are visited `step` apart starting at `first`
+// (1 thread: first=0, step=1; G cooperating lanes: first=lane, step=G -> OR the results).
+__device__ __forceinline__ bool wall_hit(const WallMap &wm, double px, double py, double radius, int first, int step) {
+    const double fx = cell_coord(wm.origin0, py, wm.cell, wm.inv_cell, true);
+    const double fy = cell_coord(wm.origin1, px, wm.cell, wm.inv_cell, false);
+    if (!(fx >= 0.0 && fy >= 0.0 && fx < (double)wm.rows && fy < (double)wm.cols)) return false;
+    const int gr = (int)fx, gc = (int)fy;
+    const double rc = radius / wm.cell;
+    const double rr2 = rc * rc;
+    double rcd = sqrt(rr2);
+    if (!(rcd < (double)(wm.rows + wm.cols))) rcd = (double)(wm.rows + wm.cols);
+    const int R = (int)rcd + 1;
+    const int r0 = max(0, gr - R), r1 = min(wm.rows - 1, gr + R);
+    const int c0 = max(0, gc - R), c1 = min(wm.cols - 1, gc + R);
+    const int wbox = c1 - c0 + 1, cells = wbox * (r1 - r0 + 1);
+    for (int k = first; k < cells; k += step) {
+        const int r = r0 + k / wbox, c = c0 + k % wbox;
+        const double dc = (double)(c - gc), dr = (double)(r - gr);
+        if (dc * dc + dr * dr < rr2 && ((wm.bits[r * wm.wpr + (c >> 5)] >> (c & 31)) & 1u)) return true;
+    }
+    return false;
+}
+
 // Observation packing plan (host-built): which packed-observation segments the pairwise+obs kernel writes.
 struct ObsPlan {
     int nseg;                    // merged contiguous segments staged through shared memory

@@ -14,7 +14,7 @@ template <typename T>
 cudaError_t run_policy_move(const cav_buffers_t &bufs, const KParams<T> &p, const float *ext, int phases, double dt,
                             int sm_count, cudaStream_t st);
 template <typename T>
-cudaError_t run_pairwise_obs(const cav_buffers_t &bufs, const KParams<T> &p, const ObsPlan &plan,
+cudaError_t run_pairwise_obs(const cav_buffers_t &bufs, const KParams<T> &p, const ObsPlan &plan, const WallMap &wm,
                              const uint8_t *env_mask, int obs_only, int sm_count, cudaStream_t st);
 
 // one-thread-per-agent variants (cav_tpa.cu), used for small N
@@ -23,7 +23,8 @@ cudaError_t run_policy_move_tpa(const cav_buffers_t &bufs, const KParams<T> &p, 
                                 int sm_count, cudaStream_t st);
 template <typename T>
 cudaError_t run_pairwise_obs_tpa(const cav_buffers_t &bufs, const KParams<T> &p, const ObsPlan &plan,
-                                 const uint8_t *env_mask, int obs_only, int sm_count, cudaStream_t st);
+                                 const WallMap &wm, const uint8_t *env_mask, int obs_only, int sm_count,
+                                 cudaStream_t st);
 size_t tpa_smem_bytes(int N, int precision_f64, const ObsPlan &plan, int K);
 
 struct LaserParams {

@@ -22,18 +22,6 @@ struct LaserPtrs {
     const uint32_t *static_map_bits;
 };
 
-// Map.world_coordinates_to_map_indices (Map.py:26-32): gx = floor(origin0 - y/cell), gy = floor(origin1 + x/cell).
-// y*inv_cell replaces the division unless the result is within 1e-9 of an integer, where the exact quotient decides.
-__device__ __forceinline__ double cell_coord(double origin, double v, double cell, double inv_cell, bool negate) {
-    const double a = v * inv_cell;
-    double c = negate ? (origin - a) : (origin + a);
-    if (fabs(c - rint(c)) < 1e-9 * fmax(1.0, fabs(c))) {
-        const double q = v / cell;
-        c = negate ? (origin - q) : (origin + q);
-    }
-    return floor(c);
-}
-
 template <typename T>
 __global__ void __launch_bounds__(256) k_laserscan(LaserPtrs b, LaserParams lp, const uint8_t *__restrict__ env_mask,
                                                      int APC, int chunks, int nwork) {

@@ -335,7 +335,7 @@ struct ObsKeyOps {
 };
 
 template <typename T, int G, int SL>
-__global__ void __launch_bounds__(512) k_pairwise_obs(DevBuffers b, KParams<T> p, ObsPlan plan,
+__global__ void __launch_bounds__(512) k_pairwise_obs(DevBuffers b, KParams<T> p, ObsPlan plan, WallMap wm,
                                                         const uint8_t *__restrict__ env_mask, int obs_only, int EPB,
                                                         int GPE, int ntiles) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -443,12 +443,19 @@ __global__ void __launch_bounds__(512) k_pairwise_obs(DevBuffers b, KParams<T> p
                     const bool anycoll = gballot<G>(gm, coll) != 0u;
                     uint32_t f = s_flags[li] & ~(uint32_t)(CAV_FLAG_COLLIDED_AGENT | CAV_FLAG_COLLIDED_WALL);
                     if (anycoll) f |= CAV_FLAG_COLLIDED_AGENT;
+                    // wall collision (env.py:494-506): the group's lanes split the cells under the disc
+                    bool wall = false;
+                    if (wm.bits) wall = gballot<G>(gm, wall_hit(wm, (double)pvh.x, (double)pvh.y, (double)glh.z, glane, G)) != 0u;
+                    if (wall) f |= CAV_FLAG_COLLIDED_WALL;
                     T r = p.reward_time_step;
                     if (f & CAV_FLAG_AT_GOAL) {
                         if (!(f & CAV_FLAG_WAS_AT_GOAL_ALREADY)) r = p.reward_at_goal;
                     } else if (!(f & CAV_FLAG_WAS_IN_COLLISION_ALREADY)) {
                         if (anycoll) {
                             r = p.reward_coll_agent;
+                            f |= CAV_FLAG_IN_COLLISION;
+                        } else if (wall) {
+                            r = p.reward_coll_wall;
                             f |= CAV_FLAG_IN_COLLISION;
                         } else {
                             if (md <= p.getting_close) r = (T)-0.1 - md / (T)2.0;
@@ -619,7 +626,7 @@ static cudaError_t launch_pm(const cav_buffers_t &bufs, const KParams<T> &p, con
 }
 
 template <typename T, int G, int SL>
-static cudaError_t launch_po(const cav_buffers_t &bufs, const KParams<T> &p, const ObsPlan &plan,
+static cudaError_t launch_po(const cav_buffers_t &bufs, const KParams<T> &p, const ObsPlan &plan, const WallMap &wm,
                              const uint8_t *env_mask, int obs_only, int EPB, int GPE, int threads, int sm_count,
                              cudaStream_t st) {
     const int ntiles = (p.E + EPB - 1) / EPB;
@@ -630,7 +637,7 @@ static cudaError_t launch_po(const cav_buffers_t &bufs, const KParams<T> &p, con
         if (e != cudaSuccess) return e;
     }
     const int grid = ntiles < sm_count * 16 ? ntiles : sm_count * 16;
-    kern<<<grid, threads, smem, st>>>(make_dev(bufs), p, plan, env_mask, obs_only, EPB, GPE, ntiles);
+    kern<<<grid, threads, smem, st>>>(make_dev(bufs), p, plan, wm, env_mask, obs_only, EPB, GPE, ntiles);
     return cudaGetLastError();
 }
 
@@ -655,11 +662,11 @@ cudaError_t run_policy_move(const cav_buffers_t &bufs, const KParams<T> &p, cons
     CAV_DISPATCH_SHAPE(launch_pm, bufs, p, ext, phases, dt, EPB, GPE, threads, sm_count, st);
 }
 template <typename T>
-cudaError_t run_pairwise_obs(const cav_buffers_t &bufs, const KParams<T> &p, const ObsPlan &plan,
+cudaError_t run_pairwise_obs(const cav_buffers_t &bufs, const KParams<T> &p, const ObsPlan &plan, const WallMap &wm,
                              const uint8_t *env_mask, int obs_only, int sm_count, cudaStream_t st) {
     int G, SL, GPE, EPB, threads;
     launch_geometry(p.N, G, SL, GPE, EPB, threads);
-    CAV_DISPATCH_SHAPE(launch_po, bufs, p, plan, env_mask, obs_only, EPB, GPE, threads, sm_count, st);
+    CAV_DISPATCH_SHAPE(launch_po, bufs, p, plan, wm, env_mask, obs_only, EPB, GPE, threads, sm_count, st);
 }
 
 template cudaError_t run_policy_move<float>(const cav_buffers_t &, const KParams<float> &, const float *, int, double,
@@ -667,8 +674,8 @@ template cudaError_t run_policy_move<float>(const cav_buffers_t &, const KParams
 template cudaError_t run_policy_move<double>(const cav_buffers_t &, const KParams<double> &, const float *, int,
                                              double, int, cudaStream_t);
 template cudaError_t run_pairwise_obs<float>(const cav_buffers_t &, const KParams<float> &, const ObsPlan &,
-                                             const uint8_t *, int, int, cudaStream_t);
+                                             const WallMap &, const uint8_t *, int, int, cudaStream_t);
 template cudaError_t run_pairwise_obs<double>(const cav_buffers_t &, const KParams<double> &, const ObsPlan &,
-                                              const uint8_t *, int, int, cudaStream_t);
+                                              const WallMap &, const uint8_t *, int, int, cudaStream_t);
 
 }  // namespace cav

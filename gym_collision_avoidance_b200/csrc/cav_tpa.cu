@@ -339,7 +339,7 @@ __device__ __forceinline__ unsigned long long make_key(T kint_d, T po, int o, bo
 }
 
 template <typename T>
-__global__ void __launch_bounds__(128) k_pairwise_obs_tpa(TpaBuffers b, KParams<T> p, ObsPlan plan,
+__global__ void __launch_bounds__(128) k_pairwise_obs_tpa(TpaBuffers b, KParams<T> p, ObsPlan plan, WallMap wm,
                                                             const uint8_t *__restrict__ env_mask, int obs_only, int EPB,
                                                             int ntiles, int region_bytes, ChunkPlan chunks) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -517,12 +517,17 @@ __global__ void __launch_bounds__(128) k_pairwise_obs_tpa(TpaBuffers b, KParams<
             if (!obs_only) {
                 f &= ~(uint32_t)(CAV_FLAG_COLLIDED_AGENT | CAV_FLAG_COLLIDED_WALL);
                 if (coll) f |= CAV_FLAG_COLLIDED_AGENT;
+                const bool wall = wm.bits && wall_hit(wm, (double)pvh.x, (double)pvh.y, (double)glh.z, 0, 1);  // :494-506
+                if (wall) f |= CAV_FLAG_COLLIDED_WALL;
                 T r = p.reward_time_step;
                 if (f & CAV_FLAG_AT_GOAL) {
                     if (!(f & CAV_FLAG_WAS_AT_GOAL_ALREADY)) r = p.reward_at_goal;
                 } else if (!(f & CAV_FLAG_WAS_IN_COLLISION_ALREADY)) {
                     if (coll) {
                         r = p.reward_coll_agent;
+                        f |= CAV_FLAG_IN_COLLISION;
+                    } else if (wall) {
+                        r = p.reward_coll_wall;
                         f |= CAV_FLAG_IN_COLLISION;
                     } else {
                         if (md <= p.getting_close) r = (T)-0.1 - md / (T)2.0;
@@ -739,7 +744,8 @@ cudaError_t run_policy_move_tpa(const cav_buffers_t &bufs, const KParams<T> &p, 
 
 template <typename T>
 cudaError_t run_pairwise_obs_tpa(const cav_buffers_t &bufs, const KParams<T> &p, const ObsPlan &plan,
-                                 const uint8_t *env_mask, int obs_only, int sm_count, cudaStream_t st) {
+                                 const WallMap &wm, const uint8_t *env_mask, int obs_only, int sm_count,
+                                 cudaStream_t st) {
     int EPB, threads;
     tpa_geometry(p.N, EPB, threads);
     const int ntiles = (p.E + EPB - 1) / EPB;
@@ -753,7 +759,7 @@ cudaError_t run_pairwise_obs_tpa(const cav_buffers_t &bufs, const KParams<T> &p,
     ChunkPlan cp;
     if (build_chunks(plan, p.K, TpaChunk<T>::CW, cp) != 0) return cudaErrorInvalidValue;
     const int grid = ntiles < sm_count * 16 ? ntiles : sm_count * 16;
-    kern<<<grid, threads, smem, st>>>(make_tpa(bufs), p, plan, env_mask, obs_only, EPB, ntiles, rb, cp);
+    kern<<<grid, threads, smem, st>>>(make_tpa(bufs), p, plan, wm, env_mask, obs_only, EPB, ntiles, rb, cp);
     return cudaGetLastError();
 }
 
@@ -772,8 +778,8 @@ template cudaError_t run_policy_move_tpa<float>(const cav_buffers_t &, const KPa
 template cudaError_t run_policy_move_tpa<double>(const cav_buffers_t &, const KParams<double> &, const float *, int,
                                                  double, int, cudaStream_t);
 template cudaError_t run_pairwise_obs_tpa<float>(const cav_buffers_t &, const KParams<float> &, const ObsPlan &,
-                                                 const uint8_t *, int, int, cudaStream_t);
+                                                 const WallMap &, const uint8_t *, int, int, cudaStream_t);
 template cudaError_t run_pairwise_obs_tpa<double>(const cav_buffers_t &, const KParams<double> &, const ObsPlan &,
-                                                  const uint8_t *, int, int, cudaStream_t);
+                                                  const WallMap &, const uint8_t *, int, int, cudaStream_t);
 
 }  // namespace cav

@@ -59,7 +59,7 @@ class DeviceState(object):
             elif a.dtype == np.uint64:
                 a = a.view(np.int64)
             self.t[name].copy_(torch.from_numpy(np.ascontiguousarray(a)))
-        if hs.static_map_bits is not None:
+        if hs.static_map_bits is not None and self.static_map_bits is None:
             self.set_static_map(hs.static_map_bits)
 
     def to_host(self):

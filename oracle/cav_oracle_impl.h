@@ -335,6 +335,28 @@ static void SFX(pairwise_obs_env)(const cav_config_t *cfg, const cav_buffers_t *
                     coll[j] = 1;
                 }
             }
+        /* wall collisions, env.py:494-506: any static-map cell under the agent's disc mask (Map.py:52-56), only when
+         * the agent's centre cell is inside the map */
+        int wall[CAVO_MAX_AGENTS];
+        for (int i = 0; i < n; ++i) wall[i] = 0;
+        if (cfg->use_static_map && b->static_map_bits) {
+            const cavo_map_t m = cavo_map_dims(cfg);
+            const int wpr = (m.cols + 31) / 32;
+            for (int i = 0; i < n; ++i) {
+                int gx, gy;
+                if (!cavo_world_to_cell(&m, (double)pv[i].x, (double)pv[i].y, &gx, &gy)) continue;
+                const double rc = (double)goal[i].z / m.cell;
+                const double rr2 = rc * rc;
+                for (int r = 0; r < m.rows && !wall[i]; ++r)
+                    for (int c = 0; c < m.cols; ++c) {
+                        const double dc = (double)(c - gy), dr = (double)(r - gx);
+                        if (dc * dc + dr * dr < rr2 && ((b->static_map_bits[r * wpr + (c >> 5)] >> (c & 31)) & 1u)) {
+                            wall[i] = 1;
+                            break;
+                        }
+                    }
+            }
+        }
         /* rewards, env.py:394-456 */
         REAL rmin = (REAL)cfg->reward_at_goal, rmax = rmin;
         const REAL vals[5] = {(REAL)cfg->reward_at_goal, (REAL)cfg->reward_collision_with_agent,
@@ -347,12 +369,16 @@ static void SFX(pairwise_obs_env)(const cav_config_t *cfg, const cav_buffers_t *
         for (int i = 0; i < n; ++i) {
             uint32_t f = flags[i] & ~(CAV_FLAG_COLLIDED_AGENT | CAV_FLAG_COLLIDED_WALL);
             if (coll[i]) f |= CAV_FLAG_COLLIDED_AGENT;
+            if (wall[i]) f |= CAV_FLAG_COLLIDED_WALL;
             REAL r = (REAL)cfg->reward_time_step;
             if (f & CAV_FLAG_AT_GOAL) {
                 if (!(f & CAV_FLAG_WAS_AT_GOAL_ALREADY)) r = (REAL)cfg->reward_at_goal;
             } else if (!(f & CAV_FLAG_WAS_IN_COLLISION_ALREADY)) {
                 if (coll[i]) {
                     r = (REAL)cfg->reward_collision_with_agent;
+                    f |= CAV_FLAG_IN_COLLISION;
+                } else if (wall[i]) {
+                    r = (REAL)cfg->reward_collision_with_wall;
                     f |= CAV_FLAG_IN_COLLISION;
                 } else {
                     if (md[i] <= (REAL)cfg->getting_close_range) r = (REAL)-0.1 - md[i] / (REAL)2.0;

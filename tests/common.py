@@ -46,6 +46,15 @@ class Golden(object):
         return to_cav_config(self.py_config(), num_envs, self.N, precision=precision, track_aux=track_aux,
                              history_len=history_len, store_history=history_len > 0)
 
+    def static_map_bits(self):
+        """uint32 bitmap of the fixture's static map (None when the fixture has none)."""
+        if "static_map" not in self.z:
+            return None
+        from gym_collision_avoidance_b200.envs.Map import Map
+        shape = tuple(self.meta["static_map_shape"])
+        sm = np.unpackbits(self.z["static_map"])[:shape[0] * shape[1]].reshape(shape).astype(bool)
+        return Map(16, 16, 0.1, static_map=sm).bits()
+
     def inject(self, st, e, t):
         """Write golden state at step t (after t steps) into env e of a HostState."""
         z = self.z
@@ -61,6 +70,8 @@ class Golden(object):
         st.done[e] = (z["st_flags"][t] & abi.CAV_FLAG_DONE) != 0
         if "laser_count" in st.arrays:
             st.laser_count[e, :self.n] = t + 1  # reset sensed once, then once per step
+        if st.static_map_bits is None and "static_map" in self.z:
+            st.static_map_bits = self.static_map_bits()
 
     def bank(self):
         rows = np.zeros((1, self.N, 8))

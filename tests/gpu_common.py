@@ -23,7 +23,15 @@ class GpuRunner(object):
         self.cav = Cavoid(c, dev)
 
     def upload(self, hs):
+        had = self.cav.state.static_map_bits is not None
         self.cav.state.load_host(hs)
+        if hs.static_map_bits is not None and not had:
+            self.cav.bind()  # the static-map pointer is part of the bound buffer set
+
+    def set_static_map(self, bits):
+        if bits is not None:
+            self.cav.state.set_static_map(bits)
+            self.cav.bind()
 
     def download(self):
         torch.cuda.synchronize()

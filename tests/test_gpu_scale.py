@@ -248,3 +248,41 @@ def test_laserscan_vs_oracle_random_scenes(N, prec, static_map):
         assert np.array_equal(got.laser_count, hs.laser_count)
         bad = got.obs[..., o:] != hs.obs[..., o:]
         assert bad.mean() <= (0.0 if prec == "f64" else 0.0), (s, int(bad.sum()))
+
+
+@pytest.mark.parametrize("mapping", ["tpa", "group"])
+def test_max_turn_rate_and_external_dynamics_vs_oracle(mapping, monkeypatch):
+    """UnicycleDynamicsMaxTurnRate (3 rad/s clip, UnicycleDynamicsMaxTurnRate.py:30-43) and ExternalDynamics (no-op,
+    ExternalDynamics.py:10-13) against the oracle (float64 semantics of the clip)."""
+    from gpu_common import GpuRunner, to_dev
+    monkeypatch.setenv("CAV_TPA_MAX_N", "32" if mapping == "tpa" else "0")
+    N, E = 6, 64
+    c = to_cav_config(make_config(N, evaluate=False), E, N, precision="f64", track_aux=True)
+    rows = random_scenario_bank(E, N, seed=33)
+    kinds = np.tile(np.array([abi.make_kind(abi.CAV_POLICY_EXTERNAL, abi.CAV_DYN_UNICYCLE_MAX_TURN_RATE),
+                              abi.make_kind(abi.CAV_POLICY_NONCOOP, abi.CAV_DYN_UNICYCLE_MAX_TURN_RATE),
+                              abi.make_kind(abi.CAV_POLICY_RVO, abi.CAV_DYN_UNICYCLE_MAX_TURN_RATE),
+                              abi.make_kind(abi.CAV_POLICY_EXTERNAL, abi.CAV_DYN_EXTERNAL),
+                              abi.make_kind(abi.CAV_POLICY_RVO, abi.CAV_DYN_UNICYCLE),
+                              abi.make_kind(abi.CAV_POLICY_LEARNING, abi.CAV_DYN_UNICYCLE_MAX_TURN_RATE)], np.uint32),
+                    (E, 1))
+    bank = HostBank(rows, kinds=kinds)
+    hs = HostState(c)
+    orc = Oracle(c)
+    orc.reset(hs, bank)
+    r = GpuRunner(c)
+    rng = np.random.RandomState(1)
+    p0 = hs.pv[:, 3, :2].copy()
+    clipped = 0
+    for s in range(12):
+        ext = np.zeros((E, N, 2), np.float32)
+        ext[..., 0] = rng.uniform(0.2, 1.5, size=(E, N))
+        ext[..., 1] = rng.uniform(-1.2, 1.2, size=(E, N))  # |a1|/dt up to 6 rad/s > 3 rad/s: the clip is active
+        ext[:, 5] = rng.uniform(0.0, 1.0, size=(E, 2))
+        clipped += int((np.abs(ext[:, 0, 1]) / c.dt > 3.0).sum())
+        r.upload(hs)
+        orc.step(hs, ext)
+        r.cav.step(to_dev(ext))
+        common.compare_states(r.download(), hs, N, 1e-9, 1e-9)
+    assert clipped > 50
+    assert np.array_equal(hs.pv[:, 3, :2], p0)  # ExternalDynamics agents are not moved by the step

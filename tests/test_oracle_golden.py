@@ -37,6 +37,7 @@ def test_free_running_f64(name):
     g = common.Golden(name)
     c = g.cav_config(1, "f64", track_aux=True, history_len=int(g.z["history"].shape[1]))
     st = HostState(c)
+    st.static_map_bits = g.static_map_bits()
     orc = Oracle(c)
     orc.reset(st, g.bank())
     # reset state == golden step 0

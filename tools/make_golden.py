@@ -84,7 +84,8 @@ def pack_obs(obs, Config, N):
     return np.stack(rows)
 
 
-def run_scenario(name, N, agents_fn, pre=(), post=(), max_steps=400, ext_action_fn=None, seed=0, stop_after=None):
+def run_scenario(name, N, agents_fn, pre=(), post=(), max_steps=400, ext_action_fn=None, seed=0, stop_after=None,
+                 static_map=None):
     cfg_path = write_cfg(N, list(pre), list(post))
     ref_harness.load_reference(cfg_path, "Cfg")
     from gym_collision_avoidance.envs import Config
@@ -98,6 +99,11 @@ def run_scenario(name, N, agents_fn, pre=(), post=(), max_steps=400, ext_action_
         assert isinstance(a.heading_global_frame, np.float64), type(a.heading_global_frame)
     env.set_agents(agents)
     obs, _ = env.reset()
+    if static_map is not None:
+        # the reference loads static maps from image files through imageio/scipy.misc (absent here, Map.py:17-21);
+        # writing the boolean layer into the Map object reset() just created is equivalent for the step path
+        assert env.map is not None and env.map.static_map.shape == static_map.shape
+        env.map.static_map[...] = static_map
     kinds = np.array([POLICY_IDS[a.policy.str] | (0 << 8) for a in agents] + [0] * (N - n), np.uint32)
     states = [agent_state(env.agents, N)]
     obs_seq = [pack_obs(obs, Config, N)]
@@ -160,7 +166,12 @@ def run_scenario(name, N, agents_fn, pre=(), post=(), max_steps=400, ext_action_
             GETTING_CLOSE_RANGE=Config.GETTING_CLOSE_RANGE, STORE_HISTORY=bool(Config.STORE_HISTORY),
         ),
     )
-    out = dict(meta=np.array(json.dumps(meta)), kinds=kinds,
+    extra = {}
+    if static_map is not None:
+        extra["static_map"] = np.packbits(static_map.astype(np.uint8), axis=None)
+        meta["static_map_shape"] = list(static_map.shape)
+        meta_json = json.dumps(meta)
+    out = dict(meta=np.array(json.dumps(meta)), kinds=kinds, **extra,
                rewards=np.stack(rewards), dones=np.stack(dones), game_over=np.array(gos),
                ext_actions=np.stack(exts), actions=np.stack(acts), obs=np.stack(obs_seq), history=hist)
     for k in states[0]:
@@ -315,6 +326,21 @@ def laser20_circle():  # BASELINE config[3] shape: 20 agents RVO + 512-beam lase
                       "self.STATES_IN_OBS = ['is_learning','num_other_agents','dist_to_goal','heading_ego_frame',"
                       "'pref_speed','radius','other_agents_states','laserscan']"],
                  post=EVAL_POST, stop_after=5)
+
+
+@scenario
+def walls6():  # static-map wall collisions (env.py:494-506): noncoop agents drive through wall blocks
+    sm = np.zeros((160, 160), bool)
+    sm[70:74, 60:100] = True     # horizontal wall just above the x axis (rows = y, Map.py:28)
+    sm[90:110, 120:123] = True   # vertical wall at x ~ +4
+    sm[20:30, 20:30] = True
+
+    def agents(tc, C):
+        rows = [[-4.0, 2.0, 4.0, -2.0, 1.0, 0.4], [3.0, -3.5, 5.5, 2.0, 1.2, 0.3], [-5.0, -4.0, -5.5, 5.0, 0.8, 0.5],
+                [0.0, 3.0, 0.0, -3.0, 1.0, 0.35], [6.0, 6.0, -6.0, 5.5, 1.5, 0.6], [-2.0, -6.0, 2.0, -6.5, 0.9, 0.25]]
+        return mk_agents(tc, rows, "noncoop")
+
+    run_scenario("walls6", 6, agents, pre=["self.USE_STATIC_MAP = True"], post=EVAL_POST, static_map=sm)
 
 
 if __name__ == "__main__":
