@@ -26,6 +26,7 @@ struct cav_handle_s {
     ResetParams rp;
     bool has_laser;
     bool use_tpa;  // one-thread-per-agent kernels (small N) instead of the sub-warp-group kernels
+    bool use_tpa_n;  // ... and, where instantiated, the compile-time-N pairwise+obs kernel (CAV_TPA_N=0 disables)
     int launches;
     char err[512];
 };
@@ -225,6 +226,9 @@ int cav_create(const cav_config_t *cfg, cav_handle_t *out) {
         h->use_tpa = cfg->num_agents <= tpa_max &&
                      tpa_smem_bytes(cfg->num_agents, cfg->precision == CAV_F64, h->plan,
                                     cfg->max_num_other_agents_observed) <= 200 * 1024;
+        // measured at 16384 x 10: float32 33 us vs 38 us generic; float64 52 us vs 50 us generic (138 registers)
+        h->use_tpa_n = h->use_tpa && cfg->precision == CAV_F32;
+        if (const char *ev = getenv("CAV_TPA_N")) h->use_tpa_n = h->use_tpa && atoi(ev) != 0;
     }
     cudaError_t ce = cudaGetDevice(&h->device);
     if (ce == cudaSuccess) ce = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device);
@@ -316,6 +320,17 @@ static WallMap wall_map(cav_handle_t h) {
 static int do_pairwise_obs(cav_handle_t h, const uint8_t *mask, int obs_only, cudaStream_t st) {
     const WallMap wm = wall_map(h);
     if (h->use_tpa) {
+        if (h->use_tpa_n) {  // compile-time-N specialisation when the configuration allows it
+            const cudaError_t ce = (h->cfg.precision == CAV_F64)
+                                       ? run_pairwise_obs_tpa_n<double>(h->bufs, h->pd, h->plan, wm, mask, obs_only, h->sm_count, st)
+                                       : run_pairwise_obs_tpa_n<float>(h->bufs, h->pf, h->plan, wm, mask, obs_only, h->sm_count, st);
+            if (ce == cudaSuccess) {
+                h->launches++;
+                return CAV_OK;
+            }
+            if (ce != cudaErrorNotSupported) return fail(h, CAV_ERR_CUDA, "pairwise_obs_tpa_n: %s", cudaGetErrorString(ce));
+            h->use_tpa_n = false;  // not applicable to this handle: stop asking
+        }
         if (h->cfg.precision == CAV_F64)
             CAV_CUDA(h, "pairwise_obs_tpa",
                      run_pairwise_obs_tpa<double>(h->bufs, h->pd, h->plan, wm, mask, obs_only, h->sm_count, st));

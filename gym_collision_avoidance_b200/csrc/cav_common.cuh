@@ -49,7 +49,13 @@ struct M<float> {
     static __device__ __forceinline__ float cos_(float a) { return cosf(a); }
     static __device__ __forceinline__ float atan2_(float y, float x) { return atan2f(y, x); }
     static __device__ __forceinline__ float abs_(float a) { return fabsf(a); }
-    static __device__ __forceinline__ float rint_(float a) { return rintf(a); }
+    // round-half-even to an integer WITHOUT the XU pipe (FRND): adding and subtracting 1.5 * 2^23 rounds exactly
+    // like rintf for |a| < 2^22; larger magnitudes are already integers.  (ncu: the pairwise+obs kernels were bound by
+    // the XU pipe -- FRND / F2I / MUFU.RSQ64H -- at 65 % of its peak, profiles/r01b_*.)
+    static __device__ __forceinline__ float rint_(float a) {
+        const float r = __fsub_rn(__fadd_rn(fabsf(a), 12582912.0f), 12582912.0f);
+        return fabsf(a) < 4194304.0f ? copysignf(r, a) : a;
+    }
     static __device__ __forceinline__ float fmod_(float a, float b) { return fmodf(a, b); }
     static __device__ __forceinline__ float inf() { return CUDART_INF_F; }
 };
@@ -60,7 +66,10 @@ struct M<double> {
     static __device__ __forceinline__ double cos_(double a) { return cos(a); }
     static __device__ __forceinline__ double atan2_(double y, double x) { return atan2(y, x); }
     static __device__ __forceinline__ double abs_(double a) { return fabs(a); }
-    static __device__ __forceinline__ double rint_(double a) { return rint(a); }
+    static __device__ __forceinline__ double rint_(double a) {  // see the float version; exact for |a| < 2^51
+        const double r = __dsub_rn(__dadd_rn(fabs(a), 6755399441055744.0), 6755399441055744.0);
+        return fabs(a) < 2251799813685248.0 ? copysign(r, a) : a;
+    }
     static __device__ __forceinline__ double fmod_(double a, double b) { return fmod(a, b); }
     static __device__ __forceinline__ double inf() { return CUDART_INF; }
 };

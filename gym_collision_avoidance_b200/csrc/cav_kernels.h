@@ -26,6 +26,10 @@ cudaError_t run_pairwise_obs_tpa(const cav_buffers_t &bufs, const KParams<T> &p,
                                  const WallMap &wm, const uint8_t *env_mask, int obs_only, int sm_count,
                                  cudaStream_t st);
 size_t tpa_smem_bytes(int N, int precision_f64, const ObsPlan &plan, int K);
+// compile-time-N, register-resident specialisation (cav_tpa_n.cu); cudaErrorNotSupported = use the generic kernel
+template <typename T>
+cudaError_t run_pairwise_obs_tpa_n(const cav_buffers_t &bufs, const KParams<T> &p, const ObsPlan &plan, const WallMap &wm,
+                                   const uint8_t *env_mask, int obs_only, int sm_count, cudaStream_t st);
 
 struct LaserParams {
     int E, N, B, P, obs_len, obs_off;

@@ -1,0 +1,346 @@
+// cav_tpa_n.cu -- pairwise collisions + rewards + sorted-neighbour observation + done, one thread per agent, with
+// the agent count N a COMPILE-TIME constant (reference env.py:394-512, OtherAgentsStatesSensor.py:58-144,
+// agent.py:323-327, env.py:514-553 -- the same contract as k_pairwise_obs_tpa in cav_tpa.cu).
+//
+// Why: ncu showed k_pairwise_obs_tpa latency-bound (profiles/r01b_*: ~5 warps per scheduler, "wait" and
+// short-scoreboard stalls, ~11 cycles per instruction): its per-thread work is one long dependent chain -- a
+// run-time loop over neighbours with an insertion sort through shared memory, then run-time loops over output rows.
+// With N known at compile time everything unrolls: the N-1 centre distances (each an IEEE sqrt chain) are independent
+// instruction streams, the neighbour keys and distances live in registers and are ordered by a branch-free odd-even
+// transposition network (no shared-memory round trips, no divergence), and the N-1 observation rows are independent
+// as well.  Used for the default observation layout (6 scalars then the (N-1) x 7 neighbour rows, closest_first,
+// K = N-1); every other configuration takes the generic kernel.  Arithmetic is identical to the generic kernel.
+#include "cav_tpa_common.cuh"
+
+namespace cav {
+
+template <typename T, int NT>
+__global__ void __launch_bounds__(128) k_pairwise_obs_tpa_n(TpaBuffers b, KParams<T> p, WallMap wm,
+                                                              const uint8_t *__restrict__ env_mask, int obs_only,
+                                                              int EPB, int ntiles) {
+    constexpr int NO = NT - 1;  // neighbours = observation rows
+    constexpr int CW = TpaChunk<T>::CW;
+    constexpr int AST = CW + 1;
+    constexpr int APL = 32 / CW;
+    constexpr int ROWS0 = (CW - 6) / 7;                   // rows that fit next to the 6 scalars in chunk 0
+    constexpr int RPC = CW / 7;                           // rows per later chunk
+    constexpr int CL = 6 + 7 * NO;                        // packed observation length
+    constexpr int KSHIFT = KeyCodec<T>::PB + 6;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int cap = EPB * NT;
+    const int nt = blockDim.x;
+    unsigned char *sp = smem_raw;
+    R4<T> *s_pv = reinterpret_cast<R4<T> *>(sp);
+    sp += a16(sizeof(R4<T>) * cap);
+    T *s_rad = reinterpret_cast<T *>(sp);
+    sp += a16(sizeof(T) * cap);
+    T *s_arena = reinterpret_cast<T *>(sp);  // [nwarps][32][AST]
+    sp += a16(sizeof(T) * (size_t)(nt >> 5) * 32 * AST);
+    uint8_t *s_done = reinterpret_cast<uint8_t *>(sp);
+    sp += a16((size_t)cap);
+    int *s_n = reinterpret_cast<int *>(sp);
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    T *arena = s_arena + (size_t)warp * 32 * AST;
+    const R4<T> *g_pv = reinterpret_cast<const R4<T> *>(b.pv);
+    const R4<T> *g_goal = reinterpret_cast<const R4<T> *>(b.goal);
+    const R4<T> *g_ego = reinterpret_cast<const R4<T> *>(b.ego);
+    T *g_obs = reinterpret_cast<T *>(b.obs);
+    T *g_reward = reinterpret_cast<T *>(b.reward);
+    T *g_mind = reinterpret_cast<T *>(b.min_dist);
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int e0 = tile * EPB;
+        const int ne = min(EPB, p.E - e0);
+        const int count = ne * NT;
+        const size_t base = (size_t)e0 * NT;
+        const bool have = tid < count;
+        const size_t gi = base + tid;
+        R4<T> pvh{}, glh{}, egh{};
+        uint32_t f = 0, kind = 0;
+        float adh = 0.f;
+        if (have) {
+            pvh = ld4(g_pv + gi);
+            glh = ld4(g_goal + gi);
+            egh = ld4(g_ego + gi);
+            f = b.flags[gi];
+            kind = b.kinds[gi];
+            adh = b.actions[2 * gi + 1];
+            s_pv[tid] = pvh;
+            s_rad[tid] = glh.z;
+        }
+        if (tid < ne) {
+            int n = b.num_active ? b.num_active[e0 + tid] : NT;
+            if (env_mask && !env_mask[e0 + tid]) n = -1;
+            s_n[tid] = n;
+        }
+        __syncthreads();
+
+        const int el = have ? tid / NT : 0, h = tid - el * NT;
+        const int n = have ? s_n[el] : -1;
+        const bool active = have && h < n;
+        const int eb = el * NT;
+        const T prx = egh.z, pry = egh.w;
+        const T orx = -pry, ory = prx;  // ref_orth, agent.py:347
+        unsigned long long key[NO > 0 ? NO : 1];
+        T dcv[NO > 0 ? NO : 1];
+        int nc = 0;
+        if (active) {
+            T md = M<T>::inf();
+            bool coll = false;
+            // ---- all neighbours at once: slot j <-> other agent o = j + (j >= h) ----
+#pragma unroll
+            for (int j = 0; j < NO; ++j) {
+                const int o = j + (j >= h ? 1 : 0);
+                key[j] = ~0ull;
+                dcv[j] = (T)0;
+                if (o < n) {
+                    const R4<T> pvo = s_pv[eb + o];
+                    const T ro = s_rad[eb + o];
+                    const T rx = pvo.x - pvh.x, ry = pvo.y - pvh.y;
+                    const T dc = M<T>::sqrt_(rx * rx + ry * ry);  // util.l2norm == util.vec2_l2_norm
+                    const T cr = glh.z + ro;                       // env.py:481
+                    md = min_keep(md, dc - cr);                    // :482-487
+                    coll = coll || (dc <= cr);                     // :490
+                    if (!(dc > p.sensing_horizon)) {               // OtherAgentsStatesSensor.py:90
+                        const T d2o = dc - glh.z - ro;             // :87
+                        const T po = (rx * orx + ry * ory) + (T)0;
+                        key[j] = make_key<T>(M<T>::rint_(d2o * (T)100), po, o, false);
+                        dcv[j] = dc;
+                        ++nc;
+                    }
+                }
+            }
+            // ---- order: branch-free odd-even transposition network on (key, dc) in registers ----
+#pragma unroll
+            for (int r = 0; r < NO; ++r) {
+#pragma unroll
+                for (int i = (r & 1); i + 1 < NO; i += 2) {
+                    const bool sw = key[i + 1] < key[i];
+                    const unsigned long long ka = key[i], kb = key[i + 1];
+                    const T da = dcv[i], db = dcv[i + 1];
+                    key[i] = sw ? kb : ka;
+                    key[i + 1] = sw ? ka : kb;
+                    dcv[i] = sw ? db : da;
+                    dcv[i + 1] = sw ? da : db;
+                }
+            }
+            // exact re-comparison inside runs of equal kint (truncated p_orth / clamped kint, see KeyCodec): rare
+            bool tie = false;
+#pragma unroll
+            for (int r = 0; r + 1 < NO; ++r) tie = tie || ((key[r] >> KSHIFT) == (key[r + 1] >> KSHIFT) && key[r + 1] != ~0ull);
+            if (tie) {
+#pragma unroll 1
+                for (int pass = 0; pass < NO; ++pass) {
+                    bool swapped = false;
+#pragma unroll
+                    for (int r = 0; r + 1 < NO; ++r) {
+                        const unsigned long long ka = key[r], kb = key[r + 1];
+                        if ((ka >> KSHIFT) == (kb >> KSHIFT) && kb != ~0ull) {
+                            const int oa = (int)(ka & 63ull), ob = (int)(kb & 63ull);
+                            const R4<T> pa = s_pv[eb + oa], pb = s_pv[eb + ob];
+                            const T kia = M<T>::rint_((dcv[r] - glh.z - s_rad[eb + oa]) * (T)100);
+                            const T kib = M<T>::rint_((dcv[r + 1] - glh.z - s_rad[eb + ob]) * (T)100);
+                            const T poa = (pa.x - pvh.x) * orx + (pa.y - pvh.y) * ory;
+                            const T pob = (pb.x - pvh.x) * orx + (pb.y - pvh.y) * ory;
+                            const bool b_first = (kib < kia) || (kib == kia && (pob < poa || (pob == poa && ob < oa)));
+                            if (b_first) {
+                                const T da = dcv[r];
+                                key[r] = kb;
+                                key[r + 1] = ka;
+                                dcv[r] = dcv[r + 1];
+                                dcv[r + 1] = da;
+                                swapped = true;
+                            }
+                        }
+                    }
+                    if (!swapped) break;
+                }
+            }
+            if (nc > p.K) nc = p.K;
+            // ---- collisions + reward (env.py:394-456) ----
+            if (!obs_only) {
+                f &= ~(uint32_t)(CAV_FLAG_COLLIDED_AGENT | CAV_FLAG_COLLIDED_WALL);
+                if (coll) f |= CAV_FLAG_COLLIDED_AGENT;
+                const bool wall = wm.bits && wall_hit(wm, (double)pvh.x, (double)pvh.y, (double)glh.z, 0, 1);
+                if (wall) f |= CAV_FLAG_COLLIDED_WALL;
+                T r = p.reward_time_step;
+                if (f & CAV_FLAG_AT_GOAL) {
+                    if (!(f & CAV_FLAG_WAS_AT_GOAL_ALREADY)) r = p.reward_at_goal;
+                } else if (!(f & CAV_FLAG_WAS_IN_COLLISION_ALREADY)) {
+                    if (coll) {
+                        r = p.reward_coll_agent;
+                        f |= CAV_FLAG_IN_COLLISION;
+                    } else if (wall) {
+                        r = p.reward_coll_wall;
+                        f |= CAV_FLAG_IN_COLLISION;
+                    } else {
+                        if (md <= p.getting_close) r = (T)-0.1 - md / (T)2.0;
+                        if (M<T>::abs_((T)adh) > p.wiggly_thr) r += p.reward_wiggly;
+                    }
+                }
+                r = r < p.reward_min ? p.reward_min : (r > p.reward_max ? p.reward_max : r);  // np.clip
+                g_reward[gi] = r;
+                if (g_mind) g_mind[gi] = md;
+                const bool d = (f & (CAV_FLAG_AT_GOAL | CAV_FLAG_RAN_OUT_OF_TIME | CAV_FLAG_IN_COLLISION)) != 0;
+                f = d ? (f | CAV_FLAG_DONE) : (f & ~(uint32_t)CAV_FLAG_DONE);
+                b.flags[gi] = f;
+                b.done[gi] = d ? 1 : 0;
+                s_done[tid] = d ? 1 : 0;
+            }
+        }
+        // ---- packed observation through the per-warp arena; chunk boundaries are compile-time constants ----
+        const unsigned vmask = __ballot_sync(0xffffffffu, active);
+        if (vmask != 0u) {
+            T *gwarp = g_obs + (base + (size_t)(warp << 5)) * (size_t)CL;
+            const int sub = lane / CW, kk = lane - sub * CW;
+            T *my = arena + lane * AST;
+            auto fill_row = [&](int r, T *dst) {  // r is a compile-time constant at every call site
+                if (r < nc) {
+                    const int o = (int)(key[r] & 63ull);
+                    const R4<T> pvo = s_pv[eb + o];
+                    const T ro = s_rad[eb + o];
+                    const T rx = pvo.x - pvh.x, ry = pvo.y - pvh.y;
+                    dst[0] = rx * prx + ry * pry;
+                    dst[1] = rx * orx + ry * ory;
+                    dst[2] = pvo.z * prx + pvo.w * pry;
+                    dst[3] = pvo.z * orx + pvo.w * ory;
+                    dst[4] = ro;
+                    dst[5] = glh.z + ro;
+                    dst[6] = dcv[r] - glh.z - ro;  // np.linalg.norm(..) - r - r (:125)
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 7; ++k) dst[k] = (T)0;  // zero rows (:108)
+                }
+            };
+            auto copy_out = [&](int c0, int len) {
+                __syncwarp();
+                if (kk < len) {
+                    const T *src = arena + sub * AST + kk;
+                    T *dst = gwarp + sub * CL + c0 + kk;
+                    if (vmask == 0xffffffffu) {
+#pragma unroll 4
+                        for (int j = sub; j < 32; j += APL) {
+                            *dst = *src;
+                            src += APL * AST;
+                            dst += APL * CL;
+                        }
+                    } else {
+#pragma unroll 1
+                        for (int j = sub; j < 32; j += APL) {
+                            if ((vmask >> j) & 1u) *dst = *src;
+                            src += APL * AST;
+                            dst += APL * CL;
+                        }
+                    }
+                }
+                __syncwarp();
+            };
+            // chunk 0: the six scalars (agent.py:323-327, default STATES_IN_OBS order) + the first ROWS0 rows
+            {
+                constexpr int R0 = ROWS0 < NO ? ROWS0 : NO;
+                if (active) {
+                    my[0] = (CAV_KIND_POLICY(kind) == CAV_POLICY_LEARNING) ? (T)1 : (T)0;  // is_learning
+                    my[1] = (T)nc;                                                          // num_other_agents
+                    my[2] = egh.x;                                                          // dist_to_goal
+                    my[3] = egh.y;                                                          // heading_ego_frame
+                    my[4] = glh.w;                                                          // pref_speed
+                    my[5] = glh.z;                                                          // radius
+#pragma unroll
+                    for (int r = 0; r < R0; ++r) fill_row(r, my + 6 + 7 * r);
+                }
+                copy_out(0, 6 + 7 * R0);
+            }
+            // later chunks: RPC rows each
+#pragma unroll
+            for (int rb = ROWS0; rb < NO; rb += RPC) {
+                const int rows = (NO - rb) < RPC ? (NO - rb) : RPC;
+                if (active) {
+#pragma unroll
+                    for (int q = 0; q < RPC; ++q)
+                        if (q < rows) fill_row(rb + q, my + 7 * q);
+                }
+                copy_out(6 + 7 * rb, 7 * rows);
+            }
+        }
+        // ---- game_over (env.py:538-551) ----
+        if (!obs_only) {
+            __syncthreads();
+            if (tid < ne && s_n[tid] >= 0) {
+                const int nn = s_n[tid];
+                bool all_done = true, all_learning_done = true;
+                for (int a = 0; a < nn; ++a) {
+                    const bool d = s_done[tid * NT + a] != 0;
+                    if (!d) {
+                        all_done = false;
+                        if (CAV_KIND_POLICY(b.kinds[base + (size_t)tid * NT + a]) == CAV_POLICY_LEARNING)
+                            all_learning_done = false;
+                    }
+                }
+                bool go;
+                if (p.game_over_mode == CAV_GAME_OVER_ALL_DONE) go = all_done;
+                else if (p.game_over_mode == CAV_GAME_OVER_AGENT0) go = s_done[tid * NT] != 0;
+                else go = all_learning_done;
+                b.game_over[e0 + tid] = go ? 1 : 0;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// true when the plan is the default layout this kernel hard-codes
+static bool standard_layout(const ObsPlan &plan, const KParams<float> *, int N, int K, int obs_len, int sorting) {
+    if (K != N - 1 || sorting != CAV_SORT_CLOSEST_FIRST || plan.oas7_goff >= 0) return false;
+    if (plan.nseg != 1 || plan.goff[0] != 0 || plan.coff[0] != 0) return false;
+    if (plan.compact_len != 6 + 7 * K || obs_len != plan.compact_len) return false;
+    const int want[6] = {CAV_OBS_IS_LEARNING, CAV_OBS_NUM_OTHER_AGENTS, CAV_OBS_DIST_TO_GOAL, CAV_OBS_HEADING_EGO_FRAME,
+                         CAV_OBS_PREF_SPEED, CAV_OBS_RADIUS};
+    for (int i = 0; i < 6; ++i)
+        if (plan.c_state[want[i]] != i) return false;
+    return plan.c_state[CAV_OBS_OTHER_AGENTS_STATES] == 6;
+}
+
+template <typename T, int NT>
+static cudaError_t launch_n(const cav_buffers_t &bufs, const KParams<T> &p, const WallMap &wm, const uint8_t *env_mask,
+                            int obs_only, int sm_count, cudaStream_t st) {
+    int EPB = 128 / NT;
+    if (EPB < 1) EPB = 1;
+    const int threads = ((EPB * NT + 31) / 32) * 32;
+    const int ntiles = (p.E + EPB - 1) / EPB;
+    const int cap = EPB * NT;
+    const size_t smem = a16(sizeof(R4<T>) * cap) + a16(sizeof(T) * cap) +
+                        a16(sizeof(T) * (size_t)(threads / 32) * 32 * (TpaChunk<T>::CW + 1)) + a16((size_t)cap) +
+                        a16(sizeof(int) * EPB) + 64;
+    const int grid = ntiles < sm_count * 16 ? ntiles : sm_count * 16;
+    k_pairwise_obs_tpa_n<T, NT><<<grid, threads, smem, st>>>(make_tpa(bufs), p, wm, env_mask, obs_only, EPB, ntiles);
+    return cudaGetLastError();
+}
+
+// Returns cudaErrorNotSupported when no specialisation applies (the caller then runs the generic kernel).
+template <typename T>
+cudaError_t run_pairwise_obs_tpa_n(const cav_buffers_t &bufs, const KParams<T> &p, const ObsPlan &plan, const WallMap &wm,
+                                   const uint8_t *env_mask, int obs_only, int sm_count, cudaStream_t st) {
+    if (!standard_layout(plan, nullptr, p.N, p.K, p.obs_len, p.sorting)) return cudaErrorNotSupported;
+    switch (p.N) {
+#define CAV_CASE(NN) \
+    case NN: return launch_n<T, NN>(bufs, p, wm, env_mask, obs_only, sm_count, st);
+        CAV_CASE(2)
+        CAV_CASE(3)
+        CAV_CASE(4)
+        CAV_CASE(5)
+        CAV_CASE(6)
+        CAV_CASE(8)
+        CAV_CASE(10)
+        CAV_CASE(12)
+#undef CAV_CASE
+        default: return cudaErrorNotSupported;
+    }
+}
+
+template cudaError_t run_pairwise_obs_tpa_n<float>(const cav_buffers_t &, const KParams<float> &, const ObsPlan &,
+                                                   const WallMap &, const uint8_t *, int, int, cudaStream_t);
+template cudaError_t run_pairwise_obs_tpa_n<double>(const cav_buffers_t &, const KParams<double> &, const ObsPlan &,
+                                                    const WallMap &, const uint8_t *, int, int, cudaStream_t);
+
+}  // namespace cav
