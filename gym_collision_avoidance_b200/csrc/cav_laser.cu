@@ -36,6 +36,12 @@ __global__ void __launch_bounds__(256) k_laserscan(LaserPtrs b, LaserParams lp, 
     int *s_gy = s_gx + CAV_MAX_AGENTS;
     int *s_in = s_gy + CAV_MAX_AGENTS;
     uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_in + CAV_MAX_AGENTS);
+    // per current agent h: the other agents whose inflated disc the beams can reach (compacted)
+    double *s_cox = reinterpret_cast<double *>(s_cnt + CAV_MAX_AGENTS);
+    double *s_coy = s_cox + CAV_MAX_AGENTS;
+    double *s_cdd = s_coy + CAV_MAX_AGENTS;
+    double *s_cR2 = s_cdd + CAV_MAX_AGENTS;
+    int *s_ncand = reinterpret_cast<int *>(s_cR2 + CAV_MAX_AGENTS);
 
     const int tid = threadIdx.x;
     const int N = lp.N;
@@ -98,6 +104,33 @@ __global__ void __launch_bounds__(256) k_laserscan(LaserPtrs b, LaserParams lp, 
             const int ego_in = s_in[h], cgx = s_gx[h], cgy = s_gy[h];
             const uint32_t cnt = s_cnt[h];
             T *o = g_obs + (base + h) * (size_t)lp.obs_len + lp.obs_off;
+            // Which samples can hit at all?  A sample can only land in a cell painted for agent c if it lies within
+            // R_c = r_c + sqrt(2)*cell (+eps) of c's centre (the sample and the centre are each anywhere inside
+            // their cells), so with an empty static map only samples inside the union of the ray's intersections with
+            // those inflated discs need the exact cell test.  Candidates (painted agents within max_range + R_c) are
+            // compacted once per agent; every beam of this agent then tests only them.
+            if (!has_static) {
+                __syncthreads();  // previous agent's beams are done with the candidate list
+                if (tid == 0) {
+                    int nc = 0;
+                    for (int c = 0; c < n; ++c) {
+                        if (c == h || !s_in[c]) continue;
+                        const double ox = s_px[c] - px, oy = s_py[c] - py;
+                        const double R = sqrt(s_rr2[c]) * lp.cell + 1.4143 * lp.cell + 1e-6;
+                        const double dd = ox * ox + oy * oy;
+                        const double reach = lp.max_range + R;
+                        if (dd > reach * reach) continue;
+                        s_cox[nc] = ox;
+                        s_coy[nc] = oy;
+                        s_cdd[nc] = dd;
+                        s_cR2[nc] = R * R;
+                        ++nc;
+                    }
+                    *s_ncand = nc;
+                }
+                __syncthreads();
+            }
+            const int ncand = has_static ? 0 : *s_ncand;
             for (int bi = tid; bi < lp.B; bi += blockDim.x) {
                 double ang0 = (double)bi * lp.ang_step + lp.min_angle;  // np.linspace (LaserScanSensor.py:38)
                 if (bi == lp.B - 1) ang0 = lp.max_angle;
@@ -105,21 +138,14 @@ __global__ void __launch_bounds__(256) k_laserscan(LaserPtrs b, LaserParams lp, 
                 double sa, ca;
                 sincos(ang, &sa, &ca);
                 int cum = 0, kstar = -1;
-                // Which samples can hit at all?  A sample can only land in a cell painted for agent o if it lies
-                // within R_o = r_o + sqrt(2)*cell (+eps) of o's centre (the sample and the centre are each anywhere
-                // inside their cells), so with an empty static map only the samples inside the union of the ray's
-                // intersections with those inflated discs need the exact cell test; everything else is a miss.
                 int k_lo = 0, k_hi = lp.nr - 1;
                 if (!has_static) {
                     double tmin = 1e300, tmax = -1e300;
 #pragma unroll 1
-                    for (int o = 0; o < n; ++o) {
-                        if (o == h || !s_in[o]) continue;
-                        const double ox = s_px[o] - px, oy = s_py[o] - py;
-                        const double R = sqrt(s_rr2[o]) * lp.cell + 1.4143 * lp.cell + 1e-6;
-                        const double tca = ox * ca + oy * sa;
-                        const double d2 = (ox * ox + oy * oy) - tca * tca;
-                        const double R2 = R * R;
+                    for (int c = 0; c < ncand; ++c) {
+                        const double tca = s_cox[c] * ca + s_coy[c] * sa;
+                        const double d2 = s_cdd[c] - tca * tca;
+                        const double R2 = s_cR2[c];
                         if (d2 > R2) continue;
                         const double thc = sqrt(R2 - d2);
                         const double t1 = tca + thc;
@@ -188,7 +214,7 @@ cudaError_t run_laserscan(const cav_buffers_t &bufs, const LaserParams &lp, cons
     const int APC = 4;
     const int chunks = (lp.N + APC - 1) / APC;
     const int nwork = lp.E * chunks;
-    const size_t smem = (((size_t)lp.rows * lp.wpr * 4 + 15) & ~(size_t)15) + CAV_MAX_AGENTS * (4 * 8 + 4 * 4) + 64;
+    const size_t smem = (((size_t)lp.rows * lp.wpr * 4 + 15) & ~(size_t)15) + CAV_MAX_AGENTS * (8 * 8 + 4 * 4) + 64;
     auto kern = k_laserscan<T>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
