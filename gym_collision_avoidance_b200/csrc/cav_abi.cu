@@ -226,8 +226,8 @@ int cav_create(const cav_config_t *cfg, cav_handle_t *out) {
         h->use_tpa = cfg->num_agents <= tpa_max &&
                      tpa_smem_bytes(cfg->num_agents, cfg->precision == CAV_F64, h->plan,
                                     cfg->max_num_other_agents_observed) <= 200 * 1024;
-        // measured at 16384 x 10: float32 33 us vs 38 us generic; float64 52 us vs 50 us generic (138 registers)
-        h->use_tpa_n = h->use_tpa && cfg->precision == CAV_F32;
+        // measured at 16384 x 10: float32 33 us vs 38 us generic; float64 45 us vs 50 us generic
+        h->use_tpa_n = h->use_tpa;
         if (const char *ev = getenv("CAV_TPA_N")) h->use_tpa_n = h->use_tpa && atoi(ev) != 0;
     }
     cudaError_t ce = cudaGetDevice(&h->device);

@@ -14,8 +14,20 @@
 
 namespace cav {
 
+// Resident CTAs per SM the compiler must allow.  float64 at N = 10 wants 138 registers unconstrained (3 CTAs / SM);
+// capping at 5 CTAs (<= 102 registers, ~170 B of spills) measured best at 16384 x 10: 44.8 us vs 51.3 (1), 49.1 (4),
+// 48.0 (6) and 49.8 for the generic kernel.  float32 needs 96 registers unconstrained, i.e. 5 CTAs already.
+template <typename T>
+struct TpaNBounds {
+    static constexpr int MINB = 1;
+};
+template <>
+struct TpaNBounds<double> {
+    static constexpr int MINB = 5;
+};
+
 template <typename T, int NT>
-__global__ void __launch_bounds__(128) k_pairwise_obs_tpa_n(TpaBuffers b, KParams<T> p, WallMap wm,
+__global__ void __launch_bounds__(128, TpaNBounds<T>::MINB) k_pairwise_obs_tpa_n(TpaBuffers b, KParams<T> p, WallMap wm,
                                                               const uint8_t *__restrict__ env_mask, int obs_only,
                                                               int EPB, int ntiles) {
     constexpr int NO = NT - 1;  // neighbours = observation rows
