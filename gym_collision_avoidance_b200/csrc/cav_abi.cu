@@ -26,6 +26,7 @@ struct cav_handle_s {
     ResetParams rp;
     bool has_laser;
     bool use_tpa;  // one-thread-per-agent kernels (small N) instead of the sub-warp-group kernels
+    bool use_tpa_n_policy;  // compile-time-N policy+move kernel (CAV_TPA_N_POLICY=0 disables)
     bool use_tpa_n;  // ... and, where instantiated, the compile-time-N pairwise+obs kernel (CAV_TPA_N=0 disables)
     int launches;
     char err[512];
@@ -229,6 +230,8 @@ int cav_create(const cav_config_t *cfg, cav_handle_t *out) {
         // measured at 16384 x 10: float32 33 us vs 38 us generic; float64 45 us vs 50 us generic
         h->use_tpa_n = h->use_tpa;
         if (const char *ev = getenv("CAV_TPA_N")) h->use_tpa_n = h->use_tpa && atoi(ev) != 0;
+        h->use_tpa_n_policy = h->use_tpa && cfg->precision == CAV_F32;
+        if (const char *ev = getenv("CAV_TPA_N_POLICY")) h->use_tpa_n_policy = h->use_tpa && atoi(ev) != 0;
     }
     cudaError_t ce = cudaGetDevice(&h->device);
     if (ce == cudaSuccess) ce = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device);
@@ -288,6 +291,17 @@ int cav_bind(cav_handle_t h, const cav_buffers_t *bufs) {
 
 static int do_policy_move(cav_handle_t h, const float *ext, int phases, double dt, cudaStream_t st) {
     if (h->use_tpa) {
+        if (h->use_tpa_n_policy) {
+            const cudaError_t ce = (h->cfg.precision == CAV_F64)
+                                       ? run_policy_move_tpa_n<double>(h->bufs, h->pd, ext, phases, dt, h->sm_count, st)
+                                       : run_policy_move_tpa_n<float>(h->bufs, h->pf, ext, phases, dt, h->sm_count, st);
+            if (ce == cudaSuccess) {
+                h->launches++;
+                return CAV_OK;
+            }
+            if (ce != cudaErrorNotSupported) return fail(h, CAV_ERR_CUDA, "policy_move_tpa_n: %s", cudaGetErrorString(ce));
+            h->use_tpa_n_policy = false;
+        }
         if (h->cfg.precision == CAV_F64)
             CAV_CUDA(h, "policy_move_tpa", run_policy_move_tpa<double>(h->bufs, h->pd, ext, phases, dt, h->sm_count, st));
         else

@@ -31,6 +31,10 @@ template <typename T>
 cudaError_t run_pairwise_obs_tpa_n(const cav_buffers_t &bufs, const KParams<T> &p, const ObsPlan &plan, const WallMap &wm,
                                    const uint8_t *env_mask, int obs_only, int sm_count, cudaStream_t st);
 
+template <typename T>
+cudaError_t run_policy_move_tpa_n(const cav_buffers_t &bufs, const KParams<T> &p, const float *ext, int phases, double dt,
+                                  int sm_count, cudaStream_t st);
+
 struct LaserParams {
     int E, N, B, P, obs_len, obs_off;
     int rows, cols, wpr, nr;

@@ -127,111 +127,8 @@ __global__ void __launch_bounds__(128) k_policy_move_tpa(TpaBuffers b, KParams<T
                 reinterpret_cast<float2 *>(b.actions)[gi] = act;
             }
             // ---- move (Agent.take_action, agent.py:192-241) ----
-            if (phases & PH_MOVE) {
-                if (f & (CAV_FLAG_AT_GOAL | CAV_FLAG_RAN_OUT_OF_TIME | CAV_FLAG_IN_COLLISION)) {  // agent.py:202-209
-                    if (f & CAV_FLAG_AT_GOAL) f |= CAV_FLAG_WAS_AT_GOAL_ALREADY;
-                    if (f & CAV_FLAG_IN_COLLISION) f |= CAV_FLAG_WAS_IN_COLLISION_ALREADY;
-                    pv.z = (T)0;
-                    pv.w = (T)0;
-                    st4(g_pv + gi, pv);
-                    b.flags[gi] = f;
-                    if (b.past_vel) {
-                        R4<T> *pvel = reinterpret_cast<R4<T> *>(b.past_vel) + gi;
-                        R4<T> q = ld4(pvel);
-                        q.z = q.x;
-                        q.w = q.y;
-                        q.x = (T)0;
-                        q.y = (T)0;
-                        st4(pvel, q);
-                    }
-                } else {
-                    if (!have_act) act = reinterpret_cast<const float2 *>(b.actions)[gi];
-                    const T a0 = (T)act.x;
-                    T a1 = (T)act.y;
-                    const uint32_t dyn = CAV_KIND_DYNAMICS(kind);
-                    if (b.past_actions) {  // agent.py:212-213
-                        R4<T> *pa = reinterpret_cast<R4<T> *>(b.past_actions) + gi;
-                        R4<T> q = ld4(pa);
-                        q.z = q.x;
-                        q.w = q.y;
-                        q.x = a0;
-                        q.y = a1;
-                        st4(pa, q);
-                    }
-                    T speed_out = (T)0, dhead_out = (T)0;
-                    if (b.aux0) {
-                        const R4<T> q = ld4(reinterpret_cast<R4<T> *>(b.aux0) + gi);
-                        speed_out = q.x;
-                        dhead_out = q.y;
-                    }
-                    if (dyn != CAV_DYN_EXTERNAL) {
-                        if (dyn == CAV_DYN_UNICYCLE_MAX_TURN_RATE) {  // UnicycleDynamicsMaxTurnRate.py:30-32
-                            T tr = a1 / dt;
-                            tr = tr < (T)-3.0 ? (T)-3.0 : (tr > (T)3.0 ? (T)3.0 : tr);
-                            a1 = tr * dt;
-                        }
-                        const T heading = ht.x;
-                        const T sel = wrap<T>(a1 + heading);  // UnicycleDynamics.py:28
-                        const T c = M<T>::cos_(sel), s = M<T>::sin_(sel);
-                        const T dx = a0 * c * dt, dy = a0 * s * dt;  // :30-31
-                        pv.x += dx;
-                        pv.y += dy;
-                        pv.z = a0 * c;  // :34-35
-                        pv.w = a0 * s;
-                        speed_out = a0;
-                        dhead_out = wrap<T>(sel - heading);  // :37-38
-                        ht.x = sel;
-                        if (dyn == CAV_DYN_UNICYCLE) {  // turning_dir, :42-47
-                            T td = ht.w;
-                            if (M<T>::abs_(td) < (T)1e-5) {
-                                td = (T)0.11 * sign<T>(sel);
-                            } else if (td * sel < (T)0) {
-                                T v = -td + sel;
-                                v = v < pi<T>() ? v : pi<T>();
-                                v = v > -pi<T>() ? v : -pi<T>();
-                                td = v;
-                            } else {
-                                T m = M<T>::abs_(td) - (T)0.1;
-                                m = m > (T)0 ? m : (T)0.0;
-                                td = sign<T>(td) * m;
-                            }
-                            ht.w = td;
-                        }
-                    }
-                    R4<T> ego;
-                    T vex, vey;
-                    update_ego<T>(pv, gl, ht.x, ego, vex, vey);  // agent.py:227
-                    if (b.aux0) st4(reinterpret_cast<R4<T> *>(b.aux0) + gi, R4<T>{speed_out, dhead_out, vex, vey});
-                    const int sn = b.step_num[gi];
-                    if (p.store_history && b.history && sn < p.history_len) {  // agent.py:257-260,275-289
-                        T *row = reinterpret_cast<T *>(b.history) + ((size_t)gi * p.history_len + sn) * CAV_HISTORY_ROW;
-                        const T v[CAV_HISTORY_ROW] = {ht.z, pv.x, pv.y, gl.x, gl.y, gl.z, gl.w, pv.z, pv.w,
-                                                      (dyn != CAV_DYN_EXTERNAL) ? a0 : speed_out, ht.x, ht.z, ego.x, ego.y};
-                        store_history_row(row, v);
-                    }
-                    // _check_if_at_goal, agent.py:150-153
-                    const T ex = pv.x - gl.x, ey = pv.y - gl.y;
-                    if (ex * ex + ey * ey <= p.near_goal_thr * p.near_goal_thr) f |= CAV_FLAG_AT_GOAL;
-                    else f &= ~CAV_FLAG_AT_GOAL;
-                    if (b.past_vel) {
-                        R4<T> *pvel = reinterpret_cast<R4<T> *>(b.past_vel) + gi;
-                        R4<T> q = ld4(pvel);
-                        q.z = q.x;
-                        q.w = q.y;
-                        q.x = pv.z;
-                        q.y = pv.w;
-                        st4(pvel, q);
-                    }
-                    ht.y -= dt;  // agent.py:235-239
-                    ht.z += dt;
-                    b.step_num[gi] = sn + 1;
-                    if (ht.y <= (T)0) f |= CAV_FLAG_RAN_OUT_OF_TIME;
-                    st4(g_pv + gi, pv);
-                    st4(g_ht + gi, ht);
-                    st4(g_ego + gi, ego);
-                    b.flags[gi] = f;
-                }
-            }
+            if (phases & PH_MOVE) tpa_move<T>(b, p, gi, pv, gl, ht, f, kind, act, have_act, dt);
+
         }
         __syncthreads();  // shared memory is re-staged by the next tile
     }

@@ -10,6 +10,7 @@
 // transposition network (no shared-memory round trips, no divergence), and the N-1 observation rows are independent
 // as well.  Used for the default observation layout (6 scalars then the (N-1) x 7 neighbour rows, closest_first,
 // K = N-1); every other configuration takes the generic kernel.  Arithmetic is identical to the generic kernel.
+#include "cav_orca_tpa.cuh"
 #include "cav_tpa_common.cuh"
 
 namespace cav {
@@ -300,6 +301,263 @@ __global__ void __launch_bounds__(128, TpaNBounds<T>::MINB) k_pairwise_obs_tpa_n
         __syncthreads();
     }
 }
+
+// =============================================================================================================
+// policy + move with compile-time N (reference env.py:304-327; same contract as k_policy_move_tpa in cav_tpa.cu)
+// =============================================================================================================
+// ORCA with everything unrolled: the N-1 neighbour keys are ordered by an odd-even transposition network in
+// registers, the N-1 half-planes (each with its own sqrt / divide chains) are built as independent instruction
+// streams into registers, and linearProgram2 / linearProgram1 (RVO2 Agent.cpp:477-581) run as straight-line
+// predicated code over those registers.  Only the rare infeasible case (linearProgram3, Agent.cpp:583-630) spills the
+// lines to shared memory and takes the generic routine.
+template <int NO>
+__device__ __forceinline__ void orca_tpa_n(int n, int ego, const float4 *s_f4, const float *s_frad, float prefx,
+                                           float prefy, float maxSpeed, float timeHorizon, float timeStep, float collab,
+                                           float neighborDist, int maxNeighbors, SmemLines slines, float &nvx, float &nvy) {
+    const float4 me = s_f4[ego];
+    const float rad_me = s_frad[ego];
+    unsigned long long key[NO > 0 ? NO : 1];
+    int nn = 0;
+    const bool any = maxNeighbors > 0 && collab > 0.0f;
+    const float rangeSq = neighborDist * neighborDist;
+#pragma unroll
+    for (int j = 0; j < NO; ++j) {
+        const int o = j + (j >= ego ? 1 : 0);
+        key[j] = ~0ull;
+        if (any && o < n) {
+            const float4 ot = s_f4[o];
+            const float dx = me.x - ot.x, dy = me.y - ot.y;  // absSq(position_ - agent->position_), Agent.cpp:427
+            const float distSq = fdot(dx, dy, dx, dy);
+            if (distSq < rangeSq) {
+                key[j] = ((unsigned long long)__float_as_uint(distSq) << 32) | (unsigned)o;
+                ++nn;
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < NO; ++r) {
+#pragma unroll
+        for (int i = (r & 1); i + 1 < NO; i += 2) {
+            const unsigned long long ka = key[i], kb = key[i + 1];
+            const bool sw = kb < ka;
+            key[i] = sw ? kb : ka;
+            key[i + 1] = sw ? ka : kb;
+        }
+    }
+    if (nn > maxNeighbors) nn = maxNeighbors;
+    const float invTimeHorizon = 1.0f / timeHorizon;
+    Line ln[NO > 0 ? NO : 1];
+#pragma unroll
+    for (int k = 0; k < NO; ++k) {
+        ln[k] = Line{0.f, 0.f, 1.f, 0.f};
+        if (k < nn) {
+            const int o = (int)(key[k] & 0xffffffffull);
+            ln[k] = orca_line(me, rad_me, s_f4[o], s_frad[o], invTimeHorizon, timeStep, collab);
+        }
+    }
+    // linearProgram2 (Agent.cpp:550-581), closest-point mode
+    float rx, ry;
+    if (fdot(prefx, prefy, prefx, prefy) > maxSpeed * maxSpeed) {
+        const float inv = 1.0f / sqrtf(fdot(prefx, prefy, prefx, prefy));
+        rx = (prefx * inv) * maxSpeed;
+        ry = (prefy * inv) * maxSpeed;
+    } else {
+        rx = prefx;
+        ry = prefy;
+    }
+    int fail = -1;
+#pragma unroll
+    for (int i = 0; i < NO; ++i) {
+        if (fail < 0 && i < nn && fdet(ln[i].dx, ln[i].dy, ln[i].px - rx, ln[i].py - ry) > 0.0f) {
+            // linearProgram1 on line i (Agent.cpp:477-548)
+            const Line L = ln[i];
+            const float dotProduct = fdot(L.px, L.py, L.dx, L.dy);
+            const float discriminant = dotProduct * dotProduct + maxSpeed * maxSpeed - fdot(L.px, L.py, L.px, L.py);
+            bool ok = !(discriminant < 0.0f);
+            const float sqrtDiscriminant = sqrtf(discriminant);
+            float tLeft = -dotProduct - sqrtDiscriminant;
+            float tRight = -dotProduct + sqrtDiscriminant;
+#pragma unroll
+            for (int j = 0; j < i; ++j) {
+                const float denominator = fdet(L.dx, L.dy, ln[j].dx, ln[j].dy);
+                const float numerator = fdet(ln[j].dx, ln[j].dy, L.px - ln[j].px, L.py - ln[j].py);
+                if (fabsf(denominator) <= CAV_RVO_EPSILON) {
+                    if (numerator < 0.0f) ok = false;
+                } else {
+                    const float t = numerator / denominator;
+                    if (denominator >= 0.0f) tRight = min_keep(tRight, t);
+                    else tLeft = max_keep(tLeft, t);
+                }
+            }
+            // the reference returns false as soon as tLeft > tRight inside the loop; the bounds only tighten, so the
+            // final comparison is equivalent
+            if (ok && !(tLeft > tRight)) {
+                const float t = fdot(L.dx, L.dy, prefx - L.px, prefy - L.py);
+                const float tc = (t < tLeft) ? tLeft : ((t > tRight) ? tRight : t);
+                rx = L.px + tc * L.dx;
+                ry = L.py + tc * L.dy;
+            } else {
+                fail = i;
+            }
+        }
+    }
+    if (fail >= 0) {  // rare: infeasible -> linearProgram3 through shared memory (generic routine)
+#pragma unroll
+        for (int k = 0; k < NO; ++k)
+            if (k < nn) slines.set(k, ln[k]);
+        tpa_lp3(slines, nn, fail, maxSpeed, rx, ry);
+    }
+    nvx = rx;
+    nvy = ry;
+}
+
+// measured at 16384 x 10 (policy+move kernel): float32 61 us with a 5-CTA cap vs 67 us generic (caps 4 / 6: 69 / 65);
+// float64 70 us vs 69 us generic, so float64 keeps the generic kernel by default (CAV_TPA_N_POLICY=1 forces this one)
+template <typename T>
+struct TpaNBoundsA {
+    static constexpr int MINB = 5;
+};
+
+template <typename T, int NT>
+__global__ void __launch_bounds__(128, TpaNBoundsA<T>::MINB) k_policy_move_tpa_n(TpaBuffers b, KParams<T> p,
+                                                                                   const float *__restrict__ ext,
+                                                                                   int phases, T dt, int EPB, int ntiles) {
+    constexpr int NO = NT - 1;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int cap = EPB * NT;
+    const int nt = blockDim.x;
+    unsigned char *sp = smem_raw;
+    float4 *s_f4 = reinterpret_cast<float4 *>(sp);
+    sp += a16(sizeof(float4) * cap);
+    float4 *s_lines = reinterpret_cast<float4 *>(sp);  // [NO][nt], only touched by the linearProgram3 fallback
+    sp += a16(sizeof(float4) * (size_t)(NO > 0 ? NO : 1) * nt);
+    float *s_frad = reinterpret_cast<float *>(sp);
+    sp += a16(sizeof(float) * cap);
+    int *s_n = reinterpret_cast<int *>(sp);
+
+    const int tid = threadIdx.x;
+    const R4<T> *g_pv = reinterpret_cast<const R4<T> *>(b.pv);
+    R4<T> *g_goal = reinterpret_cast<R4<T> *>(b.goal);
+    const R4<T> *g_ht = reinterpret_cast<const R4<T> *>(b.ht);
+    const R4<T> *g_ego = reinterpret_cast<const R4<T> *>(b.ego);
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int e0 = tile * EPB;
+        const int ne = min(EPB, p.E - e0);
+        const int count = ne * NT;
+        const size_t base = (size_t)e0 * NT;
+        const bool have = tid < count;
+        const size_t gi = base + tid;
+        R4<T> pv{}, gl{}, ht{};
+        uint32_t f = 0, kind = 0;
+        if (have) {
+            pv = ld4(g_pv + gi);
+            gl = ld4(g_goal + gi);
+            ht = ld4(g_ht + gi);
+            f = b.flags[gi];
+            kind = b.kinds[gi];
+            s_f4[tid] = make_float4((float)pv.x, (float)pv.y, (float)pv.z, (float)pv.w);  // RVOPolicy.py:57-74
+            s_frad[tid] = (float)(p.rvo_radius_scale * gl.z);
+        }
+        if (tid < ne) s_n[tid] = b.num_active ? b.num_active[e0 + tid] : NT;
+        __syncthreads();
+
+        const int el = tid / NT, a = tid - el * NT;
+        if (have && a < s_n[el]) {
+            const int n = s_n[el];
+            const int eb = el * NT;
+            float2 act = make_float2(0.f, 0.f);
+            bool have_act = false;
+            if ((phases & 1) && !(f & CAV_FLAG_DONE)) {  // action selection (env.py:310-323)
+                const uint32_t pol = CAV_KIND_POLICY(kind);
+                T a0 = (T)0, a1 = (T)0;
+                if (pol == CAV_POLICY_RVO) {
+                    const T gx = gl.x - pv.x, gy = gl.y - pv.y;  // RVOPolicy.py:66
+                    const T nrm = M<T>::sqrt_(gx * gx + gy * gy);
+                    const T sc = gl.w / nrm;  // :67
+                    const float prefx = (float)(sc * gx), prefy = (float)(sc * gy);
+                    float nvx, nvy;
+                    orca_tpa_n<NO>(n, a, s_f4 + eb, s_frad + eb, prefx, prefy, (float)gl.w, p.rvo_inv_time_horizon_num,
+                                   p.rvo_time_step, p.rvo_collab, p.rvo_neighbor_dist, p.rvo_max_neighbors,
+                                   SmemLines{s_lines + tid, nt}, nvx, nvy);
+                    // Agent::update (Agent.cpp:470-475) in float, then RVOPolicy.py:96-111 in `real`
+                    const float4 me = s_f4[tid];
+                    const float npx = me.x + nvx * p.rvo_time_step, npy = me.y + nvy * p.rvo_time_step;
+                    const T dpx = (T)npx - pv.x, dpy = (T)npy - pv.y;
+                    const T ang1 = M<T>::atan2_(dpy, dpx);
+                    const T new_heading = pymod<T>(ang1 - (T)0, two_pi<T>());
+                    T dh = wrap<T>(new_heading - ht.x);
+                    T spd = p.rvo_inv_dt * M<T>::sqrt_(dpx * dpx + dpy * dpy);
+                    if (M<T>::abs_(dh) > p.rvo_max_delta_heading) {
+                        dh = sign<T>(dh) * p.rvo_max_delta_heading;
+                        spd = (T)0;
+                    }
+                    a0 = spd;
+                    a1 = dh;
+                } else if (pol == CAV_POLICY_NONCOOP) {  // NonCooperativePolicy.py:21
+                    a0 = gl.w;
+                    a1 = -ld4(g_ego + gi).y;
+                } else if (pol == CAV_POLICY_STATIC) {  // StaticPolicy.py:21-22: goal := pos
+                    gl.x = pv.x;
+                    gl.y = pv.y;
+                    st4(g_goal + gi, gl);
+                } else if (pol == CAV_POLICY_EXTERNAL) {  // ExternalPolicy.py:14-16
+                    const float2 x = ext ? reinterpret_cast<const float2 *>(ext)[gi] : make_float2(0.f, 0.f);
+                    a0 = (T)x.x;
+                    a1 = (T)x.y;
+                } else {  // CAV_POLICY_LEARNING, LearningPolicy.py:30-32
+                    const float2 x = ext ? reinterpret_cast<const float2 *>(ext)[gi] : make_float2(0.f, 0.f);
+                    a1 = p.max_heading_change * ((T)2. * (T)x.y - (T)1.);
+                    a0 = gl.w * (T)x.x;
+                }
+                act = make_float2((float)a0, (float)a1);  // float32 store, env.py:305-307
+                have_act = true;
+                reinterpret_cast<float2 *>(b.actions)[gi] = act;
+            }
+            if (phases & 2) tpa_move<T>(b, p, gi, pv, gl, ht, f, kind, act, have_act, dt);
+        }
+        __syncthreads();
+    }
+}
+
+template <typename T, int NT>
+static cudaError_t launch_pm_n(const cav_buffers_t &bufs, const KParams<T> &p, const float *ext, int phases, double dt,
+                               int sm_count, cudaStream_t st) {
+    int EPB = 128 / NT;
+    if (EPB < 1) EPB = 1;
+    const int threads = ((EPB * NT + 31) / 32) * 32;
+    const int ntiles = (p.E + EPB - 1) / EPB;
+    const int cap = EPB * NT;
+    const size_t smem = a16(sizeof(float4) * cap) + a16(sizeof(float4) * (size_t)(NT > 1 ? NT - 1 : 1) * threads) +
+                        a16(sizeof(float) * cap) + a16(sizeof(int) * EPB) + 64;
+    const int grid = ntiles < sm_count * 16 ? ntiles : sm_count * 16;
+    k_policy_move_tpa_n<T, NT><<<grid, threads, smem, st>>>(make_tpa(bufs), p, ext, phases, (T)dt, EPB, ntiles);
+    return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t run_policy_move_tpa_n(const cav_buffers_t &bufs, const KParams<T> &p, const float *ext, int phases, double dt,
+                                  int sm_count, cudaStream_t st) {
+    switch (p.N) {
+#define CAV_CASE(NN) \
+    case NN: return launch_pm_n<T, NN>(bufs, p, ext, phases, dt, sm_count, st);
+        CAV_CASE(2)
+        CAV_CASE(3)
+        CAV_CASE(4)
+        CAV_CASE(5)
+        CAV_CASE(6)
+        CAV_CASE(8)
+        CAV_CASE(10)
+        CAV_CASE(12)
+#undef CAV_CASE
+        default: return cudaErrorNotSupported;
+    }
+}
+
+template cudaError_t run_policy_move_tpa_n<float>(const cav_buffers_t &, const KParams<float> &, const float *, int,
+                                                  double, int, cudaStream_t);
+template cudaError_t run_policy_move_tpa_n<double>(const cav_buffers_t &, const KParams<double> &, const float *, int,
+                                                   double, int, cudaStream_t);
 
 // true when the plan is the default layout this kernel hard-codes
 static bool standard_layout(const ObsPlan &plan, const KParams<float> *, int N, int K, int obs_len, int sorting) {

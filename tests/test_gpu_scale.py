@@ -286,3 +286,40 @@ def test_max_turn_rate_and_external_dynamics_vs_oracle(mapping, monkeypatch):
         common.compare_states(r.download(), hs, N, 1e-9, 1e-9)
     assert clipped > 50
     assert np.array_equal(hs.pv[:, 3, :2], p0)  # ExternalDynamics agents are not moved by the step
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("N", [2, 5, 10, 12])
+def test_compile_time_n_kernels_forced_on_and_off(N, prec, monkeypatch):
+    """The compile-time-N kernels (cav_tpa_n.cu) and the generic thread-per-agent kernels run the same arithmetic:
+    one dense bank through all four on/off combinations must give bit-identical states, and (float64) the oracle's
+    to 1e-9.  float32 is only compared across kernels here: with a dense bank a heading change can land within one
+    ulp of the reference's turn-in-place threshold (RVOPolicy.py:101-104), where CUDA's and glibc's atan2f differ."""
+    from gpu_common import GpuRunner
+    E = 64
+    c = to_cav_config(make_config(N, evaluate=True), E, N, precision=prec, track_aux=True)
+    bank = _bank(E, N, seed=300 + N, dense=True)
+    first = None
+    for pol_n in ("0", "1"):
+        for obs_n in ("0", "1"):
+            monkeypatch.setenv("CAV_TPA_N_POLICY", pol_n)
+            monkeypatch.setenv("CAV_TPA_N", obs_n)
+            hs = HostState(c)
+            orc = Oracle(c)
+            orc.reset(hs, bank)
+            r = GpuRunner(c)
+            trace = []
+            for s in range(6):
+                r.upload(hs)
+                orc.step(hs)
+                r.cav.step()
+                got = r.download()
+                if prec == "f64":
+                    common.compare_states(got, hs, N, 1e-9, 1e-9)
+                trace.append(got)
+            r.cav.close()
+            if first is None:
+                first = trace
+            else:
+                for a, b in zip(first, trace):
+                    common.compare_states(b, a, N, 0.0, 0.0)

@@ -1,11 +1,11 @@
 #!/bin/bash
-# A/B experiment helper: run bench.py with alternative builds of the library (gpurun_libs/*.so)
+# A/B experiment helper: run bench.py with alternative builds of the library (gpurun_libs/*.so); $PREC = f64|f32
 orig=gym_collision_avoidance_b200/csrc/libcavoid_sm100a.so
 cp $orig /tmp/orig.so
 for lib in "$@"; do
-  cp $lib $orig
+  [ "$lib" != "$orig" ] && cp $lib $orig
   echo "== $lib"
-  CAV_TPA_N=1 python bench.py --no-cpu-baseline --steps 50 --warmup 10 2>/dev/null | tail -1 | python -c "
+  python bench.py --no-cpu-baseline --steps 50 --warmup 10 --precision ${PREC:-f64} 2>/dev/null | tail -1 | python -c "
 import json,sys
 d=json.loads(sys.stdin.read())
 print('%.3e'%d['value'], round(d['ms_per_step']*1e3,1), round(d['roofline']['kernel_ms']*1e3,1), round(d['roofline']['policy_move_kernel_ms']*1e3,1), round(d['roofline']['frac'],3))"
