@@ -325,9 +325,10 @@ def run_ours(a):
                        "cuda_graph": not a.no_graph},
             "wall_ms_per_step_incl_flush": t_wall / a.steps * 1e3,
             "clocks": clocks,
-            "e2e": {"value": e2e_val, "unit": "agent-steps/s", "h2d_bytes_per_step": env.h2d_bytes_per_step,
-                    "d2h_bytes_per_step": env.d2h_bytes_per_step, "steps": e2e_steps},
-            "gpu_launches": launches,
+            "e2e": {"value": e2e_val, "unit": "agent-steps/s", "h2d_bytes_per_step": world * env.h2d_bytes_per_step,
+                    "d2h_bytes_per_step": world * env.d2h_bytes_per_step, "bytes_scope": "whole job (all ranks)",
+                    "steps": e2e_steps},
+            "gpu_launches": world * launches,
             "roofline": {"kernel": "k_pairwise_obs (fused pairwise collision+reward+sorted-neighbour obs+done)",
                          "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": measured_traffic(a), "peak_source": peak_src, "bytes_per_agent_step": bpa,

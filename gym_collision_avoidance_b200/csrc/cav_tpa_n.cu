@@ -10,6 +10,8 @@
 // transposition network (no shared-memory round trips, no divergence), and the N-1 observation rows are independent
 // as well.  Used for the default observation layout (6 scalars then the (N-1) x 7 neighbour rows, closest_first,
 // K = N-1); every other configuration takes the generic kernel.  Arithmetic is identical to the generic kernel.
+#include <type_traits>
+
 #include "cav_orca_tpa.cuh"
 #include "cav_tpa_common.cuh"
 
@@ -18,61 +20,84 @@ namespace cav {
 // Resident CTAs per SM the compiler must allow.  float64 at N = 10 wants 138 registers unconstrained (3 CTAs / SM);
 // capping at 5 CTAs (<= 102 registers, ~170 B of spills) measured best at 16384 x 10: 44.8 us vs 51.3 (1), 49.1 (4),
 // 48.0 (6) and 49.8 for the generic kernel.  float32 needs 96 registers unconstrained, i.e. 5 CTAs already.
+#ifndef CAV_TPA_N_MINB_F32
+#define CAV_TPA_N_MINB_F32 5
+#endif
 template <typename T>
 struct TpaNBounds {
-    static constexpr int MINB = 1;
+    static constexpr int MINB = CAV_TPA_N_MINB_F32;
 };
 template <>
 struct TpaNBounds<double> {
     static constexpr int MINB = 5;
 };
 
+// Thread mapping: environments never straddle a warp.  A warp owns EPW = 32 / N consecutive environments, i.e. the
+// LW = EPW * N consecutive agents starting at (first env) * N; lanes >= LW idle (2 of 32 at N = 10).  Everything a lane
+// needs from other agents is in its own warp, so there is no block barrier anywhere: neighbour states are exchanged
+// through a per-warp shared-memory slice behind __syncwarp, game_over is three ballots.  (ncu on the block-wide
+// version: a quarter of all stall samples sat behind the two __syncthreads, and its one partially filled warp per CTA
+// spent more instructions in the predicated copy-out than the three full warps together.)
+//
+// Observation stores: the LW agents' packed rows are ONE contiguous block of LW * CL values in HBM.  Each lane writes
+// its own row into the warp's staging slice [LW][WS] (WS odd: conflict-free), then the warp streams the slice out with
+// consecutive lanes on consecutive addresses -- 128 B (float32) / 256 B (float64) per store instruction, the whole
+// 8 KB block in 65 stores instead of ~100 partial-row ones.  float64 stages the row in two column ranges to keep the
+// slice at 8 KB per warp (5 CTAs / SM).
+template <typename T, int NT>
+struct TpaNShape {
+    static constexpr int NO = NT - 1;
+    static constexpr int EPW = 32 / NT;
+    static constexpr int LW = EPW * NT;
+    static constexpr int CL = 6 + 7 * NO;
+    static constexpr int P = (sizeof(T) == 8 && NO >= 2) ? 2 : 1;  // staging passes
+    static constexpr int RA = P == 1 ? NO : NO / 2;                // neighbour rows in pass 0
+    static constexpr int W0 = 6 + 7 * RA;
+    static constexpr int W1 = 7 * (NO - RA);
+    static constexpr int WM = W0 > W1 ? W0 : W1;
+    static constexpr int WS = WM | 1;                               // staging row stride, odd
+    static constexpr int WARPS = 4;
+    static constexpr int EPB = WARPS * EPW;
+    static constexpr size_t r16(size_t x) { return (x + 15) & ~(size_t)15; }
+    static constexpr size_t WARP_BYTES = r16(sizeof(R4<T>) * LW) + r16(sizeof(T) * LW) + r16(sizeof(T) * LW * WS);
+};
+
 template <typename T, int NT>
 __global__ void __launch_bounds__(128, TpaNBounds<T>::MINB) k_pairwise_obs_tpa_n(TpaBuffers b, KParams<T> p, WallMap wm,
                                                               const uint8_t *__restrict__ env_mask, int obs_only,
-                                                              int EPB, int ntiles) {
-    constexpr int NO = NT - 1;  // neighbours = observation rows
-    constexpr int CW = TpaChunk<T>::CW;
-    constexpr int AST = CW + 1;
-    constexpr int APL = 32 / CW;
-    constexpr int ROWS0 = (CW - 6) / 7;                   // rows that fit next to the 6 scalars in chunk 0
-    constexpr int RPC = CW / 7;                           // rows per later chunk
-    constexpr int CL = 6 + 7 * NO;                        // packed observation length
+                                                              int ntiles) {
+    using S = TpaNShape<T, NT>;
+    constexpr int NO = S::NO, EPW = S::EPW, LW = S::LW, CL = S::CL, WS = S::WS, RA = S::RA;
     constexpr int KSHIFT = KeyCodec<T>::PB + 6;
+    constexpr unsigned LWMASK = LW >= 32 ? 0xffffffffu : ((1u << LW) - 1u);
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int cap = EPB * NT;
-    const int nt = blockDim.x;
-    unsigned char *sp = smem_raw;
-    R4<T> *s_pv = reinterpret_cast<R4<T> *>(sp);
-    sp += a16(sizeof(R4<T>) * cap);
-    T *s_rad = reinterpret_cast<T *>(sp);
-    sp += a16(sizeof(T) * cap);
-    T *s_arena = reinterpret_cast<T *>(sp);  // [nwarps][32][AST]
-    sp += a16(sizeof(T) * (size_t)(nt >> 5) * 32 * AST);
-    uint8_t *s_done = reinterpret_cast<uint8_t *>(sp);
-    sp += a16((size_t)cap);
-    int *s_n = reinterpret_cast<int *>(sp);
-
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    T *arena = s_arena + (size_t)warp * 32 * AST;
+    unsigned char *sp = smem_raw + (size_t)warp * S::WARP_BYTES;
+    R4<T> *s_pv = reinterpret_cast<R4<T> *>(sp);
+    sp += a16(sizeof(R4<T>) * LW);
+    T *s_rad = reinterpret_cast<T *>(sp);
+    sp += a16(sizeof(T) * LW);
+    T *stage = reinterpret_cast<T *>(sp);  // [LW][WS]
     const R4<T> *g_pv = reinterpret_cast<const R4<T> *>(b.pv);
     const R4<T> *g_goal = reinterpret_cast<const R4<T> *>(b.goal);
     const R4<T> *g_ego = reinterpret_cast<const R4<T> *>(b.ego);
     T *g_obs = reinterpret_cast<T *>(b.obs);
     T *g_reward = reinterpret_cast<T *>(b.reward);
     T *g_mind = reinterpret_cast<T *>(b.min_dist);
+    const int el = lane / NT, h = lane - el * NT;  // env within the warp, agent within the env
+    const int eb = el * NT;
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int e0 = tile * EPB;
-        const int ne = min(EPB, p.E - e0);
-        const int count = ne * NT;
-        const size_t base = (size_t)e0 * NT;
-        const bool have = tid < count;
-        const size_t gi = base + tid;
+        const int ew0 = (tile * S::WARPS + warp) * EPW;  // first environment of this warp
+        const int e = ew0 + el;
+        const bool have = lane < LW && e < p.E;
+        const size_t wbase = (size_t)ew0 * NT;
+        const size_t gi = wbase + lane;
         R4<T> pvh{}, glh{}, egh{};
         uint32_t f = 0, kind = 0;
         float adh = 0.f;
+        int n = -1;
         if (have) {
             pvh = ld4(g_pv + gi);
             glh = ld4(g_goal + gi);
@@ -80,25 +105,20 @@ __global__ void __launch_bounds__(128, TpaNBounds<T>::MINB) k_pairwise_obs_tpa_n
             f = b.flags[gi];
             kind = b.kinds[gi];
             adh = b.actions[2 * gi + 1];
-            s_pv[tid] = pvh;
-            s_rad[tid] = glh.z;
+            n = b.num_active ? b.num_active[e] : NT;
+            if (env_mask && !env_mask[e]) n = -1;
+            s_pv[lane] = pvh;
+            s_rad[lane] = glh.z;
         }
-        if (tid < ne) {
-            int n = b.num_active ? b.num_active[e0 + tid] : NT;
-            if (env_mask && !env_mask[e0 + tid]) n = -1;
-            s_n[tid] = n;
-        }
-        __syncthreads();
+        __syncwarp();
 
-        const int el = have ? tid / NT : 0, h = tid - el * NT;
-        const int n = have ? s_n[el] : -1;
         const bool active = have && h < n;
-        const int eb = el * NT;
         const T prx = egh.z, pry = egh.w;
         const T orx = -pry, ory = prx;  // ref_orth, agent.py:347
         unsigned long long key[NO > 0 ? NO : 1];
         T dcv[NO > 0 ? NO : 1];
         int nc = 0;
+        bool done_now = false;
         if (active) {
             T md = M<T>::inf();
             bool coll = false;
@@ -196,19 +216,35 @@ __global__ void __launch_bounds__(128, TpaNBounds<T>::MINB) k_pairwise_obs_tpa_n
                 r = r < p.reward_min ? p.reward_min : (r > p.reward_max ? p.reward_max : r);  // np.clip
                 g_reward[gi] = r;
                 if (g_mind) g_mind[gi] = md;
-                const bool d = (f & (CAV_FLAG_AT_GOAL | CAV_FLAG_RAN_OUT_OF_TIME | CAV_FLAG_IN_COLLISION)) != 0;
-                f = d ? (f | CAV_FLAG_DONE) : (f & ~(uint32_t)CAV_FLAG_DONE);
+                done_now = (f & (CAV_FLAG_AT_GOAL | CAV_FLAG_RAN_OUT_OF_TIME | CAV_FLAG_IN_COLLISION)) != 0;
+                f = done_now ? (f | CAV_FLAG_DONE) : (f & ~(uint32_t)CAV_FLAG_DONE);
                 b.flags[gi] = f;
-                b.done[gi] = d ? 1 : 0;
-                s_done[tid] = d ? 1 : 0;
+                b.done[gi] = done_now ? 1 : 0;
             }
         }
-        // ---- packed observation through the per-warp arena; chunk boundaries are compile-time constants ----
         const unsigned vmask = __ballot_sync(0xffffffffu, active);
+        // ---- game_over (env.py:538-551): per environment, from ballots over its N lanes ----
+        if (!obs_only) {
+            const unsigned dmask = __ballot_sync(0xffffffffu, active && done_now);
+            const unsigned lmask = __ballot_sync(0xffffffffu, active && CAV_KIND_POLICY(kind) == CAV_POLICY_LEARNING);
+            const unsigned pmask = __ballot_sync(0xffffffffu, have && n >= 0);  // environment taking part in this launch
+            if (lane < EPW) {
+                const int sh = lane * NT;
+                const unsigned em = (NT >= 32 ? 0xffffffffu : ((1u << NT) - 1u)) << sh;
+                if ((pmask >> sh) & 1u) {
+                    const unsigned open = vmask & ~dmask & em;  // live agents that are not done
+                    bool go;
+                    if (p.game_over_mode == CAV_GAME_OVER_ALL_DONE) go = open == 0u;
+                    else if (p.game_over_mode == CAV_GAME_OVER_AGENT0) go = ((dmask >> sh) & 1u) != 0u;
+                    else go = (open & lmask) == 0u;
+                    b.game_over[ew0 + lane] = go ? 1 : 0;
+                }
+            }
+        }
+        // ---- packed observation through the warp's staging slice ----
         if (vmask != 0u) {
-            T *gwarp = g_obs + (base + (size_t)(warp << 5)) * (size_t)CL;
-            const int sub = lane / CW, kk = lane - sub * CW;
-            T *my = arena + lane * AST;
+            T *gwarp = g_obs + wbase * (size_t)CL;
+            T *my = stage + lane * WS;
             auto fill_row = [&](int r, T *dst) {  // r is a compile-time constant at every call site
                 if (r < nc) {
                     const int o = (int)(key[r] & 63ull);
@@ -227,78 +263,57 @@ __global__ void __launch_bounds__(128, TpaNBounds<T>::MINB) k_pairwise_obs_tpa_n
                     for (int k = 0; k < 7; ++k) dst[k] = (T)0;  // zero rows (:108)
                 }
             };
-            auto copy_out = [&](int c0, int len) {
+            // columns [c0, c0 + W) of every agent of the warp: element idx = agent * W + column
+            auto stream_out = [&](auto c0_, auto w_) {
+                constexpr int c0 = decltype(c0_)::value, W = decltype(w_)::value;
+                constexpr int TOT = LW * W;
                 __syncwarp();
-                if (kk < len) {
-                    const T *src = arena + sub * AST + kk;
-                    T *dst = gwarp + sub * CL + c0 + kk;
-                    if (vmask == 0xffffffffu) {
-#pragma unroll 4
-                        for (int j = sub; j < 32; j += APL) {
-                            *dst = *src;
-                            src += APL * AST;
-                            dst += APL * CL;
+                if (vmask == LWMASK) {
+#pragma unroll 8
+                    for (int i0 = 0; i0 < TOT; i0 += 32) {
+                        const int idx = i0 + lane;
+                        if (idx < TOT) {
+                            if (W == CL && WS == CL) {
+                                gwarp[idx] = stage[idx];
+                            } else {
+                                const int j = idx / W, k = idx - j * W;
+                                gwarp[j * CL + c0 + k] = stage[j * WS + k];
+                            }
                         }
-                    } else {
+                    }
+                } else {  // ragged / masked environments: inactive agents keep their old observation
 #pragma unroll 1
-                        for (int j = sub; j < 32; j += APL) {
-                            if ((vmask >> j) & 1u) *dst = *src;
-                            src += APL * AST;
-                            dst += APL * CL;
+                    for (int i0 = 0; i0 < TOT; i0 += 32) {
+                        const int idx = i0 + lane;
+                        if (idx < TOT) {
+                            const int j = idx / W, k = idx - j * W;
+                            if ((vmask >> j) & 1u) gwarp[j * CL + c0 + k] = stage[j * WS + k];
                         }
                     }
                 }
                 __syncwarp();
             };
-            // chunk 0: the six scalars (agent.py:323-327, default STATES_IN_OBS order) + the first ROWS0 rows
-            {
-                constexpr int R0 = ROWS0 < NO ? ROWS0 : NO;
-                if (active) {
-                    my[0] = (CAV_KIND_POLICY(kind) == CAV_POLICY_LEARNING) ? (T)1 : (T)0;  // is_learning
-                    my[1] = (T)nc;                                                          // num_other_agents
-                    my[2] = egh.x;                                                          // dist_to_goal
-                    my[3] = egh.y;                                                          // heading_ego_frame
-                    my[4] = glh.w;                                                          // pref_speed
-                    my[5] = glh.z;                                                          // radius
+            // pass 0: the six scalars (agent.py:323-327, default STATES_IN_OBS order) + rows [0, RA)
+            if (active) {
+                my[0] = (CAV_KIND_POLICY(kind) == CAV_POLICY_LEARNING) ? (T)1 : (T)0;  // is_learning
+                my[1] = (T)nc;                                                          // num_other_agents
+                my[2] = egh.x;                                                          // dist_to_goal
+                my[3] = egh.y;                                                          // heading_ego_frame
+                my[4] = glh.w;                                                          // pref_speed
+                my[5] = glh.z;                                                          // radius
 #pragma unroll
-                    for (int r = 0; r < R0; ++r) fill_row(r, my + 6 + 7 * r);
-                }
-                copy_out(0, 6 + 7 * R0);
+                for (int r = 0; r < RA; ++r) fill_row(r, my + 6 + 7 * r);
             }
-            // later chunks: RPC rows each
-#pragma unroll
-            for (int rb = ROWS0; rb < NO; rb += RPC) {
-                const int rows = (NO - rb) < RPC ? (NO - rb) : RPC;
+            stream_out(std::integral_constant<int, 0>{}, std::integral_constant<int, S::W0>{});
+            if (S::P == 2) {  // pass 1: rows [RA, NO)
                 if (active) {
 #pragma unroll
-                    for (int q = 0; q < RPC; ++q)
-                        if (q < rows) fill_row(rb + q, my + 7 * q);
+                    for (int r = RA; r < NO; ++r) fill_row(r, my + 7 * (r - RA));
                 }
-                copy_out(6 + 7 * rb, 7 * rows);
+                stream_out(std::integral_constant<int, S::W0>{}, std::integral_constant<int, (S::W1 > 0 ? S::W1 : 1)>{});
             }
         }
-        // ---- game_over (env.py:538-551) ----
-        if (!obs_only) {
-            __syncthreads();
-            if (tid < ne && s_n[tid] >= 0) {
-                const int nn = s_n[tid];
-                bool all_done = true, all_learning_done = true;
-                for (int a = 0; a < nn; ++a) {
-                    const bool d = s_done[tid * NT + a] != 0;
-                    if (!d) {
-                        all_done = false;
-                        if (CAV_KIND_POLICY(b.kinds[base + (size_t)tid * NT + a]) == CAV_POLICY_LEARNING)
-                            all_learning_done = false;
-                    }
-                }
-                bool go;
-                if (p.game_over_mode == CAV_GAME_OVER_ALL_DONE) go = all_done;
-                else if (p.game_over_mode == CAV_GAME_OVER_AGENT0) go = s_done[tid * NT] != 0;
-                else go = all_learning_done;
-                b.game_over[e0 + tid] = go ? 1 : 0;
-            }
-        }
-        __syncthreads();
+        __syncwarp();
     }
 }
 
@@ -574,16 +589,17 @@ static bool standard_layout(const ObsPlan &plan, const KParams<float> *, int N, 
 template <typename T, int NT>
 static cudaError_t launch_n(const cav_buffers_t &bufs, const KParams<T> &p, const WallMap &wm, const uint8_t *env_mask,
                             int obs_only, int sm_count, cudaStream_t st) {
-    int EPB = 128 / NT;
-    if (EPB < 1) EPB = 1;
-    const int threads = ((EPB * NT + 31) / 32) * 32;
-    const int ntiles = (p.E + EPB - 1) / EPB;
-    const int cap = EPB * NT;
-    const size_t smem = a16(sizeof(R4<T>) * cap) + a16(sizeof(T) * cap) +
-                        a16(sizeof(T) * (size_t)(threads / 32) * 32 * (TpaChunk<T>::CW + 1)) + a16((size_t)cap) +
-                        a16(sizeof(int) * EPB) + 64;
+    using S = TpaNShape<T, NT>;
+    const int ntiles = (p.E + S::EPB - 1) / S::EPB;
+    const size_t smem = S::WARP_BYTES * S::WARPS;
+    static bool attr_set = false;
+    if (!attr_set && smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_pairwise_obs_tpa_n<T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
     const int grid = ntiles < sm_count * 16 ? ntiles : sm_count * 16;
-    k_pairwise_obs_tpa_n<T, NT><<<grid, threads, smem, st>>>(make_tpa(bufs), p, wm, env_mask, obs_only, EPB, ntiles);
+    k_pairwise_obs_tpa_n<T, NT><<<grid, 32 * S::WARPS, smem, st>>>(make_tpa(bufs), p, wm, env_mask, obs_only, ntiles);
     return cudaGetLastError();
 }
 

@@ -5,13 +5,14 @@ import csv
 import sys
 
 
-def main(path, which=-1, top=40):
+def main(path, filt=None, top=40):
     rows = list(csv.reader(open(path)))
     segs, cur = [], None
     for r in rows:
         if r and r[0] == "Kernel Name":
             cur = []
-            segs.append(cur)
+            if filt is None or filt in ",".join(r[1:]):
+                segs.append(cur)
             continue
         if cur is not None:
             cur.append(r)
@@ -38,4 +39,4 @@ def main(path, which=-1, top=40):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1])
+    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else None, int(sys.argv[3]) if len(sys.argv) > 3 else 40)
