@@ -16,7 +16,7 @@ CSRC = os.path.join(PKG, "csrc")
 ROOT = os.path.dirname(PKG)
 OUT = os.path.join(CSRC, "libcavoid_sm100a.so")
 SOURCES = ["cav_step.cu", "cav_tpa.cu", "cav_tpa_n.cu", "cav_laser.cu", "cav_reset.cu", "cav_abi.cu"]
-HEADERS = ["cav_common.cuh", "cav_orca.cuh", "cav_orca_tpa.cuh", "cav_tpa_common.cuh", "cav_kernels.h", os.path.join(ROOT, "include", "cavoid.h")]
+HEADERS = ["cav_common.cuh", "cav_orca.cuh", "cav_orca_tpa.cuh", "cav_tpa_common.cuh", "cav_sortnet.cuh", "cav_kernels.h", os.path.join(ROOT, "include", "cavoid.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
          "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
@@ -35,6 +35,7 @@ def build(force=False, verbose=False):
     if not force and not _stale():
         return OUT
     extra = ["-Xptxas", "-v"] if verbose else []
+    extra += os.environ.get("CAV_NVCC_EXTRA", "").split()  # tuning experiments only (e.g. -DCAV_TPA_N_MINB_F32=6)
 
     def cc(src):
         obj = os.path.join(CSRC, src.replace(".cu", ".o"))

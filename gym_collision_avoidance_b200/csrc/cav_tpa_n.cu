@@ -13,6 +13,7 @@
 #include <type_traits>
 
 #include "cav_orca_tpa.cuh"
+#include "cav_sortnet.cuh"
 #include "cav_tpa_common.cuh"
 
 namespace cav {
@@ -58,8 +59,10 @@ struct TpaNShape {
     static constexpr int WS = WM | 1;                               // staging row stride, odd
     static constexpr int WARPS = 4;
     static constexpr int EPB = WARPS * EPW;
+    // float32, single pass, staging stride == packed row length: the slice is a flat image of the HBM block
+    static constexpr bool FLAT4 = sizeof(T) == 4 && P == 1 && WS == CL;
     static constexpr size_t r16(size_t x) { return (x + 15) & ~(size_t)15; }
-    static constexpr size_t WARP_BYTES = r16(sizeof(R4<T>) * LW) + r16(sizeof(T) * LW) + r16(sizeof(T) * LW * WS);
+    static constexpr size_t WARP_BYTES = r16(sizeof(R4<T>) * LW) + r16(sizeof(T) * LW) + r16(sizeof(T) * (LW * WS + 4));
 };
 
 template <typename T, int NT>
@@ -78,7 +81,7 @@ __global__ void __launch_bounds__(128, TpaNBounds<T>::MINB) k_pairwise_obs_tpa_n
     sp += a16(sizeof(R4<T>) * LW);
     T *s_rad = reinterpret_cast<T *>(sp);
     sp += a16(sizeof(T) * LW);
-    T *stage = reinterpret_cast<T *>(sp);  // [LW][WS]
+    T *const stage0 = reinterpret_cast<T *>(sp);  // [LW][WS] (+ up to 3 values of phase shift, see FLAT4)
     const R4<T> *g_pv = reinterpret_cast<const R4<T> *>(b.pv);
     const R4<T> *g_goal = reinterpret_cast<const R4<T> *>(b.goal);
     const R4<T> *g_ego = reinterpret_cast<const R4<T> *>(b.ego);
@@ -145,20 +148,16 @@ __global__ void __launch_bounds__(128, TpaNBounds<T>::MINB) k_pairwise_obs_tpa_n
                     }
                 }
             }
-            // ---- order: branch-free odd-even transposition network on (key, dc) in registers ----
-#pragma unroll
-            for (int r = 0; r < NO; ++r) {
-#pragma unroll
-                for (int i = (r & 1); i + 1 < NO; i += 2) {
-                    const bool sw = key[i + 1] < key[i];
-                    const unsigned long long ka = key[i], kb = key[i + 1];
-                    const T da = dcv[i], db = dcv[i + 1];
-                    key[i] = sw ? kb : ka;
-                    key[i + 1] = sw ? ka : kb;
-                    dcv[i] = sw ? db : da;
-                    dcv[i + 1] = sw ? da : db;
-                }
-            }
+            // ---- order: branch-free sorting network on (key, dc) in registers (keys are distinct: index bits) ----
+            sort_network<NO>([&](int i, int j) {
+                const bool sw = key[j] < key[i];
+                const unsigned long long ka = key[i], kb = key[j];
+                const T da = dcv[i], db = dcv[j];
+                key[i] = sw ? kb : ka;
+                key[j] = sw ? ka : kb;
+                dcv[i] = sw ? db : da;
+                dcv[j] = sw ? da : db;
+            });
             // exact re-comparison inside runs of equal kint (truncated p_orth / clamped kint, see KeyCodec): rare
             bool tie = false;
 #pragma unroll
@@ -244,6 +243,9 @@ __global__ void __launch_bounds__(128, TpaNBounds<T>::MINB) k_pairwise_obs_tpa_n
         // ---- packed observation through the warp's staging slice ----
         if (vmask != 0u) {
             T *gwarp = g_obs + wbase * (size_t)CL;
+            // FLAT4: shift the slice so that shared and global addresses agree modulo 16 bytes (obs is 16-byte aligned)
+            const int mis = S::FLAT4 ? (int)((wbase * (size_t)CL) & 3) : 0;
+            T *stage = stage0 + mis;
             T *my = stage + lane * WS;
             auto fill_row = [&](int r, T *dst) {  // r is a compile-time constant at every call site
                 if (r < nc) {
@@ -268,18 +270,30 @@ __global__ void __launch_bounds__(128, TpaNBounds<T>::MINB) k_pairwise_obs_tpa_n
                 constexpr int c0 = decltype(c0_)::value, W = decltype(w_)::value;
                 constexpr int TOT = LW * W;
                 __syncwarp();
-                if (vmask == LWMASK) {
-#pragma unroll 8
-                    for (int i0 = 0; i0 < TOT; i0 += 32) {
-                        const int idx = i0 + lane;
-                        if (idx < TOT) {
-                            if (W == CL && WS == CL) {
-                                gwarp[idx] = stage[idx];
-                            } else {
-                                const int j = idx / W, k = idx - j * W;
-                                gwarp[j * CL + c0 + k] = stage[j * WS + k];
-                            }
-                        }
+                if (vmask == LWMASK && S::FLAT4) {
+                    // one contiguous block, same 16-byte phase in shared and global memory: 128-bit body
+                    const int head = (4 - mis) & 3;
+                    if (lane < head) gwarp[lane] = stage[lane];
+                    const float4 *src4 = reinterpret_cast<const float4 *>(stage + head);
+                    float4 *dst4 = reinterpret_cast<float4 *>(gwarp + head);
+                    const int nvec = (TOT - head) >> 2;
+#pragma unroll
+                    for (int v0 = 0; v0 < TOT / 4; v0 += 32) {
+                        const int v = v0 + lane;
+                        if (v < nvec) dst4[v] = src4[v];
+                    }
+                    const int t = head + 4 * nvec + lane;
+                    if (t < TOT) gwarp[t] = stage[t];
+                } else if (vmask == LWMASK) {
+                    // element idx = 32 t + lane sits in agent row j = idx / W; W > 32, so j is q_t or q_t + 1 with
+                    // compile-time q_t and a per-lane carry (no division in the unrolled code)
+#pragma unroll
+                    for (int t = 0; t < (TOT + 31) / 32; ++t) {
+                        const int idx = 32 * t + lane;
+                        int j;
+                        if (W > 32) j = (32 * t) / W + ((lane >= W - (32 * t) % W) ? 1 : 0);
+                        else j = idx / W;
+                        if (idx < TOT) gwarp[idx + c0 + j * (CL - W)] = stage[idx + j * (WS - W)];
                     }
                 } else {  // ragged / masked environments: inactive agents keep their old observation
 #pragma unroll 1
@@ -349,16 +363,12 @@ __device__ __forceinline__ void orca_tpa_n(int n, int ego, const float4 *s_f4, c
             }
         }
     }
-#pragma unroll
-    for (int r = 0; r < NO; ++r) {
-#pragma unroll
-        for (int i = (r & 1); i + 1 < NO; i += 2) {
-            const unsigned long long ka = key[i], kb = key[i + 1];
-            const bool sw = kb < ka;
-            key[i] = sw ? kb : ka;
-            key[i + 1] = sw ? ka : kb;
-        }
-    }
+    sort_network<NO>([&](int i, int j) {
+        const unsigned long long ka = key[i], kb = key[j];
+        const bool sw = kb < ka;
+        key[i] = sw ? kb : ka;
+        key[j] = sw ? ka : kb;
+    });
     if (nn > maxNeighbors) nn = maxNeighbors;
     const float invTimeHorizon = 1.0f / timeHorizon;
     Line ln[NO > 0 ? NO : 1];
