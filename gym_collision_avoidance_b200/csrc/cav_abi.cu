@@ -230,7 +230,7 @@ int cav_create(const cav_config_t *cfg, cav_handle_t *out) {
         // measured at 16384 x 10: float32 33 us vs 38 us generic; float64 45 us vs 50 us generic
         h->use_tpa_n = h->use_tpa;
         if (const char *ev = getenv("CAV_TPA_N")) h->use_tpa_n = h->use_tpa && atoi(ev) != 0;
-        h->use_tpa_n_policy = h->use_tpa && cfg->precision == CAV_F32;
+        h->use_tpa_n_policy = h->use_tpa;
         if (const char *ev = getenv("CAV_TPA_N_POLICY")) h->use_tpa_n_policy = h->use_tpa && atoi(ev) != 0;
     }
     cudaError_t ce = cudaGetDevice(&h->device);

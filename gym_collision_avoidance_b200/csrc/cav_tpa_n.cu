@@ -63,6 +63,10 @@ struct TpaNShape {
     static constexpr bool FLAT4 = sizeof(T) == 4 && P == 1 && WS == CL;
     static constexpr size_t r16(size_t x) { return (x + 15) & ~(size_t)15; }
     static constexpr size_t WARP_BYTES = r16(sizeof(R4<T>) * LW) + r16(sizeof(T) * LW) + r16(sizeof(T) * (LW * WS + 4));
+    // policy kernel slice: float4 state [LW], linearProgram3 scratch lines [NO][32], float radius [LW]
+    static constexpr size_t PM_F4 = r16(sizeof(float4) * LW);
+    static constexpr size_t PM_LINES = r16(sizeof(float4) * (NO > 0 ? NO : 1) * 32);
+    static constexpr size_t PM_WARP_BYTES = PM_F4 + PM_LINES + r16(sizeof(float) * LW);
 };
 
 template <typename T, int NT>
@@ -436,61 +440,65 @@ __device__ __forceinline__ void orca_tpa_n(int n, int ego, const float4 *s_f4, c
     nvy = ry;
 }
 
-// measured at 16384 x 10 (policy+move kernel): float32 61 us with a 5-CTA cap vs 67 us generic (caps 4 / 6: 69 / 65);
-// float64 70 us vs 69 us generic, so float64 keeps the generic kernel by default (CAV_TPA_N_POLICY=1 forces this one)
+// Register cap expressed as resident 128-thread-equivalents per SM (5 -> <= 102 registers).  Measured at 16384 x 10:
+// float32 61 us with 5 vs 69 / 65 us with 4 / 6; with single-warp CTAs float64 68 us vs 74 us for the generic kernel.
 template <typename T>
 struct TpaNBoundsA {
     static constexpr int MINB = 5;
 };
 
+#ifndef CAV_TPA_NA_WARPS
+#define CAV_TPA_NA_WARPS 1
+#endif
+// Same warp-aligned mapping as k_pairwise_obs_tpa_n (TpaNShape): a warp owns whole environments, neighbour states go
+// through its own shared-memory slice behind __syncwarp, no block barrier.  ORCA run times vary a lot between warps
+// (linearProgram1 / 3 calls are data dependent), so CTAs are single warps: a finished warp frees its registers at once
+// instead of idling behind its CTA's slowest warp (16384 x 10, float64: 62 us vs 65 us with 4-warp CTAs).
 template <typename T, int NT>
-__global__ void __launch_bounds__(128, TpaNBoundsA<T>::MINB) k_policy_move_tpa_n(TpaBuffers b, KParams<T> p,
-                                                                                   const float *__restrict__ ext,
-                                                                                   int phases, T dt, int EPB, int ntiles) {
-    constexpr int NO = NT - 1;
+__global__ void __launch_bounds__(32 * CAV_TPA_NA_WARPS, (TpaNBoundsA<T>::MINB * 4) / CAV_TPA_NA_WARPS)
+    k_policy_move_tpa_n(TpaBuffers b, KParams<T> p, const float *__restrict__ ext, int phases, T dt, int ntiles) {
+    using S = TpaNShape<T, NT>;
+    constexpr int NO = S::NO, EPW = S::EPW, LW = S::LW;
+    constexpr int WARPS = CAV_TPA_NA_WARPS;
+    constexpr size_t WB = S::PM_WARP_BYTES;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int cap = EPB * NT;
-    const int nt = blockDim.x;
-    unsigned char *sp = smem_raw;
-    float4 *s_f4 = reinterpret_cast<float4 *>(sp);
-    sp += a16(sizeof(float4) * cap);
-    float4 *s_lines = reinterpret_cast<float4 *>(sp);  // [NO][nt], only touched by the linearProgram3 fallback
-    sp += a16(sizeof(float4) * (size_t)(NO > 0 ? NO : 1) * nt);
-    float *s_frad = reinterpret_cast<float *>(sp);
-    sp += a16(sizeof(float) * cap);
-    int *s_n = reinterpret_cast<int *>(sp);
-
     const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    unsigned char *sp = smem_raw + (size_t)warp * WB;
+    float4 *s_f4 = reinterpret_cast<float4 *>(sp);
+    sp += S::PM_F4;
+    float4 *s_lines = reinterpret_cast<float4 *>(sp);  // [NO][32], only touched by the linearProgram3 fallback
+    sp += S::PM_LINES;
+    float *s_frad = reinterpret_cast<float *>(sp);
+
     const R4<T> *g_pv = reinterpret_cast<const R4<T> *>(b.pv);
     R4<T> *g_goal = reinterpret_cast<R4<T> *>(b.goal);
     const R4<T> *g_ht = reinterpret_cast<const R4<T> *>(b.ht);
     const R4<T> *g_ego = reinterpret_cast<const R4<T> *>(b.ego);
+    const int el = lane / NT, a = lane - el * NT;
+    const int eb = el * NT;
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int e0 = tile * EPB;
-        const int ne = min(EPB, p.E - e0);
-        const int count = ne * NT;
-        const size_t base = (size_t)e0 * NT;
-        const bool have = tid < count;
-        const size_t gi = base + tid;
+        const int ew0 = (tile * WARPS + warp) * EPW;
+        const int e = ew0 + el;
+        const bool have = lane < LW && e < p.E;
+        const size_t gi = (size_t)ew0 * NT + lane;
         R4<T> pv{}, gl{}, ht{};
         uint32_t f = 0, kind = 0;
+        int n = 0;
         if (have) {
             pv = ld4(g_pv + gi);
             gl = ld4(g_goal + gi);
             ht = ld4(g_ht + gi);
             f = b.flags[gi];
             kind = b.kinds[gi];
-            s_f4[tid] = make_float4((float)pv.x, (float)pv.y, (float)pv.z, (float)pv.w);  // RVOPolicy.py:57-74
-            s_frad[tid] = (float)(p.rvo_radius_scale * gl.z);
+            n = b.num_active ? b.num_active[e] : NT;
+            s_f4[lane] = make_float4((float)pv.x, (float)pv.y, (float)pv.z, (float)pv.w);  // RVOPolicy.py:57-74
+            s_frad[lane] = (float)(p.rvo_radius_scale * gl.z);
         }
-        if (tid < ne) s_n[tid] = b.num_active ? b.num_active[e0 + tid] : NT;
-        __syncthreads();
+        __syncwarp();
 
-        const int el = tid / NT, a = tid - el * NT;
-        if (have && a < s_n[el]) {
-            const int n = s_n[el];
-            const int eb = el * NT;
+        if (have && a < n) {
             float2 act = make_float2(0.f, 0.f);
             bool have_act = false;
             if ((phases & 1) && !(f & CAV_FLAG_DONE)) {  // action selection (env.py:310-323)
@@ -504,9 +512,9 @@ __global__ void __launch_bounds__(128, TpaNBoundsA<T>::MINB) k_policy_move_tpa_n
                     float nvx, nvy;
                     orca_tpa_n<NO>(n, a, s_f4 + eb, s_frad + eb, prefx, prefy, (float)gl.w, p.rvo_inv_time_horizon_num,
                                    p.rvo_time_step, p.rvo_collab, p.rvo_neighbor_dist, p.rvo_max_neighbors,
-                                   SmemLines{s_lines + tid, nt}, nvx, nvy);
+                                   SmemLines{s_lines + lane, 32}, nvx, nvy);
                     // Agent::update (Agent.cpp:470-475) in float, then RVOPolicy.py:96-111 in `real`
-                    const float4 me = s_f4[tid];
+                    const float4 me = s_f4[lane];
                     const float npx = me.x + nvx * p.rvo_time_step, npy = me.y + nvy * p.rvo_time_step;
                     const T dpx = (T)npx - pv.x, dpy = (T)npy - pv.y;
                     const T ang1 = M<T>::atan2_(dpy, dpx);
@@ -541,22 +549,20 @@ __global__ void __launch_bounds__(128, TpaNBoundsA<T>::MINB) k_policy_move_tpa_n
             }
             if (phases & 2) tpa_move<T>(b, p, gi, pv, gl, ht, f, kind, act, have_act, dt);
         }
-        __syncthreads();
+        __syncwarp();
     }
 }
 
 template <typename T, int NT>
 static cudaError_t launch_pm_n(const cav_buffers_t &bufs, const KParams<T> &p, const float *ext, int phases, double dt,
                                int sm_count, cudaStream_t st) {
-    int EPB = 128 / NT;
-    if (EPB < 1) EPB = 1;
-    const int threads = ((EPB * NT + 31) / 32) * 32;
-    const int ntiles = (p.E + EPB - 1) / EPB;
-    const int cap = EPB * NT;
-    const size_t smem = a16(sizeof(float4) * cap) + a16(sizeof(float4) * (size_t)(NT > 1 ? NT - 1 : 1) * threads) +
-                        a16(sizeof(float) * cap) + a16(sizeof(int) * EPB) + 64;
-    const int grid = ntiles < sm_count * 16 ? ntiles : sm_count * 16;
-    k_policy_move_tpa_n<T, NT><<<grid, threads, smem, st>>>(make_tpa(bufs), p, ext, phases, (T)dt, EPB, ntiles);
+    using S = TpaNShape<T, NT>;
+    constexpr int WARPS = CAV_TPA_NA_WARPS;
+    const int epb = WARPS * S::EPW;
+    const int ntiles = (p.E + epb - 1) / epb;
+    const size_t smem = WARPS * S::PM_WARP_BYTES;
+    const int grid = ntiles < sm_count * 64 ? ntiles : sm_count * 64;
+    k_policy_move_tpa_n<T, NT><<<grid, 32 * WARPS, smem, st>>>(make_tpa(bufs), p, ext, phases, (T)dt, ntiles);
     return cudaGetLastError();
 }
 
