@@ -14,7 +14,7 @@ from .policies.LearningPolicy import LearningPolicy
 from .policies.NonCooperativePolicy import NonCooperativePolicy
 from .policies.RVOPolicy import RVOPolicy
 from .policies.StaticPolicy import StaticPolicy
-from .scenarios import _circle_case, _rand_case, _swap_case
+from .scenarios import reference_test_case
 from .sensors.LaserScanSensor import LaserScanSensor
 from .sensors.OtherAgentsStatesSensor import OtherAgentsStatesSensor
 
@@ -70,14 +70,9 @@ def cadrl_test_case_to_agents(test_case, policies="RVO", policy_distr=None, agen
 
 
 def generate_rand_test_case_multi(num_agents, side_length, speed_bnds, radius_bnds):
-    """Reference ``gen_rand_testcases.py:111-142`` (15 % swap / 15 % circle / 70 % random), NumPy global RNG."""
-    rng = np.random
-    u = rng.rand()
-    if u < 0.15:
-        return _swap_case(rng, num_agents, side_length, speed_bnds, radius_bnds)
-    if u < 0.3:
-        return _circle_case(rng, num_agents, side_length, speed_bnds, radius_bnds)
-    return _rand_case(rng, num_agents, side_length, speed_bnds, radius_bnds)
+    """Reference ``gen_rand_testcases.py:111-142`` (15 % swap / 15 % circle / 70 % random) on NumPy's global stream:
+    after ``np.random.seed(s)`` this returns the reference's rows bit for bit (tests/test_scenarios_cpu.py)."""
+    return reference_test_case(np.random, num_agents, side_length, speed_bnds, radius_bnds)
 
 
 def get_testcase_random(num_agents=None, side_length=4, speed_bnds=(0.5, 2.0), radius_bnds=(0.2, 0.8),

@@ -98,13 +98,3 @@ def test_config_defaults_match_reference_semantics():
     with pytest.raises(abi.CavoidError):
         m.STATES_IN_OBS = ["dist_to_goal", "other_agents_states_encoded"]
         cfgmod.obs_layout(m)
-
-
-def test_scenario_bank_respects_separation():
-    from gym_collision_avoidance_b200.envs.scenarios import random_scenario_bank, GETTING_CLOSE_RANGE
-    b = random_scenario_bank(64, 10, seed=3, mix=(0.0, 0.0))
-    for s in range(64):
-        p, r = b[s, :, 0:2], b[s, :, 5]
-        d = np.linalg.norm(p[:, None] - p[None], axis=-1) + np.eye(10) * 1e9
-        assert (d >= r[:, None] + r[None] + GETTING_CLOSE_RANGE - 1e-12).all()
-    assert np.allclose(b[..., 6], np.arctan2(b[..., 3] - b[..., 1], b[..., 2] - b[..., 0]))
