@@ -97,11 +97,16 @@ class CavScenarioBank(ctypes.Structure):
     _fields_ = [("rows", _vp), ("kinds", _vp), ("num_active", _vp), ("num_scenarios", _i), ("reserved", _i)]
 
 
+class CavScenarioGen(ctypes.Structure):
+    _fields_ = [("seed", ctypes.c_uint64), ("side_length", ctypes.c_double * 2), ("speed_bnds", ctypes.c_double * 2),
+                ("radius_bnds", ctypes.c_double * 2)]
+
+
 # every symbol include/cavoid.h declares
 EXPORTED_SYMBOLS = [
     "cav_abi_version", "cav_create", "cav_real_bytes", "cav_workspace_bytes", "cav_bind", "cav_reset", "cav_step",
     "cav_k_policy", "cav_k_dynamics", "cav_k_pairwise_obs", "cav_k_laserscan", "cav_k_observe",
-    "cav_last_launch_count",
+    "cav_generate_scenarios", "cav_last_launch_count",
     "cav_last_error", "cav_destroy",
 ]
 
@@ -151,6 +156,8 @@ def load_library(path=None):
     L.cav_k_observe.restype = ctypes.c_int
     L.cav_k_observe.argtypes = [h, _vp, _vp]
     L.cav_last_launch_count.restype = ctypes.c_int
+    L.cav_generate_scenarios.restype = ctypes.c_int
+    L.cav_generate_scenarios.argtypes = [h, ctypes.POINTER(CavScenarioGen), _vp, _vp, ctypes.c_int32, _vp]
     L.cav_last_launch_count.argtypes = [h]
     L.cav_last_error.restype = ctypes.c_char_p
     L.cav_last_error.argtypes = [h]

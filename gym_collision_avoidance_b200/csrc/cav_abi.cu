@@ -384,6 +384,24 @@ int cav_reset(cav_handle_t h, const uint8_t *env_mask, const cav_scenario_bank_t
     return rc;
 }
 
+int cav_generate_scenarios(cav_handle_t h, const cav_scenario_gen_t *gen, double *rows, int32_t *case_kind,
+                           int32_t num_scenarios, cav_stream_t stream) {
+    if (!h) return CAV_ERR_NULL_POINTER;
+    if (!gen || !rows) return fail(h, CAV_ERR_NULL_POINTER, "cav_generate_scenarios: gen / rows is NULL");
+    if (num_scenarios < 1) return fail(h, CAV_ERR_BAD_CONFIG, "cav_generate_scenarios: num_scenarios < 1");
+    if (!(gen->side_length[0] > 0.0) || gen->side_length[1] < gen->side_length[0] ||
+        !(gen->speed_bnds[0] > 0.0) || gen->speed_bnds[1] < gen->speed_bnds[0] || !(gen->radius_bnds[0] > 0.0) ||
+        gen->radius_bnds[1] < gen->radius_bnds[0])
+        return fail(h, CAV_ERR_BAD_CONFIG, "cav_generate_scenarios: bounds must be positive and ordered");
+    if ((reinterpret_cast<uintptr_t>(rows) & 7u) != 0) return fail(h, CAV_ERR_MISALIGNED, "cav_generate_scenarios: rows misaligned");
+    h->launches = 1;
+    CAV_CUDA(h, "generate_scenarios",
+             run_generate_scenarios(rows, case_kind, num_scenarios, h->cfg.num_agents, gen->seed, gen->side_length[0],
+                                    gen->side_length[1], gen->speed_bnds, gen->radius_bnds, 0.2 /* GETTING_CLOSE_RANGE,
+                                    CADRL/scripts/multi/global_var.py:8 */, (cudaStream_t)stream));
+    return CAV_OK;
+}
+
 int cav_step(cav_handle_t h, const float *ext_actions, double dt, cav_stream_t stream) {
     CAV_CHECK_READY(h, "cav_step");
     cudaStream_t st = (cudaStream_t)stream;

@@ -54,4 +54,9 @@ cudaError_t run_reset(const cav_buffers_t &bufs, const ResetParams &rp, const ui
                       const cav_scenario_bank_t &bank, const int32_t *scenario_idx, int accumulate_stats,
                       cudaStream_t st);
 
+// device-side scenario banks (cav_scenario.cu)
+cudaError_t run_generate_scenarios(double *rows, int32_t *kind_out, int S, int N, uint64_t seed, double side_lo,
+                                   double side_hi, const double speed_bnds[2], const double radius_bnds[2],
+                                   double close_range, cudaStream_t st);
+
 }  // namespace cav

@@ -83,6 +83,15 @@ class DeviceBank(object):
         self.num_active = None if na is None else torch.from_numpy(na).to(device)
         self.num_scenarios = r.shape[0]
 
+    @classmethod
+    def empty(cls, num_scenarios, num_agents, device="cuda"):
+        """Uninitialised bank for `Cavoid.generate_scenarios` to fill."""
+        b = cls.__new__(cls)
+        b.rows = torch.zeros((num_scenarios, num_agents, abi.CAV_BANK_ROW), dtype=torch.float64, device=device)
+        b.kinds, b.num_active, b.num_scenarios = None, None, int(num_scenarios)
+        b.case_kind = torch.zeros((num_scenarios,), dtype=torch.int32, device=device)
+        return b
+
     def struct(self):
         s = abi.CavScenarioBank()
         s.rows = self.rows.data_ptr()
@@ -137,6 +146,27 @@ class Cavoid(object):
         self._check(self.L.cav_reset(self._h, _ptr(env_mask), ctypes.byref(bs), _ptr(scenario_idx),
                                      int(accumulate_stats), self._stream(stream)), "cav_reset")
         self.launches += self.L.cav_last_launch_count(self._h)
+
+    def generate_scenarios(self, bank, seed, side_length=None, speed_bnds=(0.5, 2.0), radius_bnds=(0.2, 0.8),
+                           stream=None):
+        """Fill `bank.rows` on the device with reference-distributed random scenarios (cav_generate_scenarios).
+        side_length = (lo, hi) of the uniform side draw; default: the reference's Config.TEST_CASE_ARGS."""
+        n = self.c.num_agents
+        if side_length is None:
+            side_length = (4.0, 5.0) if n < 5 else (6.0, 8.0)
+        g = abi.CavScenarioGen()
+        g.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        g.side_length[0], g.side_length[1] = float(side_length[0]), float(side_length[1])
+        g.speed_bnds[0], g.speed_bnds[1] = float(speed_bnds[0]), float(speed_bnds[1])
+        g.radius_bnds[0], g.radius_bnds[1] = float(radius_bnds[0]), float(radius_bnds[1])
+        if tuple(bank.rows.shape[1:]) != (n, abi.CAV_BANK_ROW) or bank.rows.dtype != torch.float64:
+            raise abi.CavoidError("bank rows must be float64 [S, %d, %d]" % (n, abi.CAV_BANK_ROW))
+        ck = getattr(bank, "case_kind", None)
+        self._check(self.L.cav_generate_scenarios(self._h, ctypes.byref(g), bank.rows.data_ptr(), _ptr(ck),
+                                                  int(bank.num_scenarios), self._stream(stream)),
+                    "cav_generate_scenarios")
+        self.launches += self.L.cav_last_launch_count(self._h)
+        return bank
 
     def k_policy(self, ext_actions=None, stream=None):
         self._check(self.L.cav_k_policy(self._h, _ptr(ext_actions), self._stream(stream)), "cav_k_policy")

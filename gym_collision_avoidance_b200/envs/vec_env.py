@@ -47,7 +47,8 @@ class VecCollisionAvoidanceEnv(object):
 
     def __init__(self, num_envs, config=None, num_agents=None, device="cuda:0", precision="f64", scenario_bank=None,
                  bank_kinds=None, bank_num_active=None, policies="RVO", dynamics="unicycle", auto_reset=True,
-                 use_cuda_graph=True, history_len=0, track_aux=False, seed=0, num_scenarios=None):
+                 use_cuda_graph=True, history_len=0, track_aux=False, seed=0, num_scenarios=None,
+                 scenario_source="host"):
         if config is None:
             config = _config.make_config(num_agents or 10, evaluate=True)
         self.config = config
@@ -58,16 +59,31 @@ class VecCollisionAvoidanceEnv(object):
         self.c = _config.to_cav_config(config, self.num_envs, self.num_agents, precision=precision,
                                        history_len=history_len, track_aux=track_aux)
         self.obs_offsets, self.obs_len = _config.obs_layout(config)
-        if scenario_bank is None:
-            S = num_scenarios or max(256, min(4096, self.num_envs))
-            scenario_bank = random_scenario_bank(S, self.num_agents, seed=seed)
-        scenario_bank = np.asarray(scenario_bank, dtype=np.float64)
-        S = scenario_bank.shape[0]
-        if bank_kinds is None:
-            bank_kinds = kinds_array(S, self.num_agents, policies, dynamics)
+        if scenario_source not in ("host", "device"):
+            raise ValueError("scenario_source must be 'host' or 'device'")
+        self.scenario_source = scenario_source
         torch.cuda.set_device(self.device)
         self.cav = Cavoid(self.c, self.device)
-        self.bank = DeviceBank(scenario_bank, kinds=bank_kinds, num_active=bank_num_active, device=self.device)
+        if scenario_source == "device" and scenario_bank is None:
+            # bank generated in HBM by cav_generate_scenarios (reference distribution, Philox stream); call
+            # regenerate_scenarios(seed) for fresh ones
+            S = num_scenarios or max(256, min(16384, self.num_envs))
+            self.bank = DeviceBank.empty(S, self.num_agents, device=self.device)
+            if bank_kinds is None:
+                bank_kinds = kinds_array(S, self.num_agents, policies, dynamics)
+            self.bank.kinds = torch.from_numpy(np.ascontiguousarray(bank_kinds).view(np.int32).copy()).to(self.device)
+            if bank_num_active is not None:
+                self.bank.num_active = torch.from_numpy(np.asarray(bank_num_active, np.int32)).to(self.device)
+            self.cav.generate_scenarios(self.bank, seed)
+        else:
+            if scenario_bank is None:
+                S = num_scenarios or max(256, min(4096, self.num_envs))
+                scenario_bank = random_scenario_bank(S, self.num_agents, seed=seed)
+            scenario_bank = np.asarray(scenario_bank, dtype=np.float64)
+            S = scenario_bank.shape[0]
+            if bank_kinds is None:
+                bank_kinds = kinds_array(S, self.num_agents, policies, dynamics)
+            self.bank = DeviceBank(scenario_bank, kinds=bank_kinds, num_active=bank_num_active, device=self.device)
         st = self.cav.state
         self.state = st
         self.ext_actions = torch.zeros((self.num_envs, self.num_agents, 2), dtype=torch.float32, device=self.device)
@@ -94,6 +110,13 @@ class VecCollisionAvoidanceEnv(object):
     @property
     def observation(self):
         return self.state.obs
+
+    def regenerate_scenarios(self, seed):
+        """Overwrite the bank in place with fresh device-generated scenarios (same buffers, so a captured step graph
+        stays valid); they take effect at the following resets."""
+        if not hasattr(self.bank, "case_kind"):
+            raise abi.CavoidError("regenerate_scenarios needs scenario_source='device'")
+        self.cav.generate_scenarios(self.bank, seed)
 
     def reset(self):
         """Reset every environment (reference ``reset`` -> ``_get_obs``); returns ``(obs, {})``."""

@@ -273,6 +273,23 @@ int cav_k_pairwise_obs(cav_handle_t h, cav_stream_t stream);
 int cav_k_laserscan(cav_handle_t h, cav_stream_t stream);
 int cav_k_observe(cav_handle_t h, const uint8_t *env_mask, cav_stream_t stream);
 
+/* Device-side scenario generation: fills `rows` ([num_scenarios * N * CAV_BANK_ROW] doubles, device) with what the
+ * reference's get_testcase_random (envs/test_cases.py:212-253) -> generate_rand_test_case_multi
+ * (policies/CADRL/scripts/multi/gen_rand_testcases.py:111-142: 15 % swap :322-377, 15 % circle :380-423, 70 %
+ * rejection-sampled random cases :144-233 incl. the straight-line test :425-444) would build, one scenario per
+ * thread, same draw sequence per scenario but from a Philox4x32-10 stream keyed by (seed, scenario): the rows follow
+ * the reference's DISTRIBUTION (statistical parity with the bit-exact host generator, tests/test_gpu_scenarios.py),
+ * not NumPy's MT19937 stream.  case_kind ([num_scenarios] device, may be NULL) receives 0 = swap, 1 = circle,
+ * 2 = random.  The result is a valid cav_scenario_bank_t.rows for cav_reset. */
+typedef struct cav_scenario_gen {
+    uint64_t seed;
+    double side_length[2]; /* side ~ U(lo, hi): Config.TEST_CASE_ARGS['side_length'] (config.py:56-59) */
+    double speed_bnds[2];  /* config.py:54 */
+    double radius_bnds[2]; /* config.py:55 */
+} cav_scenario_gen_t;
+int cav_generate_scenarios(cav_handle_t h, const cav_scenario_gen_t *gen, double *rows, int32_t *case_kind,
+                           int32_t num_scenarios, cav_stream_t stream);
+
 /* Number of kernels the last cav_step / cav_reset call on this handle enqueued (for launch accounting). */
 int cav_last_launch_count(cav_handle_t h);
 
