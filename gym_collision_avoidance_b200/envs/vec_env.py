@@ -90,6 +90,7 @@ class VecCollisionAvoidanceEnv(object):
         self.agent_dones = torch.zeros_like(st.done)  # which_agents_done of the step (kept across auto-reset)
         # pinned host mirrors for the host-buffer API
         self._h_actions = torch.zeros((self.num_envs, self.num_agents, 2), dtype=torch.float32).pin_memory()
+        self._h_actions_np = self._h_actions.numpy()
         # the host API hands observations / rewards out as float32, the dtype the reference's observation space
         # declares (Config.STATE_INFO_DICT[...]['dtype'] = np.float32, config.py:93-170); device tensors keep `real`
         self._d_obs32 = st.obs if st.obs.dtype == torch.float32 else torch.zeros_like(st.obs, dtype=torch.float32)
@@ -178,7 +179,12 @@ class VecCollisionAvoidanceEnv(object):
         """Host-buffer API: pinned-host actions in, pinned-host ``(obs, rewards, game_over, which_agents_done)``
         out (float32 obs / rewards; host<->device copies on the current stream, then one synchronize)."""
         if actions is not None:
-            self._h_actions.copy_(torch.as_tensor(actions, dtype=torch.float32).reshape(self._h_actions.shape))
+            # plain single-threaded memcpy into the pinned staging buffer: torch's CPU copy_ fans a 1.3 MB copy out
+            # over the intra-op thread pool, whose spinning workers then starve the CUDA graph launch (measured on
+            # the B200 host: 2.9 ms per step instead of 1.07 ms)
+            if isinstance(actions, torch.Tensor):
+                actions = actions.detach().cpu().numpy()
+            np.copyto(self._h_actions_np, np.asarray(actions, dtype=np.float32).reshape(self._h_actions_np.shape))
             self.ext_actions.copy_(self._h_actions, non_blocking=True)
         self._launch()
         self.steps += 1
