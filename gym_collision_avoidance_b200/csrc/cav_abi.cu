@@ -158,10 +158,9 @@ int cav_create(const cav_config_t *cfg, cav_handle_t *out) {
     if (!(cfg->dt > 0.0)) return fail(nullptr, CAV_ERR_BAD_CONFIG, "cav_create: dt must be > 0");
     if (cfg->max_num_other_agents_observed < 0 || cfg->obs_len < 1)
         return fail(nullptr, CAV_ERR_BAD_CONFIG, "cav_create: bad observation sizes");
-    if (cfg->agent_sorting_method != CAV_SORT_CLOSEST_FIRST && cfg->agent_sorting_method != CAV_SORT_CLOSEST_LAST)
-        return fail(nullptr, CAV_ERR_UNSUPPORTED,
-                    "cav_create: agent_sorting_method %d has no device implementation (closest_first / closest_last)",
-                    cfg->agent_sorting_method);
+    if (cfg->agent_sorting_method != CAV_SORT_CLOSEST_FIRST && cfg->agent_sorting_method != CAV_SORT_CLOSEST_LAST &&
+        cfg->agent_sorting_method != CAV_SORT_TIME_TO_IMPACT)
+        return fail(nullptr, CAV_ERR_BAD_CONFIG, "cav_create: unknown agent_sorting_method %d", cfg->agent_sorting_method);
     if (cfg->game_over_mode < 0 || cfg->game_over_mode > 2)
         return fail(nullptr, CAV_ERR_BAD_CONFIG, "cav_create: bad game_over_mode");
     if (cfg->rvo_collab_coeff < 0.0)
@@ -333,7 +332,8 @@ static WallMap wall_map(cav_handle_t h) {
 
 static int do_pairwise_obs(cav_handle_t h, const uint8_t *mask, int obs_only, cudaStream_t st) {
     const WallMap wm = wall_map(h);
-    if (h->use_tpa) {
+    // 'time_to_impact' ordering (three-level real key) lives in the sub-warp-group kernel only, for every N
+    if (h->use_tpa && h->cfg.agent_sorting_method != CAV_SORT_TIME_TO_IMPACT) {
         if (h->use_tpa_n) {  // compile-time-N specialisation when the configuration allows it
             const cudaError_t ce = (h->cfg.precision == CAV_F64)
                                        ? run_pairwise_obs_tpa_n<double>(h->bufs, h->pd, h->plan, wm, mask, obs_only, h->sm_count, st)

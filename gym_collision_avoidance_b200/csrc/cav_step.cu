@@ -312,13 +312,56 @@ __global__ void __launch_bounds__(512) k_policy_move(DevBuffers b, KParams<T> p,
 // =============================================================================================================
 template <typename T>
 struct ObsKey {
-    T kr;  // round(dist_2_other, 2) (OtherAgentsStatesSensor.py:103)
+    T tt;  // -time_to_impact for AGENT_SORTING_METHOD 'time_to_impact' (OtherAgentsStatesSensor.py:36-38), else 0
+    T kr;  // round(dist_2_other, 2) (:103); negated for 'time_to_impact' (key -x[1])
     T po;  // p_orthog_ego_frame
     int idx;
 };
+
+// util.compute_time_to_impact (util.py:23-79) with tangent_vecs_from_external_pt (:81-112), operation for operation
+// (same expression order as the oracle): host at (px,py) with velocity hv, other at (a,b) with velocity ov, r = the
+// combined radius.  Only + - * / sqrt, so the result is the reference's to the last bit in float64.
+template <typename T>
+__device__ T time_to_impact(T px, T py, T a, T b, T hvx, T hvy, T ovx, T ovy, T r) {
+    const T v0 = hvx - ovx, v1 = hvy - ovy;
+    const T sq = (px - a) * (px - a) + (py - b) * (py - b) - r * r;
+    if (sq < (T)0) return (T)0;  // already inside the collision zone
+    const T sqrt_term = M<T>::sqrt_(sq);
+    const T xnum1 = (r * r) * (px - a), xnum2 = r * (py - b) * sqrt_term;
+    const T ynum1 = (r * r) * (py - b), ynum2 = r * (px - a) * sqrt_term;
+    const T den = (px - a) * (px - a) + (py - b) * (py - b);
+    const T c1x = ((xnum1 + xnum2) / den + a) - px, c1y = ((ynum1 - ynum2) / den + b) - py;
+    const T c2x = ((xnum1 - xnum2) / den + a) - px, c2y = ((ynum1 + ynum2) / den + b) - py;
+    const T k1v = c1x * v1 - c1y * v0, k12 = c1x * c2y - c1y * c2x;
+    const T k2v = c2x * v1 - c2y * v0, k21 = c2x * c1y - c2y * c1x;
+    if (!(k1v * k12 >= (T)0 && k2v * k21 >= (T)0)) return M<T>::inf();  // v_rel outside the collision cone
+    if (M<T>::abs_(v0) < (T)1e-5 && M<T>::abs_(v1) < (T)1e-5) return M<T>::inf();
+    T x1, x2, y1, y2;
+    if (M<T>::abs_(v0) < (T)1e-5) {  // vertical v_rel
+        const T A = (T)1, B = (T)-2 * b, C = b * b + (px - a) * (px - a) - r * r;
+        x1 = x2 = px;
+        y1 = (-B + M<T>::sqrt_(B * B - (T)4 * A * C)) / ((T)2 * A);
+        y2 = (-B - M<T>::sqrt_(B * B - (T)4 * A * C)) / ((T)2 * A);
+    } else {
+        const T m = v1 / v0;
+        const T A = (T)1 + m * m;
+        const T B = (T)-2 * a + (T)2 * m * (py - b - m * px);
+        const T C = a * a - r * r + (m * px - (py - b)) * (m * px - (py - b));
+        x1 = (-B + M<T>::sqrt_(B * B - (T)4 * A * C)) / ((T)2 * A);
+        x2 = (-B - M<T>::sqrt_(B * B - (T)4 * A * C)) / ((T)2 * A);
+        y1 = m * (x1 - px) + py;
+        y2 = m * (x2 - px) + py;
+    }
+    const T d1 = M<T>::sqrt_((x1 - px) * (x1 - px) + (y1 - py) * (y1 - py));
+    const T d2 = M<T>::sqrt_((x2 - px) * (x2 - px) + (y2 - py) * (y2 - py));
+    const T d = d2 < d1 ? d2 : d1;  // Python min(d1, d2)
+    return d / M<T>::sqrt_(v0 * v0 + v1 * v1);
+}
 template <typename T>
 struct ObsKeyOps {
     static __device__ __forceinline__ bool less(const ObsKey<T> &a, const ObsKey<T> &b) {
+        if (a.tt < b.tt) return true;
+        if (a.tt > b.tt) return false;
         if (a.kr < b.kr) return true;
         if (a.kr > b.kr) return false;
         if (a.po < b.po) return true;
@@ -327,6 +370,7 @@ struct ObsKeyOps {
     }
     static __device__ __forceinline__ ObsKey<T> shfl_xor(unsigned gm, const ObsKey<T> &v, int j, int w) {
         ObsKey<T> o;
+        o.tt = __shfl_xor_sync(gm, v.tt, j, w);
         o.kr = __shfl_xor_sync(gm, v.kr, j, w);
         o.po = __shfl_xor_sync(gm, v.po, j, w);
         o.idx = __shfl_xor_sync(gm, v.idx, j, w);
@@ -412,6 +456,7 @@ __global__ void __launch_bounds__(512) k_pairwise_obs(DevBuffers b, KParams<T> p
                 for (int s = 0; s < SL; ++s) {
                     const int e = s * G + glane;
                     const int o = (e < h) ? e : e + 1;
+                    key[s].tt = M<T>::inf();
                     key[s].kr = M<T>::inf();
                     key[s].po = M<T>::inf();
                     key[s].idx = CAV_MAX_AGENTS + e;
@@ -427,7 +472,12 @@ __global__ void __launch_bounds__(512) k_pairwise_obs(DevBuffers b, KParams<T> p
                         coll = coll || (dc <= cr);  // env.py:490
                         if (!(dc > p.sensing_horizon)) {  // OtherAgentsStatesSensor.py:90
                             const T d2o = dc - glh.z - ro;  // :87
+                            key[s].tt = (T)0;
                             key[s].kr = M<T>::rint_(d2o * (T)100) / (T)100;
+                            if (p.sorting == CAV_SORT_TIME_TO_IMPACT) {  // key (-tti, -round(dist, 2), p_orth), :36-38
+                                key[s].tt = -time_to_impact<T>(pvh.x, pvh.y, pvo.x, pvo.y, pvh.z, pvh.w, pvo.z, pvo.w, cr);
+                                key[s].kr = -key[s].kr;
+                            }
                             key[s].po = rx * orx + ry * ory;
                             key[s].idx = o;
                             seen = true;
@@ -480,6 +530,7 @@ __global__ void __launch_bounds__(512) k_pairwise_obs(DevBuffers b, KParams<T> p
                         if (rank < nc) {
                             key[s].kr = -key[s].kr;
                         } else {
+                            key[s].tt = M<T>::inf();
                             key[s].kr = M<T>::inf();
                             key[s].po = M<T>::inf();
                             key[s].idx = CAV_MAX_AGENTS + rank;

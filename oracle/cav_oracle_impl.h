@@ -279,13 +279,58 @@ typedef struct {
     int idx;
     REAL rdist;  /* round(dist_2_other, 2) */
     REAL porth;
+    REAL tti;    /* time_to_impact (only for AGENT_SORTING_METHOD == 'time_to_impact'), else 0 */
 } SFX(crit_t);
 
-static int SFX(crit_less)(const SFX(crit_t) * a, const SFX(crit_t) * b, int negate_dist) {
-    const REAL da = negate_dist ? -a->rdist : a->rdist, db = negate_dist ? -b->rdist : b->rdist;
+/* mode 0: (rdist, porth); 1: (-rdist, porth); 2: (-tti, -rdist, porth)  (OtherAgentsStatesSensor.py:33-50) */
+static int SFX(crit_less)(const SFX(crit_t) * a, const SFX(crit_t) * b, int mode) {
+    if (mode == 2) {
+        const REAL ta = -a->tti, tb = -b->tti;
+        if (ta < tb) return 1;
+        if (ta > tb) return 0;
+    }
+    const REAL da = mode ? -a->rdist : a->rdist, db = mode ? -b->rdist : b->rdist;
     if (da < db) return 1;
     if (da > db) return 0;
     return a->porth < b->porth;
+}
+
+/* util.compute_time_to_impact (util.py:23-79) with tangent_vecs_from_external_pt (:81-112), operation for operation:
+ * host at (px,py) with velocity hv, other at (a,b) with velocity ov, r = combined radius. */
+static REAL SFX(time_to_impact)(REAL px, REAL py, REAL a, REAL b, REAL hvx, REAL hvy, REAL ovx, REAL ovy, REAL r) {
+    const REAL v0 = hvx - ovx, v1 = hvy - ovy; /* v_rel */
+    const REAL sq = (px - a) * (px - a) + (py - b) * (py - b) - r * r;
+    if (sq < 0) return (REAL)0.0; /* already inside the collision zone */
+    const REAL sqrt_term = R_SQRT((px - a) * (px - a) + (py - b) * (py - b) - r * r);
+    const REAL xnum1 = (r * r) * (px - a), xnum2 = r * (py - b) * sqrt_term;
+    const REAL ynum1 = (r * r) * (py - b), ynum2 = r * (px - a) * sqrt_term;
+    const REAL den = (px - a) * (px - a) + (py - b) * (py - b);
+    const REAL c1x = ((xnum1 + xnum2) / den + a) - px, c1y = ((ynum1 - ynum2) / den + b) - py; /* vec1 */
+    const REAL c2x = ((xnum1 - xnum2) / den + a) - px, c2y = ((ynum1 + ynum2) / den + b) - py; /* vec2 */
+    const REAL k1v = c1x * v1 - c1y * v0, k12 = c1x * c2y - c1y * c2x; /* np.cross of 2-vectors */
+    const REAL k2v = c2x * v1 - c2y * v0, k21 = c2x * c1y - c2y * c1x;
+    if (!(k1v * k12 >= 0 && k2v * k21 >= 0)) return (REAL)INFINITY; /* v_rel outside the collision cone */
+    if (R_FABS(v0) < (REAL)1e-5 && R_FABS(v1) < (REAL)1e-5) return (REAL)INFINITY;
+    REAL x1, x2, y1, y2;
+    if (R_FABS(v0) < (REAL)1e-5) { /* vertical v_rel */
+        const REAL A = 1, B = -2 * b, C = b * b + (px - a) * (px - a) - r * r;
+        x1 = x2 = px;
+        y1 = (-B + R_SQRT(B * B - 4 * A * C)) / (2 * A);
+        y2 = (-B - R_SQRT(B * B - 4 * A * C)) / (2 * A);
+    } else {
+        const REAL m = v1 / v0;
+        const REAL A = 1 + m * m;
+        const REAL B = -2 * a + 2 * m * (py - b - m * px);
+        const REAL C = a * a - r * r + (m * px - (py - b)) * (m * px - (py - b));
+        x1 = (-B + R_SQRT(B * B - 4 * A * C)) / (2 * A);
+        x2 = (-B - R_SQRT(B * B - 4 * A * C)) / (2 * A);
+        y1 = m * (x1 - px) + py;
+        y2 = m * (x2 - px) + py;
+    }
+    const REAL d1 = R_SQRT((x1 - px) * (x1 - px) + (y1 - py) * (y1 - py));
+    const REAL d2 = R_SQRT((x2 - px) * (x2 - px) + (y2 - py) * (y2 - py));
+    const REAL d = d2 < d1 ? d2 : d1; /* Python min(d1, d2) */
+    return d / R_SQRT(v0 * v0 + v1 * v1);
 }
 /* Python's sorted() is stable: insertion sort keeps equal keys in input order */
 static void SFX(stable_sort)(SFX(crit_t) * v, int n, int negate_dist) {
@@ -412,11 +457,17 @@ static void SFX(pairwise_obs_env)(const cav_config_t *cfg, const cav_buffers_t *
             crit[nc].idx = i;
             crit[nc].rdist = R_RINT(d2o * (REAL)100) / (REAL)100; /* round(np.float64, 2) */
             crit[nc].porth = p_orth;
+            crit[nc].tti = (REAL)0;
+            if (cfg->agent_sorting_method == CAV_SORT_TIME_TO_IMPACT) /* :92-101 */
+                crit[nc].tti = SFX(time_to_impact)(pv[h].x, pv[h].y, pv[i].x, pv[i].y, pv[h].z, pv[h].w, pv[i].z,
+                                                   pv[i].w, goal[h].z + goal[i].z);
             ++nc;
         }
-        SFX(stable_sort)(crit, nc, 0); /* OtherAgentsStatesSensor.py:33-35 */
-        if (nc > K) nc = K;            /* :39 */
+        const int tti_mode = cfg->agent_sorting_method == CAV_SORT_TIME_TO_IMPACT;
+        SFX(stable_sort)(crit, nc, tti_mode ? 2 : 0); /* OtherAgentsStatesSensor.py:33-38 */
+        if (nc > K) nc = K;                            /* :39 */
         if (cfg->agent_sorting_method == CAV_SORT_CLOSEST_LAST) SFX(stable_sort)(crit, nc, 1); /* :42-44 */
+        /* time_to_impact: the second sort (:48-50) uses the same key as the first, a no-op on the clipped list */
         REAL first_row[7] = {0, 0, 0, 0, 0, 0, 0};
         int have_first = 0;
         if (off[CAV_OBS_OTHER_AGENTS_STATES] >= 0)

@@ -63,11 +63,11 @@ def test_create_rejects_bad_config_without_gpu(libpath):
     bad.num_agents = 65
     assert L.cav_create(ctypes.byref(bad), ctypes.byref(h)) == -1
     bad = abi.CavConfig.from_buffer_copy(c)
-    bad.agent_sorting_method = abi.CAV_SORT_TIME_TO_IMPACT
-    assert L.cav_create(ctypes.byref(bad), ctypes.byref(h)) == -7  # CAV_ERR_UNSUPPORTED: no CPU fallback exists
+    bad.agent_sorting_method = 7  # not a cav_sorting_t
+    assert L.cav_create(ctypes.byref(bad), ctypes.byref(h)) == -1
     bad = abi.CavConfig.from_buffer_copy(c)
     bad.rvo_collab_coeff = -0.5
-    assert L.cav_create(ctypes.byref(bad), ctypes.byref(h)) == -7
+    assert L.cav_create(ctypes.byref(bad), ctypes.byref(h)) == -7  # CAV_ERR_UNSUPPORTED: no CPU fallback exists
     assert L.cav_create(None, ctypes.byref(h)) == -2  # CAV_ERR_NULL_POINTER
     assert L.cav_step(None, None, 0.0, None) == -6  # CAV_ERR_BAD_HANDLE
     assert L.cav_destroy(None) == -6

@@ -283,6 +283,20 @@ def dense6_clip3_last():  # K=3 < N-1 with closest_last ordering, dense start (c
 
 
 @scenario
+def tti8_clip4():  # AGENT_SORTING_METHOD = 'time_to_impact' (util.compute_time_to_impact), K = 4 of 7 neighbours
+    run_scenario("tti8_clip4", 8, lambda tc, C: mk_agents(tc, fixture_rows(tc, 8, 6), "RVO"),
+                 pre=["self.MAX_NUM_OTHER_AGENTS_OBSERVED = 4"],
+                 post=EVAL_POST + ["self.AGENT_SORTING_METHOD = 'time_to_impact'"], stop_after=120)
+
+
+@scenario
+def tti6_mixed():  # time_to_impact with non-cooperative agents (collisions: time_to_impact 0) and full K
+    run_scenario("tti6_mixed", 6, lambda tc, C: mk_agents(tc, fixture_rows(tc, 6, 2),
+                                                           ["noncoop", "RVO", "noncoop", "RVO", "RVO", "noncoop"]),
+                 post=EVAL_POST + ["self.AGENT_SORTING_METHOD = 'time_to_impact'"], stop_after=100)
+
+
+@scenario
 def horizon8():  # finite SENSING_HORIZON: obs skips far agents, RVO neighborDist finite
     run_scenario("horizon8", 8, lambda tc, C: mk_agents(tc, fixture_rows(tc, 8, 3), "RVO"),
                  post=EVAL_POST + ["self.SENSING_HORIZON = 3.0"], stop_after=90)
