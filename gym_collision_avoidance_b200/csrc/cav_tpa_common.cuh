@@ -150,9 +150,11 @@ __device__ __forceinline__ void tpa_move(const TpaBuffers &b, const KParams<T> &
         }
         if (dyn != CAV_DYN_EXTERNAL) {
             if (dyn == CAV_DYN_UNICYCLE_MAX_TURN_RATE) {  // UnicycleDynamicsMaxTurnRate.py:30-32
-                T tr = a1 / dt;
-                tr = tr < (T)-3.0 ? (T)-3.0 : (tr > (T)3.0 ? (T)3.0 : tr);
-                a1 = tr * dt;
+                // `action` is a float32 array (env.py:305-307) and dt a Python float, so under NumPy >= 2 (NEP 50) the
+                // turning rate, its clip and `turning_rate*dt` are float32 operations; the sum with the heading is float64
+                float tr = (float)a1 / (float)dt;
+                tr = tr < -3.0f ? -3.0f : (tr > 3.0f ? 3.0f : tr);
+                a1 = (T)(tr * (float)dt);
             }
             const T heading = ht.x;
             const T sel = wrap<T>(a1 + heading);  // UnicycleDynamics.py:28

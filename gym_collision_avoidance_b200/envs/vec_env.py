@@ -220,6 +220,34 @@ class VecCollisionAvoidanceEnv(object):
         ONLY collective of the framework and it is not on the per-step path."""
         return gather_stats(self.cav.stats(), self.device)
 
+    def trajectories(self, env_ids=None):
+        """Episode trajectories of the CURRENT episode of the given environments, in the reference's per-agent array
+        format (needs ``history_len > 0``): a list (per env) of lists (per agent) of dicts with
+        ``global_state_history`` ``[T, 11] = [t, px, py, gx, gy, radius, pref_speed, vx, vy, speed, heading]`` and
+        ``ego_state_history`` ``[T, 3] = [t, dist_to_goal, heading_ego_frame]`` (reference ``agent.py:257-289``, rows
+        ``[:step_num]``), which is what ``visualize.plot_episode`` and
+        ``experiments/src/run_trajectory_dataset_creator.py:43-104`` consume.  With ``auto_reset`` a finished
+        episode's rows are overwritten by the next one, so collectors run with ``auto_reset=False`` and read at
+        ``game_over``.  One device->host copy of the selected envs' ring buffers."""
+        st = self.state
+        if st.t.get("history") is None:
+            raise abi.CavoidError("trajectories() needs history_len > 0")
+        ids = list(range(self.num_envs)) if env_ids is None else [int(e) for e in env_ids]
+        idx = torch.as_tensor(ids, dtype=torch.long, device=self.device)
+        hist = st.history.index_select(0, idx).cpu().numpy().astype(np.float64)
+        steps = st.step_num.index_select(0, idx).cpu().numpy()
+        nact = st.num_active.index_select(0, idx).cpu().numpy()
+        out = []
+        for k in range(len(ids)):
+            n = int(nact[k])
+            agents = []
+            for i in range(n):
+                T = min(int(steps[k, i]), hist.shape[2])
+                agents.append({"global_state_history": hist[k, i, :T, :11].copy(),
+                               "ego_state_history": hist[k, i, :T, 11:14].copy()})
+            out.append(agents)
+        return out
+
     def obs_slice(self, state_name):
         o = self.obs_offsets[state_name]
         return slice(o, o + _config.state_size(self.config, state_name))

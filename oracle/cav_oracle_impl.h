@@ -196,10 +196,13 @@ static void SFX(dynamics_env)(const cav_config_t *cfg, const cav_buffers_t *b, R
         const uint32_t dyn = CAV_KIND_DYNAMICS(kinds[i]);
         REAL speed_out = aux0 ? aux0[i].x : 0, dhead_out = aux0 ? aux0[i].y : 0;
         if (dyn != CAV_DYN_EXTERNAL) {
-            if (dyn == CAV_DYN_UNICYCLE_MAX_TURN_RATE) { /* UnicycleDynamicsMaxTurnRate.py:30-32, float64 semantics */
-                REAL tr = a1 / dt;
-                tr = tr < (REAL)-3.0 ? (REAL)-3.0 : (tr > (REAL)3.0 ? (REAL)3.0 : tr);
-                a1 = tr * dt;
+            if (dyn == CAV_DYN_UNICYCLE_MAX_TURN_RATE) { /* UnicycleDynamicsMaxTurnRate.py:30-32 */
+                /* `action` is a float32 array (env.py:305-307) and dt a Python float: under NumPy >= 2 (NEP 50)
+                 * action[1]/dt, np.clip(.., -3, 3) and turning_rate*dt are float32 operations, the sum with the
+                 * float64 heading is float64 (pinned by golden maxturn6_ext, minted with NumPy 2.3) */
+                float tr = (float)a1 / (float)dt;
+                tr = tr < -3.0f ? -3.0f : (tr > 3.0f ? 3.0f : tr);
+                a1 = (REAL)(tr * (float)dt);
             }
             const REAL heading = ht[i].x;
             const REAL sel = SFX(wrap)(a1 + heading); /* UnicycleDynamics.py:28 */

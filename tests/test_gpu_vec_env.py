@@ -102,3 +102,31 @@ def test_abi_error_paths_on_device():
     assert b"pv" in L.cav_last_error(h)
     assert L.cav_k_laserscan(h, None) in (-4, -1)
     assert L.cav_destroy(h) == 0
+
+
+def test_trajectories_match_the_oracle_history_in_reference_format():
+    """N2: per-agent global_state_history [T,11] / ego_state_history [T,3] arrays (reference agent.py:257-289)."""
+    N, E = 4, 32
+    rows = random_scenario_bank(E, N, seed=9)
+    cfg = make_config(N, evaluate=True)
+    env = VecCollisionAvoidanceEnv(E, cfg, N, precision="f64", scenario_bank=rows, policies="noncoop",
+                                   auto_reset=False, history_len=80)
+    hs = HostState(env.c)
+    orc = Oracle(env.c)
+    orc.reset(hs, HostBank(rows, kinds=kinds_array(E, N, "noncoop")))
+    env.reset()
+    for _ in range(25):
+        env.step()
+        orc.step(hs)
+    tr = env.trajectories(env_ids=[0, 5, 31])
+    assert len(tr) == 3 and all(len(a) == N for a in tr)
+    for k, e in enumerate([0, 5, 31]):
+        for i in range(N):
+            T = int(hs.step_num[e, i])
+            g, eg = tr[k][i]["global_state_history"], tr[k][i]["ego_state_history"]
+            assert g.shape == (T, 11) and eg.shape == (T, 3) and T > 0
+            assert np.allclose(g, hs.history[e, i, :T, :11], rtol=1e-9, atol=1e-9)
+            assert np.allclose(eg, hs.history[e, i, :T, 11:14], rtol=1e-9, atol=1e-9)
+            assert g[0, 0] == 0.0 and np.allclose(g[:, 3:5], rows[e, i, 2:4])  # rows start at t = 0; goal columns
+            assert np.allclose(np.diff(g[:, 0]), 0.1)                                              # t advances by dt
+    env.close()

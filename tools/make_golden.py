@@ -104,7 +104,9 @@ def run_scenario(name, N, agents_fn, pre=(), post=(), max_steps=400, ext_action_
         # writing the boolean layer into the Map object reset() just created is equivalent for the step path
         assert env.map is not None and env.map.static_map.shape == static_map.shape
         env.map.static_map[...] = static_map
-    kinds = np.array([POLICY_IDS[a.policy.str] | (0 << 8) for a in agents] + [0] * (N - n), np.uint32)
+    dyn_ids = {"UnicycleDynamics": 0, "UnicycleDynamicsMaxTurnRate": 1, "ExternalDynamics": 2}
+    kinds = np.array([POLICY_IDS[a.policy.str] | (dyn_ids[type(a.dynamics_model).__name__] << 8) for a in agents]
+                     + [0] * (N - n), np.uint32)
     states = [agent_state(env.agents, N)]
     obs_seq = [pack_obs(obs, Config, N)]
     rewards, dones, gos, exts, acts = [], [], [], [], []
@@ -294,6 +296,29 @@ def tti6_mixed():  # time_to_impact with non-cooperative agents (collisions: tim
     run_scenario("tti6_mixed", 6, lambda tc, C: mk_agents(tc, fixture_rows(tc, 6, 2),
                                                            ["noncoop", "RVO", "noncoop", "RVO", "RVO", "noncoop"]),
                  post=EVAL_POST + ["self.AGENT_SORTING_METHOD = 'time_to_impact'"], stop_after=100)
+
+
+@scenario
+def maxturn6_ext():  # UnicycleDynamicsMaxTurnRate (clip(dtheta/dt, +-3) dt) under RVO / external commands, and one
+    # ExternalDynamics agent (state never moves; the others still avoid it)
+    def agents(tc, C):
+        from gym_collision_avoidance.envs.dynamics.UnicycleDynamicsMaxTurnRate import UnicycleDynamicsMaxTurnRate
+        from gym_collision_avoidance.envs.dynamics.ExternalDynamics import ExternalDynamics
+        from gym_collision_avoidance.envs.dynamics.UnicycleDynamics import UnicycleDynamics
+        rows = fixture_rows(tc, 6, 4)
+        pol = ["RVO", "RVO", "external", "noncoop", "RVO", "external"]
+        dyn = [UnicycleDynamicsMaxTurnRate, UnicycleDynamics, UnicycleDynamicsMaxTurnRate, UnicycleDynamicsMaxTurnRate,
+               UnicycleDynamicsMaxTurnRate, ExternalDynamics]
+        out = []
+        for i in range(6):
+            out += mk_agents(tc, [rows[i]], pol[i], dynamics=dyn[i])
+            out[-1].id = i
+        return out
+
+    def ext(rng, i, t):
+        return np.array([rng.uniform(0.2, 1.2), rng.uniform(-0.6, 0.6)], np.float32)
+
+    run_scenario("maxturn6_ext", 6, agents, post=EVAL_POST, ext_action_fn=ext, stop_after=100)
 
 
 @scenario
