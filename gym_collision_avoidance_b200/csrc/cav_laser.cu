@@ -36,12 +36,12 @@ __global__ void __launch_bounds__(256) k_laserscan(LaserPtrs b, LaserParams lp, 
     int *s_gy = s_gx + CAV_MAX_AGENTS;
     int *s_in = s_gy + CAV_MAX_AGENTS;
     uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_in + CAV_MAX_AGENTS);
-    // per current agent h: the other agents whose inflated disc the beams can reach (compacted)
+    // per agent of the chunk: the other agents whose inflated disc its beams can reach (compacted), [APC][MAX_AGENTS]
     double *s_cox = reinterpret_cast<double *>(s_cnt + CAV_MAX_AGENTS);
-    double *s_coy = s_cox + CAV_MAX_AGENTS;
-    double *s_cdd = s_coy + CAV_MAX_AGENTS;
-    double *s_cR2 = s_cdd + CAV_MAX_AGENTS;
-    int *s_ncand = reinterpret_cast<int *>(s_cR2 + CAV_MAX_AGENTS);
+    double *s_coy = s_cox + APC * CAV_MAX_AGENTS;
+    double *s_cdd = s_coy + APC * CAV_MAX_AGENTS;
+    double *s_cR2 = s_cdd + APC * CAV_MAX_AGENTS;
+    int *s_ncand = reinterpret_cast<int *>(s_cR2 + APC * CAV_MAX_AGENTS);  // [APC]
 
     const int tid = threadIdx.x;
     const int N = lp.N;
@@ -97,41 +97,68 @@ __global__ void __launch_bounds__(256) k_laserscan(LaserPtrs b, LaserParams lp, 
             }
         }
         __syncthreads();
-        // ---- 3. beams ----
-        const int a_end = min(n, (chunk + 1) * APC);
-        for (int h = chunk * APC; h < a_end; ++h) {
+        // ---- 3a. which samples can hit at all?  A sample can only land in a cell painted for agent c if it lies
+        // within R_c = r_c + sqrt(2)*cell (+eps) of c's centre (the sample and the centre are each anywhere inside
+        // their cells), so with an empty static map only samples inside the union of the ray's intersections with
+        // those inflated discs need the exact cell test.  Candidates (painted agents within max_range + R_c) are
+        // compacted once per agent of the chunk -- one warp per agent, ballot compaction keeps agent order -- and
+        // every beam of that agent then tests only them.  (ncu on the previous version, which built one list at a time
+        // on thread 0 between two block barriers per agent: 35 % of all stall samples sat at those barriers.)
+        const int a0 = chunk * APC;
+        const int a_end = min(n, a0 + APC);
+        if (!has_static) {
+            const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+            for (int q = warp; q < a_end - a0; q += nwarps) {
+                const int h = a0 + q;
+                const double px = s_px[h], py = s_py[h];
+                int nc = 0;
+                for (int c0 = 0; c0 < n; c0 += 32) {
+                    const int c = c0 + lane;
+                    bool keep = false;
+                    double ox = 0.0, oy = 0.0, dd = 0.0, R = 0.0;
+                    if (c < n && c != h && s_in[c]) {
+                        ox = s_px[c] - px;
+                        oy = s_py[c] - py;
+                        R = sqrt(s_rr2[c]) * lp.cell + 1.4143 * lp.cell + 1e-6;
+                        dd = ox * ox + oy * oy;
+                        const double reach = lp.max_range + R;
+                        keep = !(dd > reach * reach);
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, keep);
+                    if (keep) {
+                        const int pos = q * CAV_MAX_AGENTS + nc + __popc(m & ((1u << lane) - 1u));
+                        s_cox[pos] = ox;
+                        s_coy[pos] = oy;
+                        s_cdd[pos] = dd;
+                        s_cR2[pos] = R * R;
+                    }
+                    nc += __popc(m);
+                }
+                if (lane == 0) s_ncand[q] = nc;
+            }
+            __syncthreads();
+        }
+        // ---- 3b. beams: the chunk's (agent, beam) pairs flattened over the CTA, no barrier between agents ----
+        const int ntask = (a_end - a0) * lp.B;
+        for (int task = tid; task < ntask; task += blockDim.x) {
+            const int q = task / lp.B, bi = task - q * lp.B;
+            const int h = a0 + q;
             const double px = s_px[h], py = s_py[h], hd = s_hd[h], rr2 = s_rr2[h];
             const int ego_in = s_in[h], cgx = s_gx[h], cgy = s_gy[h];
             const uint32_t cnt = s_cnt[h];
             T *o = g_obs + (base + h) * (size_t)lp.obs_len + lp.obs_off;
-            // Which samples can hit at all?  A sample can only land in a cell painted for agent c if it lies within
-            // R_c = r_c + sqrt(2)*cell (+eps) of c's centre (the sample and the centre are each anywhere inside
-            // their cells), so with an empty static map only samples inside the union of the ray's intersections with
-            // those inflated discs need the exact cell test.  Candidates (painted agents within max_range + R_c) are
-            // compacted once per agent; every beam of this agent then tests only them.
-            if (!has_static) {
-                __syncthreads();  // previous agent's beams are done with the candidate list
-                if (tid == 0) {
-                    int nc = 0;
-                    for (int c = 0; c < n; ++c) {
-                        if (c == h || !s_in[c]) continue;
-                        const double ox = s_px[c] - px, oy = s_py[c] - py;
-                        const double R = sqrt(s_rr2[c]) * lp.cell + 1.4143 * lp.cell + 1e-6;
-                        const double dd = ox * ox + oy * oy;
-                        const double reach = lp.max_range + R;
-                        if (dd > reach * reach) continue;
-                        s_cox[nc] = ox;
-                        s_coy[nc] = oy;
-                        s_cdd[nc] = dd;
-                        s_cR2[nc] = R * R;
-                        ++nc;
-                    }
-                    *s_ncand = nc;
-                }
-                __syncthreads();
+            // measurement history rows that will shift down: fetch them now, their latency hides behind the march
+            T older[3] = {(T)0, (T)0, (T)0};
+            const bool prefetched = cnt != 0u && lp.P <= 4;
+            if (prefetched) {
+#pragma unroll
+                for (int pp = 0; pp < 3; ++pp)
+                    if (pp < lp.P - 1) older[pp] = o[(size_t)pp * lp.B + bi];
             }
-            const int ncand = has_static ? 0 : *s_ncand;
-            for (int bi = tid; bi < lp.B; bi += blockDim.x) {
+            const int ncand = has_static ? 0 : s_ncand[q];
+            const double *cox = s_cox + q * CAV_MAX_AGENTS, *coy = s_coy + q * CAV_MAX_AGENTS;
+            const double *cdd = s_cdd + q * CAV_MAX_AGENTS, *cR2 = s_cR2 + q * CAV_MAX_AGENTS;
+            {
                 double ang0 = (double)bi * lp.ang_step + lp.min_angle;  // np.linspace (LaserScanSensor.py:38)
                 if (bi == lp.B - 1) ang0 = lp.max_angle;
                 const double ang = ang0 + hd;  // :66
@@ -143,9 +170,9 @@ __global__ void __launch_bounds__(256) k_laserscan(LaserPtrs b, LaserParams lp, 
                     double tmin = 1e300, tmax = -1e300;
 #pragma unroll 1
                     for (int c = 0; c < ncand; ++c) {
-                        const double tca = s_cox[c] * ca + s_coy[c] * sa;
-                        const double d2 = s_cdd[c] - tca * tca;
-                        const double R2 = s_cR2[c];
+                        const double tca = cox[c] * ca + coy[c] * sa;
+                        const double d2 = cdd[c] - tca * tca;
+                        const double R2 = cR2[c];
                         if (d2 > R2) continue;
                         const double thc = sqrt(R2 - d2);
                         const double t1 = tca + thc;
@@ -189,13 +216,18 @@ __global__ void __launch_bounds__(256) k_laserscan(LaserPtrs b, LaserParams lp, 
                 const double rng = kstar >= 0 ? lp.min_range + (double)kstar * lp.range_res : lp.max_range;
                 if (cnt == 0u) {  // first measurement fills every row (:84-85)
                     for (int pp = 0; pp < lp.P; ++pp) o[(size_t)pp * lp.B + bi] = (T)rng;
-                } else {  // np.roll(history, 1, axis=0); row 0 = newest (:86-88)
+                } else if (prefetched) {  // np.roll(history, 1, axis=0); row 0 = newest (:86-88)
+#pragma unroll
+                    for (int pp = 3; pp >= 1; --pp)
+                        if (pp < lp.P) o[(size_t)pp * lp.B + bi] = older[pp - 1];
+                    o[bi] = (T)rng;
+                } else {
                     for (int pp = lp.P - 1; pp >= 1; --pp) o[(size_t)pp * lp.B + bi] = o[(size_t)(pp - 1) * lp.B + bi];
                     o[bi] = (T)rng;
                 }
             }
         }
-        if (tid >= chunk * APC && tid < a_end) b.laser_count[base + tid] = s_cnt[tid] + 1u;
+        if (tid >= a0 && tid < a_end) b.laser_count[base + tid] = s_cnt[tid] + 1u;
         __syncthreads();
     }
 }
@@ -214,7 +246,8 @@ cudaError_t run_laserscan(const cav_buffers_t &bufs, const LaserParams &lp, cons
     const int APC = 4;
     const int chunks = (lp.N + APC - 1) / APC;
     const int nwork = lp.E * chunks;
-    const size_t smem = (((size_t)lp.rows * lp.wpr * 4 + 15) & ~(size_t)15) + CAV_MAX_AGENTS * (8 * 8 + 4 * 4) + 64;
+    const size_t smem = (((size_t)lp.rows * lp.wpr * 4 + 15) & ~(size_t)15) + CAV_MAX_AGENTS * (4 * 8 + 4 * 4) +
+                        (size_t)APC * CAV_MAX_AGENTS * 4 * 8 + APC * 4 + 64;
     auto kern = k_laserscan<T>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
