@@ -14,7 +14,12 @@ STATE_COLS = ("pv", "goal", "ht", "ego", "flags", "step_num")
 AUX_COLS = ("aux0", "past_actions", "past_vel")
 
 
-def golden_names():
+def golden_names(cpu_only=False):
+    """Fixture names; cpu_only=True lists tests/golden/cpu_only/ (oracle-vs-reference pins at sizes whose GPU parity is
+    covered against the oracle instead), as "cpu_only/<name>"."""
+    if cpu_only:
+        return sorted("cpu_only/" + os.path.splitext(os.path.basename(p))[0]
+                      for p in glob.glob(os.path.join(GOLDEN_DIR, "cpu_only", "*.npz")))
     return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
 
 

@@ -16,7 +16,7 @@ from gym_collision_avoidance_b200.state import HostState
 RTOL = ATOL = 1e-12
 
 
-@pytest.mark.parametrize("name", common.golden_names())
+@pytest.mark.parametrize("name", common.golden_names() + common.golden_names(cpu_only=True))
 def test_teacher_forced_f64(name):
     """Every recorded step, from the reference's exact pre-step state: one oracle step == the reference's."""
     g = common.Golden(name)
@@ -31,7 +31,8 @@ def test_teacher_forced_f64(name):
     assert worst <= 1e-9
 
 
-@pytest.mark.parametrize("name", [n for n in common.golden_names() if not n.startswith("mixed")])
+@pytest.mark.parametrize("name", [n for n in common.golden_names() + common.golden_names(cpu_only=True)
+                                  if not n.startswith("mixed")])
 def test_free_running_f64(name):
     """Reset from the scenario row and free-run: the oracle tracks the reference over whole episodes."""
     g = common.Golden(name)

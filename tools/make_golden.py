@@ -85,7 +85,7 @@ def pack_obs(obs, Config, N):
 
 
 def run_scenario(name, N, agents_fn, pre=(), post=(), max_steps=400, ext_action_fn=None, seed=0, stop_after=None,
-                 static_map=None):
+                 static_map=None, subdir=""):
     cfg_path = write_cfg(N, list(pre), list(post))
     ref_harness.load_reference(cfg_path, "Cfg")
     from gym_collision_avoidance.envs import Config
@@ -178,11 +178,12 @@ def run_scenario(name, N, agents_fn, pre=(), post=(), max_steps=400, ext_action_
                ext_actions=np.stack(exts), actions=np.stack(acts), obs=np.stack(obs_seq), history=hist)
     for k in states[0]:
         out["st_" + k] = np.stack([s[k] for s in states])
-    os.makedirs(OUT, exist_ok=True)
-    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    out_dir = os.path.join(OUT, subdir)
+    os.makedirs(out_dir, exist_ok=True)
+    np.savez_compressed(os.path.join(out_dir, name + ".npz"), **out)
     os.unlink(cfg_path)
     print("%-22s N=%d n=%d steps=%d game_over=%s  %.0f KB" % (
-        name, N, n, T, gos[-1], os.path.getsize(os.path.join(OUT, name + ".npz")) / 1024.0))
+        name, N, n, T, gos[-1], os.path.getsize(os.path.join(out_dir, name + ".npz")) / 1024.0))
 
 
 EVAL_POST = ["self.EVALUATE_MODE = True", "self.TRAIN_MODE = False", "self.DT = 0.1", "self.MAX_TIME_RATIO = 8."]
@@ -319,6 +320,33 @@ def maxturn6_ext():  # UnicycleDynamicsMaxTurnRate (clip(dtheta/dt, +-3) dt) und
         return np.array([rng.uniform(0.2, 1.2), rng.uniform(-0.6, 0.6)], np.float32)
 
     run_scenario("maxturn6_ext", 6, agents, post=EVAL_POST, ext_action_fn=ext, stop_after=100)
+
+
+# ---- tests/golden/cpu_only/: pin the ORACLE on the rest of BASELINE's N range (the GPU kernels are compared with the
+# oracle at these sizes on the same states, tests/test_gpu_scale.py); not part of the GPU parity parametrisation ----
+def _rand_rows(n, seed, side):
+    np.random.seed(seed)
+    from gym_collision_avoidance.envs.policies.CADRL.scripts.multi import gen_rand_testcases as g
+    return g.generate_rand_test_case_multi(n, side, [0.5, 2.0], [0.2, 0.8])
+
+
+@scenario
+def rvo32_rand():  # N = 32 (sub-warp-group kernels' range): the reference's kd-tree with several leaf splits
+    run_scenario("rvo32_rand", 32, lambda tc, C: mk_agents(tc, _rand_rows(32, 321, 7.0), "RVO"), post=EVAL_POST,
+                 stop_after=30, subdir="cpu_only")
+
+
+@scenario
+def rvo64_rand():  # N = 64 = CAV_MAX_AGENTS, K = 63
+    run_scenario("rvo64_rand", 64, lambda tc, C: mk_agents(tc, _rand_rows(64, 641, 7.0), "RVO"), post=EVAL_POST,
+                 stop_after=12, subdir="cpu_only")
+
+
+@scenario
+def noncoop16_tti():  # 16 agents, time_to_impact ordering clipped to K = 6, collisions
+    run_scenario("noncoop16_tti", 16, lambda tc, C: mk_agents(tc, _rand_rows(16, 161, 5.0), "noncoop"),
+                 pre=["self.MAX_NUM_OTHER_AGENTS_OBSERVED = 6"],
+                 post=EVAL_POST + ["self.AGENT_SORTING_METHOD = 'time_to_impact'"], stop_after=60, subdir="cpu_only")
 
 
 @scenario
