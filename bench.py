@@ -140,12 +140,42 @@ def auto_cpu_steps(a):
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe): `nvidia-smi -lms 100`
+    as the recipe says, plus -- the timed region of the default run lasts only ~0.1 s -- an NVML poll every 5 ms from a
+    thread (pynvml, read-only queries).  Both feed the same summary."""
+
+    HW_SLOWDOWN, SW_THERMAL, HW_THERMAL, SW_POWER_CAP = 0x8, 0x20, 0x40, 0x4
 
     def __init__(self, index=0):
         self.index = index
         self.proc = None
         self.lines = []
+        self.nvml = []  # (sm_mhz, sm_max_mhz, reasons bitmask)
+        self._stop = threading.Event()
+        self._nvml_thread = None
+
+    def _nvml_loop(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid if not uuid.startswith("GPU-") else uuid).encode())
+            except Exception:
+                h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            reasons_fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                getattr(pynvml, "nvmlDeviceGetCurrentClocksThrottleReasons")
+            smax = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            while not self._stop.is_set():
+                self.nvml.append((float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), float(smax),
+                                  int(reasons_fn(h))))
+                time.sleep(0.005)
+        except Exception:
+            return
 
     def start(self):
         q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active," \
@@ -159,19 +189,26 @@ class ClockSampler(object):
             self.t.start()
         except Exception:
             self.proc = None
+        try:
+            self._nvml_thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self._nvml_thread.start()
+        except Exception:
+            self._nvml_thread = None
 
     def _read(self):
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
+        self._stop.set()
+        if self._nvml_thread is not None:
+            self._nvml_thread.join(timeout=1.0)
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
         sm, smax, reasons = [], [], set()
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
@@ -185,8 +222,18 @@ class ClockSampler(object):
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        n_smi = len(sm)
+        for clk, cmax, mask in list(self.nvml):
+            sm.append(clk)
+            smax.append(cmax)
+            for name, bit in (("hw_slowdown", self.HW_SLOWDOWN), ("hw_thermal_slowdown", self.HW_THERMAL),
+                              ("sw_thermal_slowdown", self.SW_THERMAL), ("sw_power_cap", self.SW_POWER_CAP)):
+                if mask & bit:
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["no clock samples (nvidia-smi / NVML unavailable)"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(smax), "samples": len(sm),
+                "samples_nvidia_smi": n_smi, "samples_nvml": len(sm) - n_smi, "reasons": sorted(reasons)}
 
 
 def measured_peak():
