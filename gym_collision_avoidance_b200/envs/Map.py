@@ -4,6 +4,26 @@ the row-major bitmap the library reads (``cav_buffers_t.static_map_bits``)."""
 import numpy as np
 
 
+def load_image_map(map_filename, dims):
+    """The reference's image path (Map.py:17-21): ``imageio.imread`` -> ``scipy.misc.imresize(.., dims,
+    interp='nearest')`` when the shape differs -> ``np.invert(..).astype(bool)`` (occupied = any pixel that is not pure
+    white).  ``scipy.misc.imresize`` (removed from SciPy 1.3) was ``PIL.Image.resize(resample=NEAREST)`` on the 8-bit
+    image with size ``(dims[1], dims[0])``; Pillow is used directly here.  The reference's own maps
+    (``world_maps/00{0,1,2}.png``) are single-channel 8-bit; colour images are reduced to luminance first (the reference
+    would carry the channel axis into the map and fail later)."""
+    try:
+        from PIL import Image
+    except ImportError as e:  # pragma: no cover
+        raise ImportError("image maps need Pillow (the reference needs imageio + scipy.misc.imresize, Map.py:17-21); "
+                          "pass a boolean array or a .npy file instead") from e
+    img = Image.open(map_filename)
+    if img.mode != "L":
+        img = img.convert("L")
+    if (img.size[1], img.size[0]) != tuple(dims):
+        img = img.resize((dims[1], dims[0]), resample=Image.NEAREST)
+    return np.invert(np.asarray(img, dtype=np.uint8)).astype(bool)
+
+
 class Map(object):
     def __init__(self, x_width, y_width, grid_cell_size, map_filename=None, static_map=None):
         self.x_width, self.y_width, self.grid_cell_size = x_width, y_width, grid_cell_size
@@ -18,8 +38,7 @@ class Map(object):
             if str(map_filename).endswith(".npy"):
                 self.static_map = np.load(map_filename).astype(bool)
             else:
-                raise NotImplementedError("image maps need imageio + scipy.misc.imresize like the reference "
-                                          "(Map.py:17-21); pass a boolean array or a .npy file instead")
+                self.static_map = load_image_map(map_filename, dims)
         self.origin_coords = np.array([(x_width / 2.) / grid_cell_size, (y_width / 2.) / grid_cell_size])
         self.map = None
 

@@ -93,3 +93,37 @@ def test_config_singleton_env_vars(tmp_path, monkeypatch):
         monkeypatch.delenv("GYM_CONFIG_PATH")
         monkeypatch.delenv("GYM_CONFIG_CLASS")
         importlib.reload(envs_pkg)
+
+
+def test_image_map_loading_matches_the_reference_recipe(tmp_path):
+    """Map(map_filename=png): nearest-neighbour resize to (rows, cols), occupied = not pure white (reference Map.py:17-21)."""
+    from PIL import Image
+    from gym_collision_avoidance_b200.envs.Map import Map
+    # 80 x 80 source, one black block and one grey pixel -> 160 x 160: every source pixel becomes a 2 x 2 block
+    src = np.full((80, 80), 255, np.uint8)
+    src[10:20, 30:50] = 0
+    src[70, 5] = 128
+    f = tmp_path / "m.png"
+    Image.fromarray(src).save(str(f))
+    m = Map(16, 16, 0.1, map_filename=str(f))
+    want = np.kron(src != 255, np.ones((2, 2), bool))
+    assert m.static_map.shape == (160, 160) and m.static_map.dtype == bool and np.array_equal(m.static_map, want)
+    # non-integer scale (500 -> 160): output pixel (r, c) samples source pixel floor((r + 0.5) * 500 / 160)
+    big = np.full((500, 500), 255, np.uint8)
+    rng = np.random.RandomState(0)
+    big[rng.randint(0, 500, 4000), rng.randint(0, 500, 4000)] = 0
+    big[100:180, 200:320] = 0
+    f2 = tmp_path / "big.png"
+    Image.fromarray(big).save(str(f2))
+    m2 = Map(16, 16, 0.1, map_filename=str(f2))
+    idx = np.floor((np.arange(160) + 0.5) * 500 / 160).astype(int)
+    assert np.array_equal(m2.static_map, (big != 255)[np.ix_(idx, idx)])
+    # same-size image: no resize; the bitmap the library reads has the same set bits
+    f3 = tmp_path / "same.png"
+    Image.fromarray(np.where(want, 0, 255).astype(np.uint8)).save(str(f3))
+    m3 = Map(16, 16, 0.1, map_filename=str(f3))
+    assert np.array_equal(m3.static_map, want)
+    bits = m3.bits().reshape(160, 5)
+    r, c = np.nonzero(want)
+    assert all((bits[rr, cc >> 5] >> (cc & 31)) & 1 for rr, cc in zip(r[:200], c[:200])) and \
+        int(sum(bin(int(w)).count("1") for w in bits.ravel())) == int(want.sum())
