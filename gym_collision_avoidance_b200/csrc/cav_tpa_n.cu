@@ -612,11 +612,9 @@ static cudaError_t launch_n(const cav_buffers_t &bufs, const KParams<T> &p, cons
     using S = TpaNShape<T, NT>;
     const int ntiles = (p.E + S::EPB - 1) / S::EPB;
     const size_t smem = S::WARP_BYTES * S::WARPS;
-    static bool attr_set = false;
-    if (!attr_set && smem > 48 * 1024) {
+    if (smem > 48 * 1024) {  // per device, so not cached in a process-wide flag (no current shape needs it: <= 38.4 KB)
         cudaError_t e = cudaFuncSetAttribute(k_pairwise_obs_tpa_n<T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_set = true;
     }
     const int grid = ntiles < sm_count * 16 ? ntiles : sm_count * 16;
     k_pairwise_obs_tpa_n<T, NT><<<grid, 32 * S::WARPS, smem, st>>>(make_tpa(bufs), p, wm, env_mask, obs_only, ntiles);
