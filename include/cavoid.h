@@ -15,7 +15,7 @@
  *   - every function returns 0 (CAV_OK) or a negative cav_status_t; nothing throws across the ABI;
  *     cav_last_error(h) returns a human-readable message for the last failure on that handle.
  *   - all device pointers are BORROWED (e.g. torch tensor.data_ptr()); the library never frees them.
- *     Vector columns (pv / goal / ht / ego / aux*) must be 16-byte aligned.
+ *     Vector columns (pv / goal / ht / ego / aux*) and obs must be 16-byte aligned.
  *   - all work is enqueued on the caller's CUDA stream; no implicit synchronisation, no host allocation and
  *     no host<->device copy on the step path, so a step can be captured into a CUDA graph.
  *   - a handle is bound to the CUDA device that was current at cav_create; use it from one thread at a time.
@@ -200,7 +200,7 @@ typedef struct cav_buffers {
     void *min_dist;      /* real [E*N] dist_btwn_nearest_agent (env.py:482-487); may be NULL */
     uint8_t *done;       /* [E*N] which_agents_done (env.py:529-536) */
     uint8_t *game_over;  /* [E] (env.py:538-551) */
-    void *obs;           /* real [E*N*obs_len] packed observation, STATES_IN_OBS order */
+    void *obs;           /* real [E*N*obs_len] packed observation, STATES_IN_OBS order; 16-byte aligned */
     uint32_t *laser_count;          /* [E*N] LaserScanSensor.num_measurements_made; NULL when no laserscan */
     const uint32_t *static_map_bits; /* [rows * ceil(cols/32)] row-major bitmap of Map.static_map, or NULL (empty) */
     void *history;       /* real [E*N*T*CAV_HISTORY_ROW] or NULL (agent.py:257-260,275-289) */
