@@ -6,8 +6,8 @@
 #include <stdint.h>
 
 #include "cavoid.h"
+#include "cav_hd.cuh"  // CAV_MAX_AGENTS, min_keep / max_keep (shared with the host-compiled parts)
 
-#define CAV_MAX_AGENTS 64
 #define CAV_MAX_OBS_SEG 10
 
 namespace cav {
@@ -173,16 +173,6 @@ __device__ __forceinline__ unsigned gballot(unsigned mask, bool pred) {
     const unsigned b = __ballot_sync(mask, pred);
     const unsigned base = (threadIdx.x & 31u) & ~(unsigned)(G - 1);
     return (G == 32) ? b : ((b >> base) & ((1u << G) - 1u));
-}
-
-// std::min / std::max argument-order semantics of the reference C++ (NaN-transparent on the new value)
-template <typename T>
-__device__ __forceinline__ T min_keep(T cur, T v) {
-    return (v < cur) ? v : cur;
-}
-template <typename T>
-__device__ __forceinline__ T max_keep(T cur, T v) {
-    return (cur < v) ? v : cur;
 }
 
 // Static-map geometry for the wall-collision test (env.py:494-506, Map.py:26-32,52-56); bits == nullptr disables it.

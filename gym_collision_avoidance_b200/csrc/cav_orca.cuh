@@ -13,17 +13,9 @@
 // nvcc cannot contract a*b+c, and division / sqrt are IEEE (-prec-div/-prec-sqrt defaults).
 #pragma once
 #include "cav_common.cuh"
+#include "cav_orca_core.cuh"  // Line, fdet / fdot, CAV_RVO_EPSILON
 
 namespace cav {
-
-struct Line {
-    float px, py, dx, dy;
-};
-
-#define CAV_RVO_EPSILON 0.00001f  // RVO2 Definitions.h:52
-
-__device__ __forceinline__ float fdet(float ax, float ay, float bx, float by) { return ax * by - ay * bx; }
-__device__ __forceinline__ float fdot(float ax, float ay, float bx, float by) { return ax * bx + ay * by; }
 
 // ---- generic bitonic sort over G lanes x SL slots; element index e = s*G + lane, ascending in e -----------------
 template <int G, int SL, typename KeyOps, typename Key>

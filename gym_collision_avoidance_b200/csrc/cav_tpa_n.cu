@@ -342,108 +342,6 @@ __global__ void __launch_bounds__(32 * TpaNShape<T, NT>::WARPS, (TpaNBounds<T>::
 // =============================================================================================================
 // policy + move with compile-time N (reference env.py:304-327; same contract as k_policy_move_tpa in cav_tpa.cu)
 // =============================================================================================================
-// ORCA with everything unrolled: the N-1 neighbour keys are ordered by an odd-even transposition network in
-// registers, the N-1 half-planes (each with its own sqrt / divide chains) are built as independent instruction
-// streams into registers, and linearProgram2 / linearProgram1 (RVO2 Agent.cpp:477-581) run as straight-line
-// predicated code over those registers.  Only the rare infeasible case (linearProgram3, Agent.cpp:583-630) spills the
-// lines to shared memory and takes the generic routine.
-template <int NO>
-__device__ __forceinline__ void orca_tpa_n(int n, int ego, const float4 *s_f4, const float *s_frad, float prefx,
-                                           float prefy, float maxSpeed, float timeHorizon, float timeStep, float collab,
-                                           float neighborDist, int maxNeighbors, SmemLines slines, float &nvx, float &nvy) {
-    const float4 me = s_f4[ego];
-    const float rad_me = s_frad[ego];
-    unsigned long long key[NO > 0 ? NO : 1];
-    int nn = 0;
-    const bool any = maxNeighbors > 0 && collab > 0.0f;
-    const float rangeSq = neighborDist * neighborDist;
-#pragma unroll
-    for (int j = 0; j < NO; ++j) {
-        const int o = j + (j >= ego ? 1 : 0);
-        key[j] = ~0ull;
-        if (any && o < n) {
-            const float4 ot = s_f4[o];
-            const float dx = me.x - ot.x, dy = me.y - ot.y;  // absSq(position_ - agent->position_), Agent.cpp:427
-            const float distSq = fdot(dx, dy, dx, dy);
-            if (distSq < rangeSq) {
-                key[j] = ((unsigned long long)__float_as_uint(distSq) << 32) | (unsigned)o;
-                ++nn;
-            }
-        }
-    }
-    sort_network<NO>([&](int i, int j) {
-        const unsigned long long ka = key[i], kb = key[j];
-        const bool sw = kb < ka;
-        key[i] = sw ? kb : ka;
-        key[j] = sw ? ka : kb;
-    });
-    if (nn > maxNeighbors) nn = maxNeighbors;
-    const float invTimeHorizon = 1.0f / timeHorizon;
-    Line ln[NO > 0 ? NO : 1];
-#pragma unroll
-    for (int k = 0; k < NO; ++k) {
-        ln[k] = Line{0.f, 0.f, 1.f, 0.f};
-        if (k < nn) {
-            const int o = (int)(key[k] & 0xffffffffull);
-            ln[k] = orca_line(me, rad_me, s_f4[o], s_frad[o], invTimeHorizon, timeStep, collab);
-        }
-    }
-    // linearProgram2 (Agent.cpp:550-581), closest-point mode
-    float rx, ry;
-    if (fdot(prefx, prefy, prefx, prefy) > maxSpeed * maxSpeed) {
-        const float inv = 1.0f / sqrtf(fdot(prefx, prefy, prefx, prefy));
-        rx = (prefx * inv) * maxSpeed;
-        ry = (prefy * inv) * maxSpeed;
-    } else {
-        rx = prefx;
-        ry = prefy;
-    }
-    int fail = -1;
-#pragma unroll
-    for (int i = 0; i < NO; ++i) {
-        if (fail < 0 && i < nn && fdet(ln[i].dx, ln[i].dy, ln[i].px - rx, ln[i].py - ry) > 0.0f) {
-            // linearProgram1 on line i (Agent.cpp:477-548)
-            const Line L = ln[i];
-            const float dotProduct = fdot(L.px, L.py, L.dx, L.dy);
-            const float discriminant = dotProduct * dotProduct + maxSpeed * maxSpeed - fdot(L.px, L.py, L.px, L.py);
-            bool ok = !(discriminant < 0.0f);
-            const float sqrtDiscriminant = sqrtf(discriminant);
-            float tLeft = -dotProduct - sqrtDiscriminant;
-            float tRight = -dotProduct + sqrtDiscriminant;
-#pragma unroll
-            for (int j = 0; j < i; ++j) {
-                const float denominator = fdet(L.dx, L.dy, ln[j].dx, ln[j].dy);
-                const float numerator = fdet(ln[j].dx, ln[j].dy, L.px - ln[j].px, L.py - ln[j].py);
-                if (fabsf(denominator) <= CAV_RVO_EPSILON) {
-                    if (numerator < 0.0f) ok = false;
-                } else {
-                    const float t = numerator / denominator;
-                    if (denominator >= 0.0f) tRight = min_keep(tRight, t);
-                    else tLeft = max_keep(tLeft, t);
-                }
-            }
-            // the reference returns false as soon as tLeft > tRight inside the loop; the bounds only tighten, so the
-            // final comparison is equivalent
-            if (ok && !(tLeft > tRight)) {
-                const float t = fdot(L.dx, L.dy, prefx - L.px, prefy - L.py);
-                const float tc = (t < tLeft) ? tLeft : ((t > tRight) ? tRight : t);
-                rx = L.px + tc * L.dx;
-                ry = L.py + tc * L.dy;
-            } else {
-                fail = i;
-            }
-        }
-    }
-    if (fail >= 0) {  // rare: infeasible -> linearProgram3 through shared memory (generic routine)
-#pragma unroll
-        for (int k = 0; k < NO; ++k)
-            if (k < nn) slines.set(k, ln[k]);
-        tpa_lp3(slines, nn, fail, maxSpeed, rx, ry);
-    }
-    nvx = rx;
-    nvy = ry;
-}
-
 // Register cap expressed as resident 128-thread-equivalents per SM (5 -> <= 102 registers).  Measured at 16384 x 10:
 // float32 61 us with 5 vs 69 / 65 us with 4 / 6; with single-warp CTAs float64 68 us vs 74 us for the generic kernel.
 template <typename T>
