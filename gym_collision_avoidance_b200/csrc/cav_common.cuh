@@ -182,17 +182,7 @@ struct WallMap {
     double origin0, origin1, cell, inv_cell;
 };
 
-// Map.world_coordinates_to_map_indices: floor(origin -/+ v/cell); v*inv_cell replaces the division unless the result
-// is within 1e-9 of an integer, where the exact quotient decides.
-__device__ __forceinline__ double cell_coord(double origin, double v, double cell, double inv_cell, bool negate) {
-    const double a = v * inv_cell;
-    double c = negate ? (origin - a) : (origin + a);
-    if (fabs(c - rint(c)) < 1e-9 * fmax(1.0, fabs(c))) {
-        const double q = v / cell;
-        c = negate ? (origin - q) : (origin + q);
-    }
-    return floor(c);
-}
+// cell_coord (Map.world_coordinates_to_map_indices) lives in cav_hd.cuh: it is also compiled by the CPU tests
 
 // collision_with_wall[i] (env.py:494-506): the agent's centre cell is inside the map and some static cell lies under
 // its disc mask (col-gy)^2 + (row-gx)^2 < (radius/cell)^2.  Cells are visited `step` apart starting at `first`

@@ -48,4 +48,17 @@ CAV_HDI unsigned float_bits(float f) {
 #endif
 }
 
+// Map.world_coordinates_to_map_indices (Map.py:28-29,36-37): floor(origin -/+ v/cell).  v*inv_cell replaces the division
+// unless the result is within 1e-9 of an integer, where the exact quotient decides -- so the cell is the reference's
+// for EVERY input (tests/test_geometry_native_cpu.py: random and adversarial values against NumPy's expression).
+CAV_HDI double cell_coord(double origin, double v, double cell, double inv_cell, bool negate) {
+    const double a = v * inv_cell;
+    double c = negate ? (origin - a) : (origin + a);
+    if (fabs(c - rint(c)) < 1e-9 * fmax(1.0, fabs(c))) {
+        const double q = v / cell;
+        c = negate ? (origin - q) : (origin + q);
+    }
+    return floor(c);
+}
+
 }  // namespace cav
