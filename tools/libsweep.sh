@@ -1,7 +1,7 @@
 #!/bin/bash
 # A/B experiment helper: run bench.py with alternative builds of the library (gpurun_libs/*.so); $PREC = f64|f32
 orig=gym_collision_avoidance_b200/csrc/libcavoid_sm100a.so
-cp $orig /tmp/orig.so
+mkdir -p gpurun_out; cp $orig gpurun_out/orig_lib.so
 for lib in "$@"; do
   [ "$lib" != "$orig" ] && cp $lib $orig
   echo "== $lib"
@@ -10,4 +10,4 @@ import json,sys
 d=json.loads(sys.stdin.read())
 print('%.3e'%d['value'], round(d['ms_per_step']*1e3,1), round(d['roofline']['kernel_ms']*1e3,1), round(d['roofline']['policy_move_kernel_ms']*1e3,1), round(d['roofline']['frac'],3))"
 done
-cp /tmp/orig.so $orig
+cp gpurun_out/orig_lib.so $orig

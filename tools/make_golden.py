@@ -45,7 +45,9 @@ class Cfg(_Base):
 
 def write_cfg(N, pre, post):
     body = CFG_TEMPLATE.format(N=N, pre="\n        ".join(pre) or "pass", post="\n        ".join(post) or "pass")
-    f = tempfile.NamedTemporaryFile("w", suffix=".py", delete=False, dir="/tmp")
+    scratch = os.path.join(ROOT, "gpurun_out")  # git-ignored scratch inside the repository
+    os.makedirs(scratch, exist_ok=True)
+    f = tempfile.NamedTemporaryFile("w", suffix=".py", delete=False, dir=scratch)
     f.write(body)
     f.close()
     return f.name
