@@ -1,6 +1,7 @@
 // cav_tpa_common.cuh -- pieces shared by the thread-per-agent kernels (cav_tpa.cu: any N <= 25; cav_tpa_n.cu:
 // compile-time N, register-resident).
 #pragma once
+#include "cav_keys.cuh"
 #include "cav_kernels.h"
 
 namespace cav {
@@ -64,44 +65,8 @@ struct TpaChunk<double> {
     static constexpr int CW = 16;  // measured at 16384 x 10, f64: CW 16 -> 50 us, 8 -> 64 us, 32 -> 60 us
 };
 
-template <typename T>
-struct KeyCodec;
-template <>
-struct KeyCodec<float> {
-    static constexpr int KB = 23;  // |kint| < 2^22: exact magic-number float -> int conversion
-    static constexpr int PB = 32;
-    static __device__ __forceinline__ unsigned long long po_bits(float po) {
-        unsigned u = __float_as_uint(po);
-        u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-        return (unsigned long long)u;
-    }
-};
-template <>
-struct KeyCodec<double> {
-    static constexpr int KB = 24;
-    static constexpr int PB = 34;
-    static __device__ __forceinline__ unsigned long long po_bits(double po) {
-        unsigned long long u = (unsigned long long)__double_as_longlong(po);
-        u = (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
-        return u >> 30;
-    }
-};
-
-// integer value of an integer-valued real with |v| < 2^22, without the XU pipe (F2I): magic-number addition
-__device__ __forceinline__ int real_to_int(float v) { return __float_as_int(__fadd_rn(v, 12582912.0f)) - 0x4B400000; }
-__device__ __forceinline__ int real_to_int(double v) { return __double2loint(__dadd_rn(v, 6755399441055744.0)); }
-
-template <typename T>
-__device__ __forceinline__ unsigned long long make_key(T kint_d, T po, int o, bool descending_kr) {
-    constexpr int KB = KeyCodec<T>::KB, PB = KeyCodec<T>::PB;
-    const T kmax = (T)(1 << (KB - 1));
-    T kc = kint_d < -kmax ? -kmax : (kint_d > kmax - (T)1 ? kmax - (T)1 : kint_d);
-    if (!(kc == kc)) kc = kmax - (T)1;  // NaN sorts last
-    unsigned long long kb = (unsigned long long)(unsigned)(real_to_int(kc) + (1 << (KB - 1)));
-    if (descending_kr) kb = ((1ull << KB) - 1ull) - kb;
-    return (kb << (PB + 6)) | (KeyCodec<T>::po_bits(po) << 6) | (unsigned long long)o;
-}
-
+// KeyCodec / real_to_int / make_key (the packed 64-bit neighbour sort keys) live in cav_keys.cuh: host/device source,
+// also compiled by tests/native/keys_host.cpp
 
 // Agent.take_action for one agent by one thread (agent.py:192-241: UnicycleDynamics.py:27-47 / MaxTurnRate :30-43 /
 // ExternalDynamics, Dynamics.update_ego_frame :31-41, history row agent.py:257-289, goal / timeout checks).
