@@ -3,7 +3,7 @@
 // key = [kint : KB bits | order-preserving bits of p_orth : PB bits | agent index : 6 bits], kint = rint(dist_2_other * 100)
 // (NumPy's round(x, 2) is rint(x * 100) / 100), so an unsigned 64-bit compare orders neighbours like the reference's
 // stable two-key sort `sorted(key=(round(dist, 2), p_orth))` (OtherAgentsStatesSensor.py:33-35) with ties in agent-index
-// order.  float32: 26 + 32 + 6 bits, exact up to the sign of a zero p_orth.  float64: 24 + the TOP 34 bits of p_orth + 6: keys whose kint fields are equal
+// order.  float32: 23 + 32 + 6 bits, exact up to the sign of a zero p_orth.  float64: 24 + the TOP 34 bits of p_orth + 6: keys whose kint fields are equal
 // are re-compared exactly by the kernels (bounded bubble pass, both precisions), which also covers +0.0 vs -0.0 and a
 // kint clamped at the field's range.
 // tests/test_keys_native_cpu.py compiles this file with g++ and checks those ordering properties.
