@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(128) k_policy_move_tpa(TpaBuffers b, KParams<T
 // Neighbour ordering key, one 64-bit word per neighbour:  [ kint | p_orth (order-preserving bits) | agent index ].
 //   kint = rint(dist_2_other * 100): ordering by round(dist_2_other, 2) == ordering by kint (NumPy rounds as
 //   rint(x*100)/100, OtherAgentsStatesSensor.py:103), biased and clamped into KB bits.
-//   float32 state: 26 + 32 + 6 bits -- exact.   float64 state: 24 + top 34 bits of p_orth + 6 bits; keys whose kint
+//   float32 state: 23 + 32 + 6 bits -- exact.   float64 state: 24 + top 34 bits of p_orth + 6 bits; keys whose kint
 //   fields are equal are re-compared exactly (kint as a real, full p_orth, index) by a bounded bubble pass, so the
 //   final order is exactly the reference's stable two-key sort also for clamped / truncated fields.
 template <typename T>
