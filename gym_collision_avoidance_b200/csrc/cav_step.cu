@@ -15,6 +15,7 @@
 // (SL per lane when N-1 > 32), distances / ORCA lines / sort keys live in registers, reductions and the bitonic
 // neighbour sort are warp shuffles.  The purely per-agent move phase runs one thread per agent.
 #include "cav_kernels.h"
+#include "cav_tti.cuh"
 #include "cav_orca.cuh"
 
 namespace cav {
@@ -320,45 +321,7 @@ struct ObsKey {
     int idx;
 };
 
-// util.compute_time_to_impact (util.py:23-79) with tangent_vecs_from_external_pt (:81-112), operation for operation
-// (same expression order as the oracle): host at (px,py) with velocity hv, other at (a,b) with velocity ov, r = the
-// combined radius.  Only + - * / sqrt, so the result is the reference's to the last bit in float64.
-template <typename T>
-__device__ T time_to_impact(T px, T py, T a, T b, T hvx, T hvy, T ovx, T ovy, T r) {
-    const T v0 = hvx - ovx, v1 = hvy - ovy;
-    const T sq = (px - a) * (px - a) + (py - b) * (py - b) - r * r;
-    if (sq < (T)0) return (T)0;  // already inside the collision zone
-    const T sqrt_term = M<T>::sqrt_(sq);
-    const T xnum1 = (r * r) * (px - a), xnum2 = r * (py - b) * sqrt_term;
-    const T ynum1 = (r * r) * (py - b), ynum2 = r * (px - a) * sqrt_term;
-    const T den = (px - a) * (px - a) + (py - b) * (py - b);
-    const T c1x = ((xnum1 + xnum2) / den + a) - px, c1y = ((ynum1 - ynum2) / den + b) - py;
-    const T c2x = ((xnum1 - xnum2) / den + a) - px, c2y = ((ynum1 + ynum2) / den + b) - py;
-    const T k1v = c1x * v1 - c1y * v0, k12 = c1x * c2y - c1y * c2x;
-    const T k2v = c2x * v1 - c2y * v0, k21 = c2x * c1y - c2y * c1x;
-    if (!(k1v * k12 >= (T)0 && k2v * k21 >= (T)0)) return M<T>::inf();  // v_rel outside the collision cone
-    if (M<T>::abs_(v0) < (T)1e-5 && M<T>::abs_(v1) < (T)1e-5) return M<T>::inf();
-    T x1, x2, y1, y2;
-    if (M<T>::abs_(v0) < (T)1e-5) {  // vertical v_rel
-        const T A = (T)1, B = (T)-2 * b, C = b * b + (px - a) * (px - a) - r * r;
-        x1 = x2 = px;
-        y1 = (-B + M<T>::sqrt_(B * B - (T)4 * A * C)) / ((T)2 * A);
-        y2 = (-B - M<T>::sqrt_(B * B - (T)4 * A * C)) / ((T)2 * A);
-    } else {
-        const T m = v1 / v0;
-        const T A = (T)1 + m * m;
-        const T B = (T)-2 * a + (T)2 * m * (py - b - m * px);
-        const T C = a * a - r * r + (m * px - (py - b)) * (m * px - (py - b));
-        x1 = (-B + M<T>::sqrt_(B * B - (T)4 * A * C)) / ((T)2 * A);
-        x2 = (-B - M<T>::sqrt_(B * B - (T)4 * A * C)) / ((T)2 * A);
-        y1 = m * (x1 - px) + py;
-        y2 = m * (x2 - px) + py;
-    }
-    const T d1 = M<T>::sqrt_((x1 - px) * (x1 - px) + (y1 - py) * (y1 - py));
-    const T d2 = M<T>::sqrt_((x2 - px) * (x2 - px) + (y2 - py) * (y2 - py));
-    const T d = d2 < d1 ? d2 : d1;  // Python min(d1, d2)
-    return d / M<T>::sqrt_(v0 * v0 + v1 * v1);
-}
+// time_to_impact<T> (util.compute_time_to_impact) lives in cav_tti.cuh: host/device source, also compiled by the CPU tests
 template <typename T>
 struct ObsKeyOps {
     static __device__ __forceinline__ bool less(const ObsKey<T> &a, const ObsKey<T> &b) {

@@ -352,3 +352,13 @@ int cavo_step(const cav_config_t *cfg, const cav_buffers_t *b, const float *ext,
         if ((rc = cavo_laserscan(cfg, b))) return rc;
     return 0;
 }
+
+/* util.compute_time_to_impact as restated in cav_oracle_impl.h, exported for the unit tests that pin it against values
+ * computed by the reference's own Python function (tests/test_tti_native_cpu.py). */
+double cavo_time_to_impact_f64(double px, double py, double a, double b, double hvx, double hvy, double ovx, double ovy,
+                               double r) {
+    return time_to_impact_f64(px, py, a, b, hvx, hvy, ovx, ovy, r);
+}
+float cavo_time_to_impact_f32(float px, float py, float a, float b, float hvx, float hvy, float ovx, float ovy, float r) {
+    return time_to_impact_f32(px, py, a, b, hvx, hvy, ovx, ovy, r);
+}
