@@ -16,10 +16,18 @@
 #define CAV_HD
 #define CAV_HDI inline
 #define CAV_HD_NOINLINE
-struct float4 {
+struct alignas(16) float4 {
     float x, y, z, w;
 };
+struct alignas(8) float2 {
+    float x, y;
+};
+struct alignas(16) double2 {
+    double x, y;
+};
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+static inline float2 make_float2(float x, float y) { return float2{x, y}; }
+static inline double2 make_double2(double x, double y) { return double2{x, y}; }
 #endif
 
 #ifndef CAV_MAX_AGENTS
