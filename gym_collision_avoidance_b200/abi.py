@@ -6,7 +6,7 @@ The product path has NO CPU fallback: :func:`load_library` raises if the CUDA li
 import ctypes
 import os
 
-CAV_ABI_VERSION = 1
+CAV_ABI_VERSION = 2
 
 # cav_status_t
 CAV_OK = 0
@@ -57,6 +57,7 @@ STAT_IS_DOUBLE = (CAV_STAT_SUM_TIME_TO_GOAL, CAV_STAT_SUM_EXTRA_TIME)
 CAV_HISTORY_ROW = 14
 CAV_BANK_ROW = 8
 CAV_MAX_AGENTS = 64
+CAV_KD_MAX_LEAF = 10  # RVO2 KdTree.h MAX_LEAF_SIZE: more agents than this split the agent kd-tree
 
 _d, _i = ctypes.c_double, ctypes.c_int32
 _vp = ctypes.c_void_p
@@ -87,7 +88,7 @@ class CavBuffers(ctypes.Structure):
     _fields_ = [(n, _vp) for n in (
         "pv", "goal", "ht", "ego", "flags", "kinds", "step_num", "num_active", "actions", "reward", "min_dist",
         "done", "game_over", "obs", "laser_count", "static_map_bits", "history", "aux0", "past_actions", "past_vel",
-        "episode", "stats")]
+        "episode", "stats", "kd_order")]
 
 
 BUFFER_FIELDS = [n for n, _ in CavBuffers._fields_]

@@ -9,6 +9,7 @@
 #include <new>
 
 #include "cav_kernels.h"
+#include "cav_kdtree.cuh"
 
 using namespace cav;
 
@@ -27,6 +28,7 @@ struct cav_handle_s {
     bool has_laser;
     bool use_tpa;  // one-thread-per-agent kernels (small N) instead of the sub-warp-group kernels
     bool use_tpa_n_policy;  // compile-time-N policy+move kernel (CAV_TPA_N_POLICY=0 disables)
+    bool use_v2_policy;     // k_policy_move_v2 (cav_policy.cu, N <= 32; CAV_POLICY_V2=0 falls back to the older kernels)
     bool use_tpa_n;  // ... and, where instantiated, the compile-time-N pairwise+obs kernel (CAV_TPA_N=0 disables)
     int launches;
     char err[512];
@@ -231,6 +233,8 @@ int cav_create(const cav_config_t *cfg, cav_handle_t *out) {
         if (const char *ev = getenv("CAV_TPA_N")) h->use_tpa_n = h->use_tpa && atoi(ev) != 0;
         h->use_tpa_n_policy = h->use_tpa;
         if (const char *ev = getenv("CAV_TPA_N_POLICY")) h->use_tpa_n_policy = h->use_tpa && atoi(ev) != 0;
+        h->use_v2_policy = cfg->num_agents >= 2 && cfg->num_agents <= 32 && tpa_max > 0;
+        if (const char *ev = getenv("CAV_POLICY_V2")) h->use_v2_policy = h->use_v2_policy && atoi(ev) != 0;
     }
     cudaError_t ce = cudaGetDevice(&h->device);
     if (ce == cudaSuccess) ce = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device);
@@ -273,6 +277,8 @@ int cav_bind(cav_handle_t h, const cav_buffers_t *bufs) {
     for (const void *p : optvec)
         if (p && ((uintptr_t)p & 15u)) return fail(h, CAV_ERR_MISALIGNED, "cav_bind: aux column not 16-byte aligned");
     if (h->has_laser && !bufs->laser_count) return fail(h, CAV_ERR_NULL_POINTER, "cav_bind: laser_count is NULL");
+    if (h->cfg.num_agents > CAV_KD_MAX_LEAF && !bufs->kd_order)
+        return fail(h, CAV_ERR_NULL_POINTER, "cav_bind: kd_order is NULL (required when num_agents > %d)", CAV_KD_MAX_LEAF);
     if (h->cfg.store_history && !bufs->history) return fail(h, CAV_ERR_NULL_POINTER, "cav_bind: history is NULL");
     h->bufs = *bufs;
     h->bound = true;
@@ -291,6 +297,17 @@ int cav_bind(cav_handle_t h, const cav_buffers_t *bufs) {
     } while (0)
 
 static int do_policy_move(cav_handle_t h, const float *ext, int phases, double dt, cudaStream_t st) {
+    if (h->use_v2_policy) {
+        const cudaError_t ce = (h->cfg.precision == CAV_F64)
+                                   ? run_policy_move_v2<double>(h->bufs, h->pd, ext, phases, dt, h->sm_count, st)
+                                   : run_policy_move_v2<float>(h->bufs, h->pf, ext, phases, dt, h->sm_count, st);
+        if (ce == cudaSuccess) {
+            h->launches++;
+            return CAV_OK;
+        }
+        if (ce != cudaErrorNotSupported) return fail(h, CAV_ERR_CUDA, "policy_move_v2: %s", cudaGetErrorString(ce));
+        h->use_v2_policy = false;
+    }
     if (h->use_tpa) {
         if (h->use_tpa_n_policy) {
             const cudaError_t ce = (h->cfg.precision == CAV_F64)
@@ -388,7 +405,7 @@ int cav_reset(cav_handle_t h, const uint8_t *env_mask, const cav_scenario_bank_t
 
 int cav_generate_scenarios(cav_handle_t h, const cav_scenario_gen_t *gen, double *rows, int32_t *case_kind,
                            int32_t num_scenarios, cav_stream_t stream) {
-    if (!h) return CAV_ERR_NULL_POINTER;
+    if (!valid(h)) return fail(nullptr, CAV_ERR_BAD_HANDLE, "cav_generate_scenarios: bad handle");
     if (!gen || !rows) return fail(h, CAV_ERR_NULL_POINTER, "cav_generate_scenarios: gen / rows is NULL");
     if (num_scenarios < 1) return fail(h, CAV_ERR_BAD_CONFIG, "cav_generate_scenarios: num_scenarios < 1");
     if (!(gen->side_length[0] > 0.0) || gen->side_length[1] < gen->side_length[0] ||
@@ -396,7 +413,7 @@ int cav_generate_scenarios(cav_handle_t h, const cav_scenario_gen_t *gen, double
         gen->radius_bnds[1] < gen->radius_bnds[0])
         return fail(h, CAV_ERR_BAD_CONFIG, "cav_generate_scenarios: bounds must be positive and ordered");
     if ((reinterpret_cast<uintptr_t>(rows) & 7u) != 0) return fail(h, CAV_ERR_MISALIGNED, "cav_generate_scenarios: rows misaligned");
-    h->launches = 1;
+    h->launches = 0;
     CAV_CUDA(h, "generate_scenarios",
              run_generate_scenarios(rows, case_kind, num_scenarios, h->cfg.num_agents, gen->seed, gen->side_length[0],
                                     gen->side_length[1], gen->speed_bnds, gen->radius_bnds, 0.2 /* GETTING_CLOSE_RANGE,

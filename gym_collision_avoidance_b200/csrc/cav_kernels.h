@@ -35,6 +35,12 @@ template <typename T>
 cudaError_t run_policy_move_tpa_n(const cav_buffers_t &bufs, const KParams<T> &p, const float *ext, int phases, double dt,
                                   int sm_count, cudaStream_t st);
 
+// second-generation thread-per-agent policy + move kernel (cav_policy.cu): every N in [2, 32], kd-tree order for N > 10;
+// cudaErrorNotSupported otherwise
+template <typename T>
+cudaError_t run_policy_move_v2(const cav_buffers_t &bufs, const KParams<T> &p, const float *ext, int phases, double dt,
+                               int sm_count, cudaStream_t st);
+
 struct LaserParams {
     int E, N, B, P, obs_len, obs_off;
     int rows, cols, wpr, nr;

@@ -233,11 +233,32 @@ template <int G, int SL>
 __device__ __forceinline__ void orca_group(unsigned gm, int glane, int n, int ego, const float4 *s_f4,
                                            const float *s_frad, float prefx, float prefy, float maxSpeed,
                                            float timeHorizon, float timeStep, float collab, float neighborDist,
-                                           int maxNeighbors, float &nvx, float &nvy) {
+                                           int maxNeighbors, const KdTree *kd, float &nvx, float &nvy) {
     const float4 me = s_f4[ego];
     const float rad_me = s_frad[ego];
     const float rangeSq = neighborDist * neighborDist;
     unsigned long long key[SL];
+    // tie-break of equal distSq = insertion order (Agent.cpp:424-448): the agent index inside a single kd-tree leaf
+    // (n <= 10), else the rank of the agent in the tree's visiting order for this ego (KdTree.cpp:266-298); every lane
+    // walks the (tiny) tree itself and keeps the ranks of the neighbours it owns
+    int ins[SL];
+#pragma unroll
+    for (int s = 0; s < SL; ++s) {
+        const int e = s * G + glane;
+        ins[s] = (e < ego) ? e : e + 1;
+    }
+    if (kd) {
+        int seq = 0;
+        int mine[SL];
+#pragma unroll
+        for (int s = 0; s < SL; ++s) mine[s] = ins[s];
+        kd_traverse(*kd, me.x, me.y, [&](int ag) {
+#pragma unroll
+            for (int s = 0; s < SL; ++s)
+                if (ag == mine[s]) ins[s] = seq;
+            ++seq;
+        });
+    }
 #pragma unroll
     for (int s = 0; s < SL; ++s) {
         const int e = s * G + glane;
@@ -247,7 +268,8 @@ __device__ __forceinline__ void orca_group(unsigned gm, int glane, int n, int eg
             const float4 ot = s_f4[o];
             const float dx = me.x - ot.x, dy = me.y - ot.y;  // absSq(position_ - agent->position_), Agent.cpp:427
             const float distSq = fdot(dx, dy, dx, dy);
-            if (distSq < rangeSq) key[s] = ((unsigned long long)__float_as_uint(distSq) << 32) | (unsigned)o;
+            if (distSq < rangeSq)
+                key[s] = ((unsigned long long)__float_as_uint(distSq) << 32) | ((unsigned)ins[s] << 8) | (unsigned)o;
         }
     }
     bitonic_sort<G, SL, U64Key>(gm, glane, key);
@@ -261,7 +283,7 @@ __device__ __forceinline__ void orca_group(unsigned gm, int glane, int n, int eg
         valid[s] = (key[s] != ~0ull) && rank < maxNeighbors;
         ln[s] = Line{0.f, 0.f, 1.f, 0.f};
         if (valid[s]) {
-            const int o = (int)(key[s] & 0xffffffffull);
+            const int o = (int)(key[s] & 0xffull);
             const float4 ot = s_f4[o];
             const float rpx = ot.x - me.x, rpy = ot.y - me.y;
             const float rvx = me.z - ot.z, rvy = me.w - ot.w;

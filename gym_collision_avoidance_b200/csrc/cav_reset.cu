@@ -20,6 +20,7 @@ struct ResetPtrs {
     void *aux0, *past_actions, *past_vel;
     int32_t *episode;
     unsigned long long *stats;
+    uint8_t *kd_order;
 };
 
 template <typename V>
@@ -137,6 +138,7 @@ __global__ void __launch_bounds__(256) k_reset(ResetPtrs b, ResetParams rp, cons
             if (b.past_actions) st4(reinterpret_cast<R4<T> *>(b.past_actions) + gi, z);
             if (b.past_vel) st4(reinterpret_cast<R4<T> *>(b.past_vel) + gi, z);
             if (b.laser_count) b.laser_count[gi] = 0u;
+            if (b.kd_order) b.kd_order[gi] = (uint8_t)a;  // new episode = new simulators: KdTree::agents_ is the identity
             if (b.min_dist) reinterpret_cast<T *>(b.min_dist)[gi] = (a < n) ? M<T>::inf() : (T)0;
         }
     }
@@ -166,6 +168,7 @@ cudaError_t run_reset(const cav_buffers_t &bufs, const ResetParams &rp, const ui
     p.past_vel = bufs.past_vel;
     p.episode = bufs.episode;
     p.stats = reinterpret_cast<unsigned long long *>(bufs.stats);
+    p.kd_order = bufs.kd_order;
     const int wpb = 8;
     int grid = (rp.E + wpb - 1) / wpb;
     if (grid > 148 * 16) grid = 148 * 16;

@@ -65,7 +65,8 @@ __device__ __forceinline__ size_t align16(size_t x) { return (x + 15) & ~(size_t
 // =============================================================================================================
 template <typename T, int G, int SL>
 __global__ void __launch_bounds__(512) k_policy_move(DevBuffers b, KParams<T> p, const float *__restrict__ ext,
-                                                       int phases, T dt, int EPB, int GPE, int ntiles) {
+                                                       uint8_t *__restrict__ kd_order, int phases, T dt, int EPB, int GPE,
+                                                       int ntiles) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = p.N;
     const int cap = EPB * N;
@@ -89,6 +90,17 @@ __global__ void __launch_bounds__(512) k_policy_move(DevBuffers b, KParams<T> p,
     uint32_t *s_kinds = reinterpret_cast<uint32_t *>(sp);
     sp += align16(sizeof(uint32_t) * cap);
     int *s_n = reinterpret_cast<int *>(sp);
+    sp += align16(sizeof(int) * EPB);
+    // agent kd-tree per environment (N > MAX_LEAF_SIZE only; cav_kdtree.cuh): boxes, node records, permutation, in-use flag
+    const bool kd_cfg = N > CAV_KD_MAX_LEAF && kd_order != nullptr;
+    const int kd_slots_n = 2 * N - 1;
+    float4 *s_kdbox = reinterpret_cast<float4 *>(sp);
+    sp += kd_cfg ? align16(sizeof(float4) * (size_t)EPB * kd_slots_n) : 0;
+    KdMeta *s_kdmeta = reinterpret_cast<KdMeta *>(sp);
+    sp += kd_cfg ? align16(sizeof(KdMeta) * (size_t)EPB * kd_slots_n) : 0;
+    uint8_t *s_kdperm = reinterpret_cast<uint8_t *>(sp);
+    sp += kd_cfg ? align16((size_t)cap) : 0;
+    uint8_t *s_kduse = reinterpret_cast<uint8_t *>(sp);
 
     const int tid = threadIdx.x;
     const unsigned gm = group_mask<G>();
@@ -125,10 +137,33 @@ __global__ void __launch_bounds__(512) k_policy_move(DevBuffers b, KParams<T> p,
         if (tid < ne) s_n[tid] = b.num_active ? b.num_active[e0 + tid] : N;
         __syncthreads();
 
+        // ---- doStep -> buildAgentTree (KdTree.cpp:47-111): one thread per environment advances the persistent agent
+        // permutation, if any RVO agent of the environment is still stepping its simulator --------------------------
+        if (kd_cfg && (phases & PH_POLICY)) {
+            if (tid < ne) {
+                const int n = s_n[tid], ebk = tid * N;
+                bool have_rvo = false;
+                for (int i = 0; i < n; ++i)
+                    have_rvo = have_rvo || (!(s_flags[ebk + i] & CAV_FLAG_DONE) &&
+                                            CAV_KIND_POLICY(s_kinds[ebk + i]) == CAV_POLICY_RVO);
+                const bool use = have_rvo && n > CAV_KD_MAX_LEAF;
+                s_kduse[tid] = use ? 1 : 0;
+                if (use) {
+                    KdTree t{s_kdbox + tid * kd_slots_n, s_kdmeta + tid * kd_slots_n, s_kdperm + ebk};
+                    for (int i = 0; i < n; ++i) t.perm[i] = kd_order[base + ebk + i];
+                    kd_build(s_f4 + ebk, n, t);
+                    for (int i = 0; i < n; ++i) kd_order[base + ebk + i] = t.perm[i];
+                }
+            }
+            __syncthreads();
+        }
+
         // ---- policy phase: one group per (env, agent) -------------------------------------------------------
         if ((phases & PH_POLICY) && g_el < ne && grp < EPB * GPE) {
             const int n = s_n[g_el];
             const int eb = g_el * N;
+            const KdTree kdt{s_kdbox + g_el * kd_slots_n, s_kdmeta + g_el * kd_slots_n, s_kdperm + eb};
+            const KdTree *kd = (kd_cfg && s_kduse[g_el]) ? &kdt : nullptr;
             for (int a = g_first; a < n; a += GPE) {
                 const int li = eb + a;
                 const uint32_t f = s_flags[li];
@@ -145,7 +180,7 @@ __global__ void __launch_bounds__(512) k_policy_move(DevBuffers b, KParams<T> p,
                     float nvx, nvy;
                     orca_group<G, SL>(gm, glane, n, a, s_f4 + eb, s_frad + eb, prefx, prefy, (float)gl.w,
                                       p.rvo_inv_time_horizon_num, p.rvo_time_step, p.rvo_collab, p.rvo_neighbor_dist,
-                                      p.rvo_max_neighbors, nvx, nvy);
+                                      p.rvo_max_neighbors, kd, nvx, nvy);
                     // Agent::update (Agent.cpp:470-475) in float, then RVOPolicy.py:96-111 in `real`
                     const float4 me = s_f4[li];
                     const float npx = me.x + nvx * p.rvo_time_step, npy = me.y + nvy * p.rvo_time_step;
@@ -614,10 +649,14 @@ void launch_geometry(int N, int &G, int &SL, int &GPE, int &EPB, int &threads) {
 }
 
 template <typename T>
-size_t smem_policy_move(int cap, int EPB) {
+size_t smem_policy_move(int cap, int EPB, int N) {
     auto a16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    size_t kd = 0;
+    if (N > CAV_KD_MAX_LEAF)
+        kd = a16(sizeof(float4) * (size_t)EPB * (2 * N - 1)) + a16(sizeof(KdMeta) * (size_t)EPB * (2 * N - 1)) + a16(cap) +
+             a16(EPB);
     return 4 * a16(sizeof(R4<T>) * cap) + a16(sizeof(float4) * cap) + a16(sizeof(float2) * cap) +
-           3 * a16(sizeof(float) * cap) + a16(sizeof(int) * EPB) + 64;
+           3 * a16(sizeof(float) * cap) + a16(sizeof(int) * EPB) + kd + 64;
 }
 template <typename T>
 size_t smem_pairwise_obs(int cap, int EPB, int groups, int CL) {
@@ -630,14 +669,14 @@ template <typename T, int G, int SL>
 static cudaError_t launch_pm(const cav_buffers_t &bufs, const KParams<T> &p, const float *ext, int phases, double dt,
                              int EPB, int GPE, int threads, int sm_count, cudaStream_t st) {
     const int ntiles = (p.E + EPB - 1) / EPB;
-    const size_t smem = smem_policy_move<T>(EPB * p.N, EPB);
+    const size_t smem = smem_policy_move<T>(EPB * p.N, EPB, p.N);
     auto kern = k_policy_move<T, G, SL>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
     const int grid = ntiles < sm_count * 16 ? ntiles : sm_count * 16;
-    kern<<<grid, threads, smem, st>>>(make_dev(bufs), p, ext, phases, (T)dt, EPB, GPE, ntiles);
+    kern<<<grid, threads, smem, st>>>(make_dev(bufs), p, ext, bufs.kd_order, phases, (T)dt, EPB, GPE, ntiles);
     return cudaGetLastError();
 }
 

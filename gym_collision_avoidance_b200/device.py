@@ -29,6 +29,9 @@ class DeviceState(object):
             self.t[name] = torch.zeros(shape, dtype=dt, device=self.device)
             self.kinds_of[name] = kind
         self.t["num_active"].fill_(c.num_agents)
+        if "kd_order" in self.t:
+            self.t["kd_order"].copy_(torch.arange(c.num_agents, dtype=torch.uint8, device=self.device).expand(
+                c.num_envs, c.num_agents))
         self.static_map_bits = None
 
     def __getattr__(self, k):

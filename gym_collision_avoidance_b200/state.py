@@ -24,6 +24,8 @@ def column_specs(c):
         "obs": ((E, N, c.obs_len), "real"),
         "episode": ((E,), "i32"), "stats": ((abi.CAV_STAT_NUM,), "u64"),
     }
+    if N > abi.CAV_KD_MAX_LEAF:  # RVO2's persistent kd-tree agent permutation (cavoid.h: kd_order)
+        specs["kd_order"] = ((E, N), "u8")
     if c.obs_offset[abi.CAV_OBS_LASERSCAN] >= 0:
         specs["laser_count"] = ((E, N), "u32")
     if c.store_history and c.history_len > 0:
@@ -49,6 +51,8 @@ class HostState(object):
             dt = self.real if kind == "real" else _NP_KIND[kind]
             self.arrays[name] = np.zeros(shape, dtype=dt)
         self.arrays["num_active"][:] = c.num_agents
+        if "kd_order" in self.arrays:
+            self.arrays["kd_order"][:] = np.arange(c.num_agents, dtype=np.uint8)
         self.static_map_bits = None
 
     def __getattr__(self, k):

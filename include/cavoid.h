@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define CAV_ABI_VERSION 1
+#define CAV_ABI_VERSION 2
 
 typedef enum {
     CAV_OK = 0,
@@ -209,6 +209,11 @@ typedef struct cav_buffers {
     void *past_vel;      /* real4 [E*N]: past_global_velocities[0,:], [1,:]; or NULL */
     int32_t *episode;    /* [E] episodes started per env (reset bookkeeping) */
     uint64_t *stats;     /* [CAV_STAT_NUM] per-handle episode statistics (doubles bit-cast for the SUM_* slots) */
+    uint8_t *kd_order;   /* [E*N] RVO2 KdTree::agents_ (KdTree.cpp:47-111): the simulators' persistent agent permutation,
+                          * re-partitioned in place by every step's buildAgentTree and reset to identity by cav_reset;
+                          * it fixes the neighbour order at exactly equal float distances (Agent.cpp:424-448).  Required
+                          * when num_agents > 10 (= MAX_LEAF_SIZE: below that the tree is one leaf and the order is the
+                          * agent index); may be NULL otherwise. */
 } cav_buffers_t;
 
 /* Scenario bank for reset: S scenarios x N agent rows.  Row = 8 doubles

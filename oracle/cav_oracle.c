@@ -157,36 +157,151 @@ static void orca_lp3(const orca_line_t *lines, int n, int beginLine, float radiu
     }
 }
 
-/* One ego solve: neighbours (R/Agent.cpp:44-56,424-448; insertion in agent-index order = single kd-tree leaf,
- * R/KdTree.cpp:266-271, exact for N <= 10; for N > 10 the kd-tree only changes the order of EXACT float
- * distance ties), ORCA lines (R/Agent.cpp:295-366), LP2 then LP3 (:417-421).
+/* ------------------------------------------------------------------------------------------------------------
+ * Agent kd-tree (R/KdTree.cpp:47-111 build, :266-298 query; MAX_LEAF_SIZE R/KdTree.h:48 = 10).
+ * `perm` is the simulator's persistent KdTree::agents_ permutation: buildAgentTree re-partitions it IN PLACE every
+ * doStep (R/RVOSimulator.cpp:163-168), it is never reset, so the leaf order -- and with it the order in which
+ * insertAgentNeighbor sees agents at EXACTLY equal float distances -- depends on the whole position history since
+ * the simulator was created (RVOPolicy.__init__, i.e. once per Agent / episode).  Every RVO agent of an environment
+ * owns its own simulator, but all of them are fed the same positions on the same steps from identity, so one
+ * permutation per environment reproduces them all.  For n <= 10 the root is a leaf: no swap ever happens.
+ * ---------------------------------------------------------------------------------------------------------- */
+#define CAVO_KD_MAX_LEAF 10
+typedef struct {
+    int begin, end, left, right;
+    float minX, maxX, minY, maxY;
+} kd_node_t;
+typedef struct {
+    kd_node_t node[2 * CAVO_MAX_AGENTS];
+    const uint8_t *perm;
+    const float *pos;
+} kd_tree_t;
+
+static void kd_build_rec(kd_tree_t *t, uint8_t *perm, int begin, int end, int node) { /* KdTree.cpp:62-111 */
+    const float *pos = t->pos;
+    kd_node_t *nd = &t->node[node];
+    nd->begin = begin;
+    nd->end = end;
+    nd->minX = nd->maxX = pos[2 * perm[begin]];
+    nd->minY = nd->maxY = pos[2 * perm[begin] + 1];
+    for (int i = begin + 1; i < end; ++i) {
+        const float x = pos[2 * perm[i]], y = pos[2 * perm[i] + 1];
+        nd->maxX = (nd->maxX < x) ? x : nd->maxX; /* std::max(a, b) = (a < b) ? b : a */
+        nd->minX = (x < nd->minX) ? x : nd->minX; /* std::min(a, b) = (b < a) ? b : a */
+        nd->maxY = (nd->maxY < y) ? y : nd->maxY;
+        nd->minY = (y < nd->minY) ? y : nd->minY;
+    }
+    if (end - begin > CAVO_KD_MAX_LEAF) {
+        const int isVertical = (nd->maxX - nd->minX > nd->maxY - nd->minY);
+        const float splitValue = isVertical ? 0.5f * (nd->maxX + nd->minX) : 0.5f * (nd->maxY + nd->minY);
+        int left = begin, right = end;
+        while (left < right) {
+            while (left < right && pos[2 * perm[left] + (isVertical ? 0 : 1)] < splitValue) ++left;
+            while (right > left && pos[2 * perm[right - 1] + (isVertical ? 0 : 1)] >= splitValue) --right;
+            if (left < right) {
+                const uint8_t tmp = perm[left];
+                perm[left] = perm[right - 1];
+                perm[right - 1] = tmp;
+                ++left;
+                --right;
+            }
+        }
+        if (left == begin) {
+            ++left;
+            ++right;
+        }
+        nd->left = node + 1;
+        nd->right = node + 2 * (left - begin);
+        kd_build_rec(t, perm, begin, left, nd->left);
+        kd_build_rec(t, perm, left, end, nd->right);
+    }
+}
+/* KdTree::buildAgentTree (KdTree.cpp:47-60): pos [n][2] float32, perm [n] updated in place */
+void cavo_kd_build(kd_tree_t *t, const float *pos, uint8_t *perm, int n) {
+    t->pos = pos;
+    t->perm = perm;
+    if (n > 0) kd_build_rec(t, perm, 0, n, 0);
+}
+/* Replays the persistent permutation over a sequence of position sets (test helper: the teacher-forced golden
+ * tests need the permutation the reference's simulators had reached at step t). pos_seq [steps][n][2] float32. */
+void cavo_kd_replay(const float *pos_seq, int steps, int n, uint8_t *perm) {
+    kd_tree_t t;
+    for (int i = 0; i < n; ++i) perm[i] = (uint8_t)i;
+    for (int s = 0; s < steps; ++s) cavo_kd_build(&t, pos_seq + (size_t)s * n * 2, perm, n);
+}
+
+typedef struct {
+    int ego, nn, maxNeighbors;
+    const float *pos;
+    int *nb_idx;
+    float *nb_d;
+} kd_query_t;
+/* Agent::insertAgentNeighbor, R/Agent.cpp:424-448 */
+static void orca_insert_neighbor(kd_query_t *q, int j, float *rangeSq) {
+    if (j == q->ego) return;
+    const float dx = q->pos[2 * q->ego] - q->pos[2 * j], dy = q->pos[2 * q->ego + 1] - q->pos[2 * j + 1];
+    const float distSq = o_dot(dx, dy, dx, dy);
+    if (distSq < *rangeSq) {
+        if (q->nn < q->maxNeighbors) ++q->nn;
+        int i = q->nn - 1;
+        while (i != 0 && distSq < q->nb_d[i - 1]) {
+            q->nb_d[i] = q->nb_d[i - 1];
+            q->nb_idx[i] = q->nb_idx[i - 1];
+            --i;
+        }
+        q->nb_d[i] = distSq;
+        q->nb_idx[i] = j;
+        if (q->nn == q->maxNeighbors) *rangeSq = q->nb_d[q->nn - 1];
+    }
+}
+static inline float o_sqr(float a) { return a * a; }
+static inline float o_max0(float a) { return (0.0f < a) ? a : 0.0f; } /* std::max(0.0f, a) */
+/* KdTree::queryAgentTreeRecursive, KdTree.cpp:266-298 */
+static void kd_query_rec(const kd_tree_t *t, kd_query_t *q, float *rangeSq, int node) {
+    const kd_node_t *nd = &t->node[node];
+    if (nd->end - nd->begin <= CAVO_KD_MAX_LEAF) {
+        for (int i = nd->begin; i < nd->end; ++i) orca_insert_neighbor(q, t->perm[i], rangeSq);
+        return;
+    }
+    const float px = q->pos[2 * q->ego], py = q->pos[2 * q->ego + 1];
+    const kd_node_t *L = &t->node[nd->left], *R = &t->node[nd->right];
+    const float distSqLeft = o_sqr(o_max0(L->minX - px)) + o_sqr(o_max0(px - L->maxX)) + o_sqr(o_max0(L->minY - py)) +
+                             o_sqr(o_max0(py - L->maxY));
+    const float distSqRight = o_sqr(o_max0(R->minX - px)) + o_sqr(o_max0(px - R->maxX)) + o_sqr(o_max0(R->minY - py)) +
+                              o_sqr(o_max0(py - R->maxY));
+    if (distSqLeft < distSqRight) {
+        if (distSqLeft < *rangeSq) {
+            kd_query_rec(t, q, rangeSq, nd->left);
+            if (distSqRight < *rangeSq) kd_query_rec(t, q, rangeSq, nd->right);
+        }
+    } else {
+        if (distSqRight < *rangeSq) {
+            kd_query_rec(t, q, rangeSq, nd->right);
+            if (distSqLeft < *rangeSq) kd_query_rec(t, q, rangeSq, nd->left);
+        }
+    }
+}
+
+/* One ego solve: neighbours (R/Agent.cpp:44-56 computeNeighbors -> kd-tree query -> insertAgentNeighbor :424-448; with
+ * tree == NULL agents are inserted in index order, which is what the single-leaf tree of n <= 10 agents does), ORCA
+ * lines (R/Agent.cpp:295-366), LP2 then LP3 (:417-421).
  * pos/vel [n][2] float32, rad [n] (already scaled), returns newVelocity. */
-void cavo_orca_solve(int n, int ego, const float *pos, const float *vel, const float *rad, float maxSpeed,
-                     float prefx, float prefy, float timeHorizon, float timeStep, float collab,
-                     float neighborDist, int maxNeighbors, float *out_vx, float *out_vy, orca_line_t *out_lines,
-                     int *out_nlines) {
+void cavo_orca_solve_kd(int n, int ego, const float *pos, const float *vel, const float *rad, float maxSpeed,
+                        float prefx, float prefy, float timeHorizon, float timeStep, float collab,
+                        float neighborDist, int maxNeighbors, const kd_tree_t *tree, float *out_vx, float *out_vy,
+                        orca_line_t *out_lines, int *out_nlines) {
     int nb_idx[CAVO_MAX_AGENTS];
     float nb_d[CAVO_MAX_AGENTS];
     int nn = 0;
     if (maxNeighbors > 0) {
         float rangeSq = neighborDist * neighborDist;
-        for (int j = 0; j < n; ++j) {
-            if (j == ego) continue;
-            const float dx = pos[2 * ego] - pos[2 * j], dy = pos[2 * ego + 1] - pos[2 * j + 1];
-            const float distSq = o_dot(dx, dy, dx, dy);
-            if (distSq < rangeSq) {
-                if (nn < maxNeighbors) ++nn;
-                int i = nn - 1;
-                while (i != 0 && distSq < nb_d[i - 1]) {
-                    nb_d[i] = nb_d[i - 1];
-                    nb_idx[i] = nb_idx[i - 1];
-                    --i;
-                }
-                nb_d[i] = distSq;
-                nb_idx[i] = j;
-                if (nn == maxNeighbors) rangeSq = nb_d[nn - 1];
-            }
+        kd_query_t q = {ego, 0, maxNeighbors, pos, nb_idx, nb_d};
+        if (tree) {
+            kd_query_rec(tree, &q, &rangeSq, 0);
+        } else {
+            for (int j = 0; j < n; ++j) orca_insert_neighbor(&q, j, &rangeSq);
         }
+        nn = q.nn;
     }
     orca_line_t lines[CAVO_MAX_AGENTS];
     int nl = 0;
@@ -253,6 +368,25 @@ void cavo_orca_solve(int n, int ego, const float *pos, const float *vel, const f
     *out_vy = ry;
     if (out_lines) memcpy(out_lines, lines, sizeof(orca_line_t) * (size_t)nl);
     if (out_nlines) *out_nlines = nl;
+}
+
+void cavo_orca_solve(int n, int ego, const float *pos, const float *vel, const float *rad, float maxSpeed,
+                     float prefx, float prefy, float timeHorizon, float timeStep, float collab,
+                     float neighborDist, int maxNeighbors, float *out_vx, float *out_vy, orca_line_t *out_lines,
+                     int *out_nlines) {
+    cavo_orca_solve_kd(n, ego, pos, vel, rad, maxSpeed, prefx, prefy, timeHorizon, timeStep, collab, neighborDist,
+                       maxNeighbors, NULL, out_vx, out_vy, out_lines, out_nlines);
+}
+/* One solve on a caller-held permutation (tests: bit-exact pin against the reference library over several doSteps).
+ * perm [n] is updated in place exactly like one buildAgentTree. */
+void cavo_orca_solve_perm(int n, int ego, const float *pos, const float *vel, const float *rad, float maxSpeed,
+                          float prefx, float prefy, float timeHorizon, float timeStep, float collab,
+                          float neighborDist, int maxNeighbors, uint8_t *perm, int rebuild, float *out_vx,
+                          float *out_vy) {
+    static __thread kd_tree_t t;
+    if (rebuild || t.pos != pos || t.perm != perm) cavo_kd_build(&t, pos, perm, n);
+    cavo_orca_solve_kd(n, ego, pos, vel, rad, maxSpeed, prefx, prefy, timeHorizon, timeStep, collab, neighborDist,
+                       maxNeighbors, &t, out_vx, out_vy, NULL, NULL);
 }
 
 /* ------------------------------------------------------------------------------------------------------------

@@ -47,6 +47,8 @@ def lib():
         L.cavo_orca_solve.argtypes = [ctypes.c_int, ctypes.c_int, fp, fp, fp, ctypes.c_float, ctypes.c_float,
                                       ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                                       ctypes.c_int, fp, fp, vp, ctypes.POINTER(ctypes.c_int)]
+        L.cavo_kd_build.argtypes = [vp, vp, vp, ctypes.c_int]
+        L.cavo_kd_build.restype = None
         _LIB = L
     return _LIB
 

@@ -87,6 +87,24 @@ static void SFX(policy_env)(const cav_config_t *cfg, const cav_buffers_t *b, con
             frad[a] = (float)((REAL)(1 + 5e-2) * goal[a].z); /* (1+5e-2)*radius, RVOPolicy.py:71 */
         }
     }
+    /* doStep -> kdTree_->buildAgentTree() (R/RVOSimulator.cpp:163-168): every live RVO agent's simulator holds the
+     * same permutation (see the kd-tree notes in cav_oracle.c), so it is advanced once per environment step. */
+    kd_tree_t kd;
+    const kd_tree_t *tree = NULL;
+    uint8_t local_perm[CAVO_MAX_AGENTS];
+    if (have_rvo && n > CAVO_KD_MAX_LEAF) {
+        uint8_t *perm = local_perm;
+        if (b->kd_order) {
+            perm = b->kd_order + (size_t)e * N;
+        } else {
+            for (int a = 0; a < n; ++a) local_perm[a] = (uint8_t)a;
+        }
+        cavo_kd_build(&kd, fpos, perm, n);
+        tree = &kd;
+#ifdef CAVO_TEST_NO_KD /* sensitivity experiments only: the pre-kd-tree restatement (index order) */
+        tree = NULL;
+#endif
+    }
     for (int i = 0; i < n; ++i) {
         if (flags[i] & CAV_FLAG_DONE) continue; /* env.py:311-312 (act keeps the last live action) */
         const uint32_t pol = CAV_KIND_POLICY(kinds[i]);
@@ -125,9 +143,9 @@ static void SFX(policy_env)(const cav_config_t *cfg, const cav_buffers_t *b, con
                     py_ = (float)(goal[who].w / on * ogy);
                     ms = (float)goal[who].w;
                 }
-                cavo_orca_solve(n, who, fpos, fvel, frad, ms, px_, py_, (float)cfg->rvo_time_horizon, (float)cfg->dt,
-                                who == i ? (float)cfg->rvo_collab_coeff : 0.5f, (float)cfg->rvo_neighbor_dist,
-                                cfg->rvo_max_neighbors, &tx, &ty, NULL, NULL);
+                cavo_orca_solve_kd(n, who, fpos, fvel, frad, ms, px_, py_, (float)cfg->rvo_time_horizon, (float)cfg->dt,
+                                   who == i ? (float)cfg->rvo_collab_coeff : 0.5f, (float)cfg->rvo_neighbor_dist,
+                                   cfg->rvo_max_neighbors, tree, &tx, &ty, NULL, NULL);
                 if (who == i) {
                     nvx = tx;
                     nvy = ty;
@@ -648,6 +666,7 @@ static void SFX(reset_env)(const cav_config_t *cfg, const cav_buffers_t *b, cons
         if (b->past_actions) memset((SFX(r4) *)b->past_actions + g, 0, sizeof(SFX(r4)));
         if (b->past_vel) memset((SFX(r4) *)b->past_vel + g, 0, sizeof(SFX(r4)));
         if (b->laser_count) b->laser_count[g] = 0;
+        if (b->kd_order) b->kd_order[g] = (uint8_t)i; /* new Agent -> new RVOPolicy -> new simulator: KdTree::agents_ = identity */
         if (b->min_dist) ((REAL *)b->min_dist)[g] = (REAL)INFINITY;
         /* env.reset zeroes the observation dict before sensing (env.py:276-281) */
         memset((REAL *)b->obs + g * cfg->obs_len, 0, sizeof(REAL) * (size_t)cfg->obs_len);

@@ -77,6 +77,33 @@ class Golden(object):
             st.laser_count[e, :self.n] = t + 1  # reset sensed once, then once per step
         if st.static_map_bits is None and "static_map" in self.z:
             st.static_map_bits = self.static_map_bits()
+        if "kd_order" in st.arrays:
+            st.kd_order[e] = self.kd_order(t)
+
+    def kd_order(self, t):
+        """RVO2's persistent kd-tree agent permutation after t steps of this episode (hidden simulator state the golden
+        cannot record: the reference library has no accessor for KdTree::agents_).  It is a pure function of the float32
+        position history, replayed here with the oracle's cavo_kd_build (itself pinned bit for bit against the reference
+        library on tie-heavy scenes, tests/test_oracle_rvo2.py).  The reference stops stepping an agent's simulator once
+        that agent is done, so replay while any RVO agent is live -- afterwards nobody reads it."""
+        if not hasattr(self, "_kd"):
+            import ctypes
+            import cav_oracle
+            L = cav_oracle.lib()
+            pos = np.ascontiguousarray(self.z["st_pv"][:, :self.n, 0:2].astype(np.float32))
+            T = pos.shape[0]
+            out = np.zeros((T + 1, self.N), np.uint8)
+            out[:] = np.arange(self.N, dtype=np.uint8)
+            perm = np.arange(self.n, dtype=np.uint8)
+            tree = ctypes.create_string_buffer(1 << 16)
+            rvo = (self.z["kinds"][:self.n] & 0xff) == abi.CAV_POLICY_RVO
+            for k in range(T):
+                live = (self.z["st_flags"][k][:self.n] & abi.CAV_FLAG_DONE) == 0
+                if self.n > abi.CAV_KD_MAX_LEAF and (live & rvo).any():
+                    L.cavo_kd_build(tree, pos[k].ctypes.data, perm.ctypes.data, self.n)
+                out[k + 1, :self.n] = perm
+            self._kd = out
+        return self._kd[t]
 
     def bank(self):
         rows = np.zeros((1, self.N, 8))
@@ -154,7 +181,8 @@ def compare_step(g, st, envs, ts, rtol, atol=None, check_aux=True):
     worst = max(worst, assert_close("dist_to_goal", G("ego")[..., 0], W("ego")[..., 0], *tol.pos))
     worst = max(worst, assert_close("heading_ego", G("ego")[..., 1], W("ego")[..., 1], *tol.ang, angle=True))
     worst = max(worst, assert_close("ref_prll", G("ego")[..., 2:], W("ego")[..., 2:], *tol.ang))
-    worst = max(worst, assert_close("reward", st.reward[envs][:, :n], z["rewards"][t0][:, :n], *tol.pos))
+    nr = 1 if g.meta["config"].get("TRAIN_SINGLE_AGENT") else n  # step() returns rewards[0] alone (env.py:454-455)
+    worst = max(worst, assert_close("reward", st.reward[envs][:, :nr], z["rewards"][t0][:, :nr], *tol.pos))
     live = (z["st_flags"][t0][:, :n] & abi.CAV_FLAG_DONE) == 0
     ga = st.actions[envs][:, :n].astype(np.float64)
     wa = z["actions"][t0][:, :n].astype(np.float64)

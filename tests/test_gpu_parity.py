@@ -31,10 +31,13 @@ def _inject_all(g, c):
     return st
 
 
-@pytest.fixture(params=["tpa", "group"])
+@pytest.fixture(params=["tpa", "group", "tpa_v1"])
 def mapping(request, monkeypatch):
-    """Run with both kernel families: one thread per agent (default for N <= 24) and sub-warp groups."""
-    monkeypatch.setenv("CAV_TPA_MAX_N", "32" if request.param == "tpa" else "0")
+    """Run with every kernel family: one thread per agent (default; policy + move = k_policy_move_v2 for N <= 32),
+    sub-warp groups, and the first-generation thread-per-agent policy kernels (CAV_POLICY_V2=0)."""
+    monkeypatch.setenv("CAV_TPA_MAX_N", "0" if request.param == "group" else "32")
+    if request.param == "tpa_v1":
+        monkeypatch.setenv("CAV_POLICY_V2", "0")
     return request.param
 
 

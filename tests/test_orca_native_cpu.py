@@ -30,6 +30,9 @@ def host(tmp_path_factory):
     L.host_orca_solve.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, fp, fp, fp] + [ctypes.c_float] * 7 + \
         [ctypes.c_int, fp, fp]
     L.host_orca_solve.restype = ctypes.c_int
+    L.host_orca_solve_kd.argtypes = [ctypes.c_int, ctypes.c_int, fp, fp, fp] + [ctypes.c_float] * 7 + \
+        [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, fp, fp]
+    L.host_orca_solve_kd.restype = ctypes.c_int
     return L
 
 
@@ -46,7 +49,7 @@ def test_device_orca_source_bit_exact_vs_reference_rvo2(host, n, side, trials):
     rng = np.random.RandomState(n * 977 + int(side * 10))
     dt, th = np.float32(0.1), np.float32(5.0)
     sim = R.rvo2ref_new(dt, np.float32(np.inf), 64, th, th, 0.0, 0.0, 0.0, 0.0)
-    variants = [0] + ([1] if n in (2, 3, 4, 5, 6, 8, 10, 12) else [])
+    variants = [0, 2] + ([1] if n in (2, 3, 4, 5, 6, 8, 10, 12) else []) + ([3] if n <= 10 else [])
     overlaps = 0
     for trial in range(trials):
         pos = rng.uniform(-side / 2, side / 2, size=(n, 2)).astype(np.float32)
@@ -95,10 +98,62 @@ def test_finite_neighbor_dist_and_max_neighbors_match_reference(host):
             ref_pos, ref_vel = np.zeros(2, np.float32), np.zeros(2, np.float32)
             R.rvo2ref_solve_ego(sim, n, ego, _fp(pos), _fp(vel), _fp(pref), _fp(rad), _fp(msp), np.float32(0.5),
                                 _fp(ref_pos), _fp(ref_vel))
-            for v in (0, 1):
+            for v in (0, 1, 2, 3):
                 ovx, ovy = ctypes.c_float(), ctypes.c_float()
                 assert host.host_orca_solve(v, n, ego, _fp(pos), _fp(vel), _fp(rad), msp[ego], pref[ego, 0], pref[ego, 1],
                                             th, dt, np.float32(0.5), nd, maxn, ctypes.byref(ovx), ctypes.byref(ovy)) == 0
                 got = np.array([ovx.value, ovy.value], np.float32)
                 assert got.tobytes() == ref_vel.tobytes(), (maxn, v, trial, got, ref_vel)
         R.rvo2ref_delete(sim)
+
+
+@pytest.mark.parametrize("n,kind", [(12, "circle"), (16, "circle"), (20, "circle"), (20, "lattice"), (33, "lattice"),
+                                    (64, "lattice"), (11, "stack"), (24, "circle_finite")])
+def test_device_kdtree_source_tie_order_bit_exact_vs_reference_rvo2(host, n, kind):
+    """cav_kdtree.cuh (the kernels' kd-tree: build over the persistent permutation + visiting order) and the generic
+    solver's insertion in that order, on scenes made of exact float32 distance ties, stepped for 60 doSteps against ONE
+    persistent reference simulator: bit-identical new velocity for every ego at every step (the same scenes as
+    tests/test_oracle_rvo2.py::test_kdtree_tie_order_bit_exact_vs_reference_rvo2, which pins the oracle)."""
+    import rvo2_ref
+    R = rvo2_ref.lib()
+    rng = np.random.RandomState(n)
+    dt, th = np.float32(0.1), np.float32(5.0)
+    nd = np.float32(3.0) if kind == "circle_finite" else np.float32(np.inf)
+    sim = R.rvo2ref_new(dt, nd, 64, th, th, 0.0, 0.0, 0.0, 0.0)
+    perm = np.arange(n, dtype=np.uint8)
+    if kind.startswith("circle"):
+        ang = 2 * np.pi * np.arange(n) / n
+        pos0 = np.stack([4 * np.cos(ang), 4 * np.sin(ang)], 1)
+        goal = -pos0
+    elif kind == "lattice":
+        side = int(np.ceil(np.sqrt(n)))
+        pos0 = np.array([[i % side, i // side] for i in range(n)], np.float64) * 1.5
+        pos0 = pos0[rng.permutation(n)]
+        goal = pos0[::-1].copy()
+    else:
+        pos0 = np.zeros((n, 2))
+        pos0[n // 2:] = [1.0, 0.0]
+        goal = pos0 + [3.0, 1.0]
+    pos = pos0.astype(np.float32)
+    vel = np.zeros((n, 2), np.float32)
+    rad = np.full(n, 0.5 * 1.05, np.float32)
+    msp = np.ones(n, np.float32)
+    for step in range(60):
+        pref = goal - pos
+        pref = (msp[:, None] * pref / np.maximum(np.linalg.norm(pref, axis=1, keepdims=True), 1e-9)).astype(np.float32)
+        rp, rv = np.zeros(2, np.float32), np.zeros(2, np.float32)
+        R.rvo2ref_solve_ego(sim, n, 0, _fp(pos), _fp(vel), _fp(pref), _fp(rad), _fp(msp), np.float32(0.5), _fp(rp), _fp(rv))
+        all_ref = np.zeros((n, 2), np.float32)
+        for a in range(n):
+            R.rvo2ref_get_velocity(sim, a, _fp(all_ref[a]))
+        for ego in range(n):
+            ovx, ovy = ctypes.c_float(), ctypes.c_float()
+            rc = host.host_orca_solve_kd(n, ego, _fp(pos), _fp(vel), _fp(rad), msp[ego], pref[ego, 0], pref[ego, 1], th, dt,
+                                         np.float32(0.5), nd, 64, perm.ctypes.data, int(ego == 0), ctypes.byref(ovx),
+                                         ctypes.byref(ovy))
+            assert rc == 0
+            got = np.array([ovx.value, ovy.value], np.float32)
+            assert got.tobytes() == all_ref[ego].tobytes(), (kind, step, ego, got, all_ref[ego], perm.tolist())
+        vel = all_ref
+        pos = (pos + vel * dt).astype(np.float32)
+    R.rvo2ref_delete(sim)

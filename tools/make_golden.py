@@ -131,7 +131,10 @@ def run_scenario(name, N, agents_fn, pre=(), post=(), max_steps=400, ext_action_
         states.append(st)
         obs_seq.append(pack_obs(obs, Config, N))
         r = np.zeros(N)
-        r[:n] = np.asarray(rew, dtype=np.float64).reshape(-1)[:n] if np.ndim(rew) else rew
+        if np.ndim(rew):
+            r[:n] = np.asarray(rew, dtype=np.float64).reshape(-1)[:n]
+        else:  # Config.TRAIN_SINGLE_AGENT: step() returns rewards[0] only (env.py:454-455)
+            r[0] = rew
         rewards.append(r)
         d = np.zeros(N, np.uint8)
         for i, a in enumerate(env.agents):
@@ -382,19 +385,49 @@ def laser6():  # laserscan (512 beams x 3 past) + neighbour rows, RVO, agents ne
 
 
 @scenario
-def laser20_circle():  # BASELINE config[3] shape: 20 agents RVO + 512-beam laserscan (reference gen_circle_test_case)
+def laser20_circle():  # BASELINE config[3] shape: 20 agents RVO + 512-beam laserscan, the reference's own symmetric
+    # gen_circle_test_case (exact float32 distance ties -> kd-tree leaf order decides the ORCA neighbour order)
     def agents(tc, C):
-        rows = tc.gen_circle_test_case(20, 7.0)
-        rows[:, 4] = np.linspace(0.8, 1.3, 20)  # break the exact symmetry (no float distance ties)
-        rows[:, 5] = np.linspace(0.3, 0.55, 20)
-        rows[:, 0:2] += np.random.RandomState(3).uniform(-0.3, 0.3, size=(20, 2))
-        return mk_agents(tc, rows, "RVO", sensors=("other_agents_states", "laserscan"))
+        return mk_agents(tc, tc.gen_circle_test_case(20, 7.0), "RVO", sensors=("other_agents_states", "laserscan"))
 
     run_scenario("laser20_circle", 20, agents,
                  pre=["self.USE_STATIC_MAP = True",
                       "self.STATES_IN_OBS = ['is_learning','num_other_agents','dist_to_goal','heading_ego_frame',"
                       "'pref_speed','radius','other_agents_states','laserscan']"],
-                 post=EVAL_POST, stop_after=5)
+                 post=EVAL_POST, stop_after=8)
+
+
+# ---- the reference's own symmetric presets, UN-perturbed, whole episodes: exact float32 distance ties at every step,
+# so the ORCA neighbour order is decided by the kd-tree's persistent agent permutation (KdTree.cpp:47-111,266-298) ----
+def _circle(name, n, radius, **kw):
+    def f():
+        run_scenario(name, n, lambda tc, C: mk_agents(tc, tc.gen_circle_test_case(n, radius), "RVO"), post=EVAL_POST,
+                     **kw)
+    f.__name__ = name
+    return scenario(f)
+
+
+_circle("circle20_r10", 20, 10.0)   # preset_testCases(20) (test_cases.py:884-889)
+_circle("circle16_r8", 16, 8.0)
+_circle("circle12_r6", 12, 6.0)
+_circle("circle10_r5", 10, 5.0, stop_after=150)     # single leaf (n <= MAX_LEAF_SIZE): index order
+
+
+@scenario
+def single_agent_train():  # Config.TRAIN_SINGLE_AGENT: game_over = done[0] (env.py:541-542), scalar reward rewards[0]
+    # (env.py:454-455); agent 0 learning (external actions), the others RVO / noncoop
+    def agents(tc, C):
+        rows = np.array(fixture_rows(tc, 4, 3), dtype=np.float64)
+        rows[0, 2:4] = rows[0, 0:2] + [1.6, 0.9]  # agent 0 arrives while the others are still under way
+        hd = np.random.uniform(-np.pi, np.pi, size=4)
+        hd[0] = np.arctan2(0.9, 1.6)
+        return mk_agents(tc, rows, ["learning", "RVO", "noncoop", "RVO"], headings=hd)
+
+    def ext(rng, i, t):
+        return np.array([rng.uniform(0.8, 1.0), rng.uniform(0.45, 0.55)], np.float32)
+
+    run_scenario("single_agent_train", 4, agents, post=["self.TRAIN_SINGLE_AGENT = True"], ext_action_fn=ext,
+                 max_steps=200)
 
 
 @scenario
