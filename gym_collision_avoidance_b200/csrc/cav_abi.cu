@@ -27,8 +27,7 @@ struct cav_handle_s {
     ResetParams rp;
     bool has_laser;
     bool use_tpa;  // one-thread-per-agent kernels (small N) instead of the sub-warp-group kernels
-    bool use_tpa_n_policy;  // compile-time-N policy+move kernel (CAV_TPA_N_POLICY=0 disables)
-    bool use_v2_policy;     // k_policy_move_v2 (cav_policy.cu, N <= 32; CAV_POLICY_V2=0 falls back to the older kernels)
+    bool use_v2_policy;  // k_policy_move_v2 (cav_policy.cu, thread per agent, N <= 32) instead of the sub-warp-group kernel
     bool use_tpa_n;  // ... and, where instantiated, the compile-time-N pairwise+obs kernel (CAV_TPA_N=0 disables)
     int launches;
     char err[512];
@@ -231,10 +230,10 @@ int cav_create(const cav_config_t *cfg, cav_handle_t *out) {
         // compile-time-N kernels wherever they apply (16384 x 10: float32 24 us vs 38 us generic, float64 39 us vs 50 us)
         h->use_tpa_n = h->use_tpa;
         if (const char *ev = getenv("CAV_TPA_N")) h->use_tpa_n = h->use_tpa && atoi(ev) != 0;
-        h->use_tpa_n_policy = h->use_tpa;
-        if (const char *ev = getenv("CAV_TPA_N_POLICY")) h->use_tpa_n_policy = h->use_tpa && atoi(ev) != 0;
+        // policy + move: thread per agent up to 32 agents (k_policy_move_v2), sub-warp groups above (and under
+        // CAV_TPA_MAX_N=0, which the tests use to run the group kernels at every N)
         h->use_v2_policy = cfg->num_agents >= 2 && cfg->num_agents <= 32 && tpa_max > 0;
-        if (const char *ev = getenv("CAV_POLICY_V2")) h->use_v2_policy = h->use_v2_policy && atoi(ev) != 0;
+        if (const char *ev = getenv("CAV_POLICY_GROUP")) h->use_v2_policy = h->use_v2_policy && atoi(ev) == 0;
     }
     cudaError_t ce = cudaGetDevice(&h->device);
     if (ce == cudaSuccess) ce = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device);
@@ -307,24 +306,6 @@ static int do_policy_move(cav_handle_t h, const float *ext, int phases, double d
         }
         if (ce != cudaErrorNotSupported) return fail(h, CAV_ERR_CUDA, "policy_move_v2: %s", cudaGetErrorString(ce));
         h->use_v2_policy = false;
-    }
-    if (h->use_tpa) {
-        if (h->use_tpa_n_policy) {
-            const cudaError_t ce = (h->cfg.precision == CAV_F64)
-                                       ? run_policy_move_tpa_n<double>(h->bufs, h->pd, ext, phases, dt, h->sm_count, st)
-                                       : run_policy_move_tpa_n<float>(h->bufs, h->pf, ext, phases, dt, h->sm_count, st);
-            if (ce == cudaSuccess) {
-                h->launches++;
-                return CAV_OK;
-            }
-            if (ce != cudaErrorNotSupported) return fail(h, CAV_ERR_CUDA, "policy_move_tpa_n: %s", cudaGetErrorString(ce));
-            h->use_tpa_n_policy = false;
-        }
-        if (h->cfg.precision == CAV_F64)
-            CAV_CUDA(h, "policy_move_tpa", run_policy_move_tpa<double>(h->bufs, h->pd, ext, phases, dt, h->sm_count, st));
-        else
-            CAV_CUDA(h, "policy_move_tpa", run_policy_move_tpa<float>(h->bufs, h->pf, ext, phases, dt, h->sm_count, st));
-        return CAV_OK;
     }
     if (h->cfg.precision == CAV_F64)
         CAV_CUDA(h, "policy_move", run_policy_move<double>(h->bufs, h->pd, ext, phases, dt, h->sm_count, st));

@@ -17,10 +17,7 @@ template <typename T>
 cudaError_t run_pairwise_obs(const cav_buffers_t &bufs, const KParams<T> &p, const ObsPlan &plan, const WallMap &wm,
                              const uint8_t *env_mask, int obs_only, int sm_count, cudaStream_t st);
 
-// one-thread-per-agent variants (cav_tpa.cu), used for small N
-template <typename T>
-cudaError_t run_policy_move_tpa(const cav_buffers_t &bufs, const KParams<T> &p, const float *ext, int phases, double dt,
-                                int sm_count, cudaStream_t st);
+// one-thread-per-agent pairwise+obs kernel (cav_tpa.cu), any observation layout, N <= 24
 template <typename T>
 cudaError_t run_pairwise_obs_tpa(const cav_buffers_t &bufs, const KParams<T> &p, const ObsPlan &plan,
                                  const WallMap &wm, const uint8_t *env_mask, int obs_only, int sm_count,
@@ -31,12 +28,9 @@ template <typename T>
 cudaError_t run_pairwise_obs_tpa_n(const cav_buffers_t &bufs, const KParams<T> &p, const ObsPlan &plan, const WallMap &wm,
                                    const uint8_t *env_mask, int obs_only, int sm_count, cudaStream_t st);
 
-template <typename T>
-cudaError_t run_policy_move_tpa_n(const cav_buffers_t &bufs, const KParams<T> &p, const float *ext, int phases, double dt,
-                                  int sm_count, cudaStream_t st);
 
-// second-generation thread-per-agent policy + move kernel (cav_policy.cu): every N in [2, 32], kd-tree order for N > 10;
-// cudaErrorNotSupported otherwise
+// thread-per-agent policy + move kernel (cav_policy.cu): every N in [2, 32], kd-tree order for N > 10;
+// cudaErrorNotSupported otherwise (N = 1 and N > 32: the sub-warp-group kernel above)
 template <typename T>
 cudaError_t run_policy_move_v2(const cav_buffers_t &bufs, const KParams<T> &p, const float *ext, int phases, double dt,
                                int sm_count, cudaStream_t st);

@@ -17,122 +17,10 @@
 // Arithmetic (expression order, -fmad=false, IEEE sqrt/div) is identical to the group kernels and the oracle.
 #include <cstdlib>
 
-#include "cav_orca_tpa.cuh"
 #include "cav_tpa_common.cuh"
 
 namespace cav {
 
-enum { PH_POLICY = 1, PH_MOVE = 2 };
-
-// =============================================================================================================
-// kernel A (TPA): policy + move
-// =============================================================================================================
-template <typename T>
-__global__ void __launch_bounds__(128) k_policy_move_tpa(TpaBuffers b, KParams<T> p, const float *__restrict__ ext,
-                                                           int phases, T dt, int EPB, int ntiles) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int N = p.N;
-    const int cap = EPB * N;
-    const int nt = blockDim.x;
-    unsigned char *sp = smem_raw;
-    float4 *s_f4 = reinterpret_cast<float4 *>(sp);
-    sp += a16(sizeof(float4) * cap);
-    float4 *s_lines = reinterpret_cast<float4 *>(sp);
-    sp += a16(sizeof(float4) * (size_t)(N - 1) * nt);
-    unsigned long long *s_keys = reinterpret_cast<unsigned long long *>(sp);
-    sp += a16(sizeof(unsigned long long) * (size_t)(N - 1) * nt);
-    float *s_frad = reinterpret_cast<float *>(sp);
-    sp += a16(sizeof(float) * cap);
-    int *s_n = reinterpret_cast<int *>(sp);
-
-    const int tid = threadIdx.x;
-    R4<T> *g_pv = reinterpret_cast<R4<T> *>(b.pv);
-    R4<T> *g_goal = reinterpret_cast<R4<T> *>(b.goal);
-    R4<T> *g_ht = reinterpret_cast<R4<T> *>(b.ht);
-    R4<T> *g_ego = reinterpret_cast<R4<T> *>(b.ego);
-
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int e0 = tile * EPB;
-        const int ne = min(EPB, p.E - e0);
-        const int count = ne * N;
-        const size_t base = (size_t)e0 * N;
-        const bool have = tid < count;
-        const size_t gi = base + tid;
-        R4<T> pv{}, gl{}, ht{};
-        uint32_t f = 0, kind = 0;
-        if (have) {
-            pv = ld4(g_pv + gi);
-            gl = ld4(g_goal + gi);
-            ht = ld4(g_ht + gi);
-            f = b.flags[gi];
-            kind = b.kinds[gi];
-            // what RVOPolicy.py:57-74 pushes into the float32 simulator
-            s_f4[tid] = make_float4((float)pv.x, (float)pv.y, (float)pv.z, (float)pv.w);
-            s_frad[tid] = (float)(p.rvo_radius_scale * gl.z);
-        }
-        if (tid < ne) s_n[tid] = b.num_active ? b.num_active[e0 + tid] : N;
-        __syncthreads();
-
-        const int el = tid / N, a = tid - el * N;
-        if (have && a < s_n[el]) {
-            const int n = s_n[el];
-            const int eb = el * N;
-            float2 act = make_float2(0.f, 0.f);
-            bool have_act = false;
-            // ---- action selection (env.py:310-323) ----
-            if ((phases & PH_POLICY) && !(f & CAV_FLAG_DONE)) {
-                const uint32_t pol = CAV_KIND_POLICY(kind);
-                T a0 = (T)0, a1 = (T)0;
-                if (pol == CAV_POLICY_RVO) {
-                    const T gx = gl.x - pv.x, gy = gl.y - pv.y;  // RVOPolicy.py:66
-                    const T nrm = M<T>::sqrt_(gx * gx + gy * gy);
-                    const T sc = gl.w / nrm;  // :67
-                    const float prefx = (float)(sc * gx), prefy = (float)(sc * gy);
-                    float nvx, nvy;
-                    orca_tpa(n, a, s_f4 + eb, s_frad + eb, prefx, prefy, (float)gl.w, p.rvo_inv_time_horizon_num,
-                             p.rvo_time_step, p.rvo_collab, p.rvo_neighbor_dist, p.rvo_max_neighbors, s_keys + tid, nt,
-                             SmemLines{s_lines + tid, nt}, nvx, nvy);
-                    // Agent::update (Agent.cpp:470-475) in float, then RVOPolicy.py:96-111 in `real`
-                    const float4 me = s_f4[tid];
-                    const float npx = me.x + nvx * p.rvo_time_step, npy = me.y + nvy * p.rvo_time_step;
-                    const T dpx = (T)npx - pv.x, dpy = (T)npy - pv.y;
-                    const T ang1 = M<T>::atan2_(dpy, dpx);
-                    const T new_heading = pymod<T>(ang1 - (T)0, two_pi<T>());
-                    T dh = wrap<T>(new_heading - ht.x);
-                    T spd = p.rvo_inv_dt * M<T>::sqrt_(dpx * dpx + dpy * dpy);
-                    if (M<T>::abs_(dh) > p.rvo_max_delta_heading) {
-                        dh = sign<T>(dh) * p.rvo_max_delta_heading;
-                        spd = (T)0;
-                    }
-                    a0 = spd;
-                    a1 = dh;
-                } else if (pol == CAV_POLICY_NONCOOP) {  // NonCooperativePolicy.py:21
-                    a0 = gl.w;
-                    a1 = -ld4(g_ego + gi).y;
-                } else if (pol == CAV_POLICY_STATIC) {  // StaticPolicy.py:21-22: goal := pos
-                    gl.x = pv.x;
-                    gl.y = pv.y;
-                    st4(g_goal + gi, gl);
-                } else if (pol == CAV_POLICY_EXTERNAL) {  // ExternalPolicy.py:14-16
-                    const float2 x = ext ? reinterpret_cast<const float2 *>(ext)[gi] : make_float2(0.f, 0.f);
-                    a0 = (T)x.x;
-                    a1 = (T)x.y;
-                } else {  // CAV_POLICY_LEARNING, LearningPolicy.py:30-32
-                    const float2 x = ext ? reinterpret_cast<const float2 *>(ext)[gi] : make_float2(0.f, 0.f);
-                    a1 = p.max_heading_change * ((T)2. * (T)x.y - (T)1.);
-                    a0 = gl.w * (T)x.x;
-                }
-                act = make_float2((float)a0, (float)a1);  // float32 store, env.py:305-307
-                have_act = true;
-                reinterpret_cast<float2 *>(b.actions)[gi] = act;
-            }
-            // ---- move (Agent.take_action, agent.py:192-241) ----
-            if (phases & PH_MOVE) tpa_move<T>(b, p, gi, pv, gl, ht, f, kind, act, have_act, dt);
-
-        }
-        __syncthreads();  // shared memory is re-staged by the next tile
-    }
-}
 
 // =============================================================================================================
 // kernel B (TPA): pairwise collisions + rewards + sorted-neighbour observation + done
@@ -517,34 +405,11 @@ static int build_chunks(const ObsPlan &plan, int K, int cw, ChunkPlan &cp) {
 }
 
 template <typename T>
-size_t tpa_smem_policy_move(int N, int EPB, int nt) {
-    const int cap = EPB * N;
-    return a16(sizeof(float4) * cap) + a16(sizeof(float4) * (size_t)(N - 1) * nt) +
-           a16(sizeof(unsigned long long) * (size_t)(N - 1) * nt) + a16(sizeof(float) * cap) + a16(sizeof(int) * EPB) + 64;
-}
-template <typename T>
 size_t tpa_smem_pairwise_obs(int N, int EPB, int nt, int region_bytes) {
     const int cap = EPB * N;
     const int nwarps = (nt + 31) / 32;
     return a16(sizeof(R4<T>) * cap) + a16(sizeof(T) * cap) + a16(sizeof(T) * (size_t)N * nt) +
            a16((size_t)nwarps * region_bytes) + a16((size_t)cap) + a16(sizeof(int) * EPB) + 64;
-}
-
-template <typename T>
-cudaError_t run_policy_move_tpa(const cav_buffers_t &bufs, const KParams<T> &p, const float *ext, int phases, double dt,
-                                int sm_count, cudaStream_t st) {
-    int EPB, threads;
-    tpa_geometry(p.N, EPB, threads);
-    const int ntiles = (p.E + EPB - 1) / EPB;
-    const size_t smem = tpa_smem_policy_move<T>(p.N, EPB, threads);
-    auto kern = k_policy_move_tpa<T>;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
-    const int grid = ntiles < sm_count * 16 ? ntiles : sm_count * 16;
-    kern<<<grid, threads, smem, st>>>(make_tpa(bufs), p, ext, phases, (T)dt, EPB, ntiles);
-    return cudaGetLastError();
 }
 
 template <typename T>
@@ -571,17 +436,10 @@ cudaError_t run_pairwise_obs_tpa(const cav_buffers_t &bufs, const KParams<T> &p,
 size_t tpa_smem_bytes(int N, int precision_f64, const ObsPlan &plan, int K) {
     int EPB, threads;
     tpa_geometry(N, EPB, threads);
-    const size_t a = precision_f64 ? tpa_smem_policy_move<double>(N, EPB, threads) : tpa_smem_policy_move<float>(N, EPB, threads);
-    const size_t bb = precision_f64
-                          ? tpa_smem_pairwise_obs<double>(N, EPB, threads, tpa_region_bytes<double>(N, plan, K))
-                          : tpa_smem_pairwise_obs<float>(N, EPB, threads, tpa_region_bytes<float>(N, plan, K));
-    return a > bb ? a : bb;
+    return precision_f64 ? tpa_smem_pairwise_obs<double>(N, EPB, threads, tpa_region_bytes<double>(N, plan, K))
+                         : tpa_smem_pairwise_obs<float>(N, EPB, threads, tpa_region_bytes<float>(N, plan, K));
 }
 
-template cudaError_t run_policy_move_tpa<float>(const cav_buffers_t &, const KParams<float> &, const float *, int,
-                                                double, int, cudaStream_t);
-template cudaError_t run_policy_move_tpa<double>(const cav_buffers_t &, const KParams<double> &, const float *, int,
-                                                 double, int, cudaStream_t);
 template cudaError_t run_pairwise_obs_tpa<float>(const cav_buffers_t &, const KParams<float> &, const ObsPlan &,
                                                  const WallMap &, const uint8_t *, int, int, cudaStream_t);
 template cudaError_t run_pairwise_obs_tpa<double>(const cav_buffers_t &, const KParams<double> &, const ObsPlan &,

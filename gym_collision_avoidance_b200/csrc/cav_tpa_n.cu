@@ -12,7 +12,6 @@
 // K = N-1); every other configuration takes the generic kernel.  Arithmetic is identical to the generic kernel.
 #include <type_traits>
 
-#include "cav_orca_tpa.cuh"
 #include "cav_sortnet.cuh"
 #include "cav_tpa_common.cuh"
 
@@ -64,10 +63,6 @@ struct TpaNShape {
     static constexpr bool FLAT4 = sizeof(T) == 4 && P == 1 && WS == CL;
     static constexpr size_t r16(size_t x) { return (x + 15) & ~(size_t)15; }
     static constexpr size_t WARP_BYTES = r16(sizeof(R4<T>) * LW) + r16(sizeof(T) * LW) + r16(sizeof(T) * (LW * WS + 4));
-    // policy kernel slice: float4 state [LW], linearProgram3 scratch lines [NO][32], float radius [LW]
-    static constexpr size_t PM_F4 = r16(sizeof(float4) * LW);
-    static constexpr size_t PM_LINES = r16(sizeof(float4) * (NO > 0 ? NO : 1) * 32);
-    static constexpr size_t PM_WARP_BYTES = PM_F4 + PM_LINES + r16(sizeof(float) * LW);
 };
 
 template <typename T, int NT>
@@ -338,159 +333,6 @@ __global__ void __launch_bounds__(32 * TpaNShape<T, NT>::WARPS, (TpaNBounds<T>::
         __syncwarp();
     }
 }
-
-// =============================================================================================================
-// policy + move with compile-time N (reference env.py:304-327; same contract as k_policy_move_tpa in cav_tpa.cu)
-// =============================================================================================================
-// Register cap expressed as resident 128-thread-equivalents per SM (5 -> <= 102 registers).  Measured at 16384 x 10:
-// float32 61 us with 5 vs 69 / 65 us with 4 / 6; with single-warp CTAs float64 68 us vs 74 us for the generic kernel.
-template <typename T>
-struct TpaNBoundsA {
-    static constexpr int MINB = 5;
-};
-
-#ifndef CAV_TPA_NA_WARPS
-#define CAV_TPA_NA_WARPS 1
-#endif
-// Same warp-aligned mapping as k_pairwise_obs_tpa_n (TpaNShape): a warp owns whole environments, neighbour states go
-// through its own shared-memory slice behind __syncwarp, no block barrier.  ORCA run times vary a lot between warps
-// (linearProgram1 / 3 calls are data dependent), so CTAs are single warps: a finished warp frees its registers at once
-// instead of idling behind its CTA's slowest warp (16384 x 10, float64: 62 us vs 65 us with 4-warp CTAs).
-template <typename T, int NT>
-__global__ void __launch_bounds__(32 * CAV_TPA_NA_WARPS, (TpaNBoundsA<T>::MINB * 4) / CAV_TPA_NA_WARPS)
-    k_policy_move_tpa_n(TpaBuffers b, KParams<T> p, const float *__restrict__ ext, int phases, T dt, int ntiles) {
-    using S = TpaNShape<T, NT>;
-    constexpr int NO = S::NO, EPW = S::EPW, LW = S::LW;
-    constexpr int WARPS = CAV_TPA_NA_WARPS;
-    constexpr size_t WB = S::PM_WARP_BYTES;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
-    unsigned char *sp = smem_raw + (size_t)warp * WB;
-    float4 *s_f4 = reinterpret_cast<float4 *>(sp);
-    sp += S::PM_F4;
-    float4 *s_lines = reinterpret_cast<float4 *>(sp);  // [NO][32], only touched by the linearProgram3 fallback
-    sp += S::PM_LINES;
-    float *s_frad = reinterpret_cast<float *>(sp);
-
-    const R4<T> *g_pv = reinterpret_cast<const R4<T> *>(b.pv);
-    R4<T> *g_goal = reinterpret_cast<R4<T> *>(b.goal);
-    const R4<T> *g_ht = reinterpret_cast<const R4<T> *>(b.ht);
-    const R4<T> *g_ego = reinterpret_cast<const R4<T> *>(b.ego);
-    const int el = lane / NT, a = lane - el * NT;
-    const int eb = el * NT;
-
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int ew0 = (tile * WARPS + warp) * EPW;
-        const int e = ew0 + el;
-        const bool have = lane < LW && e < p.E;
-        const size_t gi = (size_t)ew0 * NT + lane;
-        R4<T> pv{}, gl{}, ht{};
-        uint32_t f = 0, kind = 0;
-        int n = 0;
-        if (have) {
-            pv = ld4(g_pv + gi);
-            gl = ld4(g_goal + gi);
-            ht = ld4(g_ht + gi);
-            f = b.flags[gi];
-            kind = b.kinds[gi];
-            n = b.num_active ? b.num_active[e] : NT;
-            s_f4[lane] = make_float4((float)pv.x, (float)pv.y, (float)pv.z, (float)pv.w);  // RVOPolicy.py:57-74
-            s_frad[lane] = (float)(p.rvo_radius_scale * gl.z);
-        }
-        __syncwarp();
-
-        if (have && a < n) {
-            float2 act = make_float2(0.f, 0.f);
-            bool have_act = false;
-            if ((phases & 1) && !(f & CAV_FLAG_DONE)) {  // action selection (env.py:310-323)
-                const uint32_t pol = CAV_KIND_POLICY(kind);
-                T a0 = (T)0, a1 = (T)0;
-                if (pol == CAV_POLICY_RVO) {
-                    const T gx = gl.x - pv.x, gy = gl.y - pv.y;  // RVOPolicy.py:66
-                    const T nrm = M<T>::sqrt_(gx * gx + gy * gy);
-                    const T sc = gl.w / nrm;  // :67
-                    const float prefx = (float)(sc * gx), prefy = (float)(sc * gy);
-                    float nvx, nvy;
-                    orca_tpa_n<NO>(n, a, s_f4 + eb, s_frad + eb, prefx, prefy, (float)gl.w, p.rvo_inv_time_horizon_num,
-                                   p.rvo_time_step, p.rvo_collab, p.rvo_neighbor_dist, p.rvo_max_neighbors,
-                                   SmemLines{s_lines + lane, 32}, nvx, nvy);
-                    // Agent::update (Agent.cpp:470-475) in float, then RVOPolicy.py:96-111 in `real`
-                    const float4 me = s_f4[lane];
-                    const float npx = me.x + nvx * p.rvo_time_step, npy = me.y + nvy * p.rvo_time_step;
-                    const T dpx = (T)npx - pv.x, dpy = (T)npy - pv.y;
-                    const T ang1 = M<T>::atan2_(dpy, dpx);
-                    const T new_heading = pymod<T>(ang1 - (T)0, two_pi<T>());
-                    T dh = wrap<T>(new_heading - ht.x);
-                    T spd = p.rvo_inv_dt * M<T>::sqrt_(dpx * dpx + dpy * dpy);
-                    if (M<T>::abs_(dh) > p.rvo_max_delta_heading) {
-                        dh = sign<T>(dh) * p.rvo_max_delta_heading;
-                        spd = (T)0;
-                    }
-                    a0 = spd;
-                    a1 = dh;
-                } else if (pol == CAV_POLICY_NONCOOP) {  // NonCooperativePolicy.py:21
-                    a0 = gl.w;
-                    a1 = -ld4(g_ego + gi).y;
-                } else if (pol == CAV_POLICY_STATIC) {  // StaticPolicy.py:21-22: goal := pos
-                    gl.x = pv.x;
-                    gl.y = pv.y;
-                    st4(g_goal + gi, gl);
-                } else if (pol == CAV_POLICY_EXTERNAL) {  // ExternalPolicy.py:14-16
-                    const float2 x = ext ? reinterpret_cast<const float2 *>(ext)[gi] : make_float2(0.f, 0.f);
-                    a0 = (T)x.x;
-                    a1 = (T)x.y;
-                } else {  // CAV_POLICY_LEARNING, LearningPolicy.py:30-32
-                    const float2 x = ext ? reinterpret_cast<const float2 *>(ext)[gi] : make_float2(0.f, 0.f);
-                    a1 = p.max_heading_change * ((T)2. * (T)x.y - (T)1.);
-                    a0 = gl.w * (T)x.x;
-                }
-                act = make_float2((float)a0, (float)a1);  // float32 store, env.py:305-307
-                have_act = true;
-                reinterpret_cast<float2 *>(b.actions)[gi] = act;
-            }
-            if (phases & 2) tpa_move<T>(b, p, gi, pv, gl, ht, f, kind, act, have_act, dt);
-        }
-        __syncwarp();
-    }
-}
-
-template <typename T, int NT>
-static cudaError_t launch_pm_n(const cav_buffers_t &bufs, const KParams<T> &p, const float *ext, int phases, double dt,
-                               int sm_count, cudaStream_t st) {
-    using S = TpaNShape<T, NT>;
-    constexpr int WARPS = CAV_TPA_NA_WARPS;
-    const int epb = WARPS * S::EPW;
-    const int ntiles = (p.E + epb - 1) / epb;
-    const size_t smem = WARPS * S::PM_WARP_BYTES;
-    const int grid = ntiles < sm_count * 64 ? ntiles : sm_count * 64;
-    k_policy_move_tpa_n<T, NT><<<grid, 32 * WARPS, smem, st>>>(make_tpa(bufs), p, ext, phases, (T)dt, ntiles);
-    return cudaGetLastError();
-}
-
-template <typename T>
-cudaError_t run_policy_move_tpa_n(const cav_buffers_t &bufs, const KParams<T> &p, const float *ext, int phases, double dt,
-                                  int sm_count, cudaStream_t st) {
-    switch (p.N) {
-#define CAV_CASE(NN) \
-    case NN: return launch_pm_n<T, NN>(bufs, p, ext, phases, dt, sm_count, st);
-        CAV_CASE(2)
-        CAV_CASE(3)
-        CAV_CASE(4)
-        CAV_CASE(5)
-        CAV_CASE(6)
-        CAV_CASE(8)
-        CAV_CASE(10)
-        CAV_CASE(12)
-#undef CAV_CASE
-        default: return cudaErrorNotSupported;
-    }
-}
-
-template cudaError_t run_policy_move_tpa_n<float>(const cav_buffers_t &, const KParams<float> &, const float *, int,
-                                                  double, int, cudaStream_t);
-template cudaError_t run_policy_move_tpa_n<double>(const cav_buffers_t &, const KParams<double> &, const float *, int,
-                                                   double, int, cudaStream_t);
 
 // true when the plan is the default layout this kernel hard-codes
 static bool standard_layout(const ObsPlan &plan, const KParams<float> *, int N, int K, int obs_len, int sorting) {

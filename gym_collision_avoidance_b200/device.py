@@ -54,8 +54,11 @@ class DeviceState(object):
         a = np.ascontiguousarray(bits_u32, dtype=np.uint32).view(np.int32)
         self.static_map_bits = torch.from_numpy(a.copy()).to(self.device)
 
-    def load_host(self, hs):
+    def load_host(self, hs, cols=None):
+        """Host columns -> device (all of them, or only the named ones)."""
         for name, arr in hs.arrays.items():
+            if cols is not None and name not in cols:
+                continue
             a = arr
             if a.dtype == np.uint32:
                 a = a.view(np.int32)

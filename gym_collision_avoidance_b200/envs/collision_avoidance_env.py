@@ -35,12 +35,40 @@ class _Space(object):
         self.spaces[k] = v
 
 
+_HOST_HOOKS = ("find_next_action", "external_action_to_action", "step", "update_ego_frame")
+
+
 def _kernel_id(obj, what):
-    kid = getattr(type(obj), "kernel_id", None)
+    """Device kernel id of a built-in plugin object.  A user subclass that overrides a method the reference would call
+    on the step path (``find_next_action`` ...) cannot be honoured -- the device runs the built-in arithmetic -- so it
+    is rejected instead of being silently replaced (there is no CPU fallback)."""
+    cls = type(obj)
+    kid = getattr(cls, "kernel_id", None)
     if kid is None:
         raise abi.CavoidError("%s %s has no device implementation (kernel_id); this framework has no CPU fallback "
-                              "for the step path" % (what, type(obj).__name__))
+                              "for the step path" % (what, cls.__name__))
+    owner = next(k for k in cls.__mro__ if "kernel_id" in vars(k))
+    for k in cls.__mro__:
+        if k is owner:
+            break
+        over = [h for h in _HOST_HOOKS if h in vars(k)]
+        if over:
+            raise abi.CavoidError("%s %s overrides %s of the built-in %s: the step path runs on the device and cannot "
+                                  "call Python code (no CPU fallback)" % (what, cls.__name__, over, owner.__name__))
     return kid
+
+
+def _action_of(actions, i):
+    """actions[i] for a dict keyed by agent index or any sequence / array indexed by it (the reference indexes
+    ``actions[agent_index]``, env.py:316)."""
+    try:
+        if isinstance(actions, dict):
+            return actions[i]
+        if actions is None or i >= len(actions):
+            raise KeyError(i)
+        return actions[i]
+    except (KeyError, IndexError, TypeError):
+        raise KeyError("agent %d has an external policy but no action was supplied" % i)
 
 
 class CollisionAvoidanceEnv(object):
@@ -157,9 +185,16 @@ class CollisionAvoidanceEnv(object):
             self._cav.state.set_static_map(self.map.bits())
             self._cav.bind()
 
-    def _upload_agents(self):
+    # columns that hold Agent attributes; everything else (observation incl. the laserscan history rows, trajectory ring,
+    # laser_count, min_dist, done / game_over, episode bookkeeping, kd_order) is device-side history that an upload of
+    # agent STATES must leave alone
+    _AGENT_COLS = ("pv", "goal", "ht", "ego", "flags", "step_num", "kinds", "num_active", "aux0", "past_actions",
+                   "past_vel", "actions")
+
+    def _upload_agents(self, full=True):
         """Agent objects -> device columns (Agent attributes as they are: the reference's reset does not
-        re-initialise ``default_agents`` either, env.py:362-363)."""
+        re-initialise ``default_agents`` either, env.py:362-363).  ``full=False`` (Agent.set_state between steps, the
+        ExternalDynamics workflow) writes only the agent-state columns."""
         hs = HostState(self._c)
         n = len(self.agents)
         hs.num_active[0] = n
@@ -182,7 +217,7 @@ class CollisionAvoidanceEnv(object):
             hs.past_actions[0, i] = a.past_actions.reshape(-1)
             hs.past_vel[0, i] = a.past_global_velocities.reshape(-1)
             hs.actions[0, i] = a.past_actions[0]
-        self._cav.state.load_host(hs)
+        self._cav.state.load_host(hs, cols=None if full else self._AGENT_COLS)
 
     def _download(self):
         torch.cuda.synchronize()
@@ -287,12 +322,10 @@ class CollisionAvoidanceEnv(object):
         dirty = False
         for i, a in enumerate(self.agents):
             if a.policy.is_external and not a.is_done:
-                if actions is None or i not in actions:
-                    raise KeyError("agent %d has an external policy but no action was supplied" % i)
-                ext[0, i] = np.asarray(actions[i], dtype=np.float64)[:2]
+                ext[0, i] = np.asarray(_action_of(actions, i), dtype=np.float64).reshape(-1)[:2]
             dirty = dirty or getattr(a, "_state_dirty", False)
         if dirty:  # Agent.set_state was used (ExternalDynamics agents): push the new states first
-            self._upload_agents()
+            self._upload_agents(full=False)
             for a in self.agents:
                 a._state_dirty = False
         self._cav.step(torch.from_numpy(ext).to(self.device), float(dt))

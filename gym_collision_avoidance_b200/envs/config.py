@@ -119,6 +119,82 @@ class EvaluateConfig(Config):
         self.MAX_TIME_RATIO = 8.0
 
 
+class Example(EvaluateConfig):
+    """Reference ``config.py:202-210`` (the plotting switches are host-side only)."""
+
+    def __init__(self):
+        EvaluateConfig.__init__(self)
+        self.SAVE_EPISODE_PLOTS = True
+        self.PLOT_CIRCLES_ALONG_TRAJ = True
+        self.ANIMATE_EPISODES = True
+
+
+class Formations(EvaluateConfig):
+    """Reference ``config.py:212-224``."""
+
+    def __init__(self):
+        EvaluateConfig.__init__(self)
+        self.SAVE_EPISODE_PLOTS, self.SHOW_EPISODE_PLOTS, self.ANIMATE_EPISODES = True, False, True
+        self.NEAR_GOAL_THRESHOLD = 0.2
+        self.PLT_LIMITS, self.PLT_FIG_SIZE = [[-5, 6], [-2, 7]], (10, 10)
+        self.PLOT_CIRCLES_ALONG_TRAJ = False
+        self.NUM_AGENTS_TO_TEST, self.POLICIES_TO_TEST, self.NUM_TEST_CASES = [6], ["GA3C-CADRL-10"], 2
+        self.LETTERS = ["C", "A", "D", "R", "L"]
+
+
+class SmallTestSuite(EvaluateConfig):
+    """Reference ``config.py:226-233``."""
+
+    def __init__(self):
+        EvaluateConfig.__init__(self)
+        self.SAVE_EPISODE_PLOTS, self.SHOW_EPISODE_PLOTS, self.ANIMATE_EPISODES = True, False, False
+        self.PLOT_CIRCLES_ALONG_TRAJ = True
+        self.NUM_TEST_CASES = 4
+
+
+class LargeNumAgents(EvaluateConfig):
+    """Reference ``config.py:235-251``: observe 39 others (the reference still caps the environment at 19 agents)."""
+
+    def __init__(self):
+        self.MAX_NUM_OTHER_AGENTS_OBSERVED = 39
+        EvaluateConfig.__init__(self)
+        self.SAVE_EPISODE_PLOTS, self.SHOW_EPISODE_PLOTS, self.ANIMATE_EPISODES = True, False, False
+        self.PLOT_CIRCLES_ALONG_TRAJ = False
+        self.PLT_LIMITS = [[-20, 20], [-15, 15]]
+        self.NUM_TEST_CASES, self.NUM_AGENTS_TO_TEST = 10, [40]
+        self.RECORD_PICKLE_FILES = False
+        self.POLICIES_TO_TEST = ["GA3C-CADRL-10"]
+        self.FIXED_RADIUS_AND_VPREF = False
+        self.NEAR_GOAL_THRESHOLD = 0.2
+
+
+class FullTestSuite(EvaluateConfig):
+    """Reference ``config.py:253-287``."""
+
+    def __init__(self):
+        self.MAX_NUM_OTHER_AGENTS_OBSERVED = 19
+        EvaluateConfig.__init__(self)
+        self.SAVE_EPISODE_PLOTS, self.SHOW_EPISODE_PLOTS, self.ANIMATE_EPISODES = True, False, False
+        self.PLOT_CIRCLES_ALONG_TRAJ = True
+        self.NUM_TEST_CASES, self.NUM_AGENTS_TO_TEST = 4, [2, 3, 4]
+        self.RECORD_PICKLE_FILES = False
+        self.POLICIES_TO_TEST = ["CADRL", "RVO", "GA3C-CADRL-10"]
+        self.FIXED_RADIUS_AND_VPREF = False
+        self.NEAR_GOAL_THRESHOLD = 0.2
+
+
+class CollectRegressionDataset(EvaluateConfig):
+    """Reference ``config.py:290-304``."""
+
+    def __init__(self):
+        self.MAX_NUM_AGENTS_IN_ENVIRONMENT = 4
+        self.MAX_NUM_AGENTS_TO_SIM = 4
+        self.DATASET_NAME = ""
+        EvaluateConfig.__init__(self)
+        self.TEST_CASE_ARGS["policies"] = "CADRL"
+        self.AGENT_SORTING_METHOD = "closest_first"
+
+
 def make_config(num_agents, evaluate=True, use_static_map=False, states_in_obs=None, **overrides):
     """Convenience: a Config for exactly ``num_agents`` slots (what the oracle harness does with
     ``GYM_CONFIG_PATH``)."""

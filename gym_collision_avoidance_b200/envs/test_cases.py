@@ -104,10 +104,26 @@ def gen_circle_test_case(num_agents, radius):
     return tc
 
 
-def preset_testCases(num_agents, test_case_dir=None, num_test_cases=500):
-    """Loads a reference fixture file ``{N}_agents_500_cases.p`` (list of (N,6) arrays; reference
-    ``test_cases.py:593-625``).  The fixture files are the reference's data and are not bundled: pass the
-    directory that holds them (``.../gym_collision_avoidance/envs/test_cases``) or set ``CAV_TEST_CASE_DIR``."""
+_PRESETS = None
+
+
+def preset_testCases(num_agents, full_test_suite=False, test_case_dir=None, num_test_cases=500):
+    """Reference ``test_cases.py:593-897``.  ``full_test_suite=False``: the hard-coded small suite (rows
+    ``[px, py, gx, gy, pref_speed, radius]``) for 1, 2, 3, 4, 5, 6, 10 or 20 agents, shipped as data
+    (``envs/data/preset_cases.npz``, minted from the reference by ``tools/make_preset_cases.py``).
+    ``full_test_suite=True``: a reference fixture file ``{N}_agents_500_cases.p`` (list of (N,6) arrays, :601-624); those
+    files are the reference's data and are not bundled: pass the directory that holds them
+    (``.../gym_collision_avoidance/envs/test_cases``) or set ``CAV_TEST_CASE_DIR``."""
+    global _PRESETS
+    if not full_test_suite and test_case_dir is None:
+        if _PRESETS is None:
+            z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "preset_cases.npz"))
+            _PRESETS = {k: z[k] for k in z.files}
+        cases = []
+        while "n%d_c%d" % (num_agents, len(cases)) in _PRESETS:
+            cases.append(_PRESETS["n%d_c%d" % (num_agents, len(cases))].copy())
+        assert cases, "[preset_testCases] invalid num_agents %r" % (num_agents,)
+        return cases
     d = test_case_dir or os.environ.get("CAV_TEST_CASE_DIR")
     if d is None:
         raise FileNotFoundError("set CAV_TEST_CASE_DIR to the reference's envs/test_cases directory")
@@ -118,6 +134,44 @@ def preset_testCases(num_agents, test_case_dir=None, num_test_cases=500):
 def full_test_suite(num_agents, test_case_index, policies="learning", agents_dynamics="unicycle", agents_sensors=(),
                     prev_agents=None, test_case_dir=None):
     """Reference ``test_cases.py:332-355``."""
-    tc = preset_testCases(num_agents, test_case_dir)[test_case_index]
+    tc = preset_testCases(num_agents, full_test_suite=True, test_case_dir=test_case_dir)[test_case_index]
     return cadrl_test_case_to_agents(tc, policies=policies, agents_dynamics=agents_dynamics,
                                      agents_sensors=agents_sensors, prev_agents=prev_agents)
+
+
+def small_test_suite(num_agents, test_case_index, policies="learning", agents_dynamics="unicycle",
+                     agents_sensors=("other_agents_states",), vpref_constraint=False, radius_bnds=None):
+    """Reference ``test_cases.py:313-329``: case ``test_case_index`` of the hard-coded small suite."""
+    return cadrl_test_case_to_agents(preset_testCases(num_agents)[test_case_index], policies=policies,
+                                     agents_dynamics=agents_dynamics, agents_sensors=agents_sensors)
+
+
+def get_testcase_two_agents_laserscanners():
+    """Reference ``test_cases.py:178-209``: the head-on swap with laserscan-only learning agents (the reference names
+    ``PPOPolicy``, a learning policy that is not part of its tree; ``LearningPolicy`` is its device equivalent)."""
+    g = 3
+    return [Agent(-g, -g, g, g, 0.5, 1.0, 0.0, LearningPolicy, UnicycleDynamics, [LaserScanSensor], 0),
+            Agent(g, g, -g, -g, 0.5, 1.0, np.pi, LearningPolicy, UnicycleDynamics, [LaserScanSensor], 1)]
+
+
+# goal layouts of the letters C A D R L, six agents each (reference test_cases.py:425-492), in units of 2 m
+_LETTERS = {
+    "A": [[-1.5, 0.0], [1.5, 0.0], [0.75, 1.5], [-0.75, 1.5], [0.0, 1.5], [0.0, 3.0]],
+    "C": [[0.0, 0.0], [-0.5, 1.0], [-0.5, 2.0], [0.0, 3.0], [1.5, 0.0], [1.5, 3.0]],
+    "L": [[0.0, 0.0], [0.0, 1.0], [0.0, 2.0], [0.0, 3.0], [0.75, 0.0], [1.5, 0.0]],
+    "D": [[0.0, 0.0], [0.0, 1.5], [0.0, 3.0], [1.5, 1.5], [1.2, 2.5], [1.2, 0.5]],
+    "R": [[0.0, 0.0], [0.0, 1.5], [0.0, 3.0], [1.3, 2.8], [1.2, 1.7], [1.7, 0.0]],
+}
+
+
+def formation(agents, letter, num_agents=6):
+    """Reference ``test_cases.py:425-492``: send the agents (from where they stand) to a random assignment of the
+    letter's goal positions."""
+    goals = 2.0 * np.array(_LETTERS[letter])
+    agent_inds = np.arange(num_agents)
+    np.random.shuffle(agent_inds)
+    for agent in agents:
+        sx, sy = agent.pos_global_frame
+        gx, gy = goals[agent_inds[agent.id]]
+        agent.reset(px=sx, py=sy, gx=gx, gy=gy, heading=agent.heading_global_frame)
+    return agents

@@ -283,3 +283,79 @@ def gather_stats(stats, device=None):
     per_rank = torch.stack(out).cpu().numpy()
     tot = per_rank.sum(axis=0)
     return dict(zip(abi.STAT_NAMES, tot.tolist())), per_rank
+
+
+class VecEnv(object):
+    """Reference ``envs/vec_env.py:6-84`` interface: ``reset`` / ``step_async`` / ``step_wait`` / ``step`` / ``close``."""
+
+    def __init__(self, num_envs, observation_space, action_space):
+        self.num_envs, self.observation_space, self.action_space = num_envs, observation_space, action_space
+
+    def step(self, actions):
+        self.step_async(actions)
+        return self.step_wait()
+
+    @property
+    def unwrapped(self):
+        return self
+
+
+class DummyVecEnv(VecEnv):
+    """Drop-in for the reference's ``DummyVecEnv`` (``envs/vec_env.py:86-159``): ``DummyVecEnv([make_env] * E)`` steps
+    E environments and auto-resets the finished ones (``step_wait`` :120-128) -- here as ONE batched
+    ``VecCollisionAvoidanceEnv`` on the GPU instead of a Python loop over env objects.  ``env_fns[0]()`` is called once
+    to read the environment's Config (its wrappers, if any, only fix the observation view: the packed
+    ``(max_num_agents, obs_len)`` array of ``MultiagentDictToMultiagentArrayWrapper``, or agent 0's row for
+    ``FlattenDictWrapper``); episodes come from the Config's ``TEST_CASE_ARGS`` distribution (device scenario generator)
+    or an explicit ``scenario_bank``.  Returns host NumPy arrays like the reference: ``obs [E, ...]`` float32, ``rews``
+    (``[E]`` = agent 0's reward under ``TRAIN_SINGLE_AGENT``, else ``[E, N]``), ``dones [E]`` bool, ``infos`` list of
+    dicts with ``which_agents_done``."""
+
+    def __init__(self, env_fns, device="cuda:0", scenario_bank=None, policies=None, precision="f64", seed=0):
+        from .wrappers import FlattenDictWrapper
+        proto = env_fns[0]()
+        base = getattr(proto, "unwrapped", proto)
+        C = getattr(base, "Config", None)
+        if C is None:
+            from . import Config as C
+        self.single_agent_view = isinstance(proto, FlattenDictWrapper) or bool(C.TRAIN_SINGLE_AGENT)
+        VecEnv.__init__(self, len(env_fns), getattr(proto, "observation_space", None), getattr(proto, "action_space", None))
+        N = C.MAX_NUM_AGENTS_IN_ENVIRONMENT
+        if policies is None:
+            pol = C.TEST_CASE_ARGS.get("policies", "RVO")
+            policies = pol if isinstance(pol, str) else (["learning"] + ["RVO"] * (N - 1))
+        if hasattr(base, "close"):
+            base.close()
+        self.venv = VecCollisionAvoidanceEnv(self.num_envs, C, N, device=device, precision=precision,
+                                             scenario_bank=scenario_bank, policies=policies, seed=seed,
+                                             scenario_source="host" if scenario_bank is not None else "device")
+        self.Config = C
+        self.actions = None
+
+    def _view(self, obs):
+        return obs[:, 0] if self.single_agent_view else obs
+
+    def reset(self):
+        self.venv.reset()
+        torch.cuda.current_stream(self.venv.device).synchronize()
+        return self._view(self.venv.state.obs.float().cpu().numpy())
+
+    def step_async(self, actions):
+        self.actions = actions
+
+    def step_wait(self):
+        a = None
+        if self.actions is not None:
+            a = np.asarray(self.actions, dtype=np.float32)
+            if a.ndim == 2:  # one action per environment = agent 0's (single-agent training)
+                full = np.zeros((self.num_envs, self.venv.num_agents, 2), np.float32)
+                full[:, 0] = a
+                a = full
+        obs, rew, over, dones = self.venv.step_host(a)
+        rew = rew.numpy()
+        infos = [{"which_agents_done": dict(enumerate(d.astype(bool)))} for d in dones.numpy()]
+        return (np.copy(self._view(obs.numpy())), np.copy(rew[:, 0] if self.Config.TRAIN_SINGLE_AGENT else rew),
+                over.numpy().astype(bool), infos)
+
+    def close(self):
+        self.venv.close()

@@ -105,3 +105,72 @@ def test_external_actions_and_set_state():
         env.close()
     finally:
         envs_pkg.set_config(old)
+
+
+def test_set_state_mid_episode_keeps_history_and_laser_rows():
+    """Agent.set_state between steps (the reference's ExternalDynamics workflow, agent.py:155-190) must only move the
+    agent: the trajectory rows written so far, the laserscan's 3-deep measurement history (and its 'first measurement'
+    counter), and the other agents' state stay as they were; list / ndarray actions index like the reference's."""
+    old = envs_pkg.Config
+    cfg = envs_pkg.set_config(cfgmod.make_config(
+        3, evaluate=True, use_static_map=True,
+        states_in_obs=["is_learning", "num_other_agents", "dist_to_goal", "heading_ego_frame", "pref_speed", "radius",
+                       "other_agents_states", "laserscan"]))
+    try:
+        from gym_collision_avoidance_b200.envs import test_cases as tc
+        from gym_collision_avoidance_b200.envs.agent import Agent
+        from gym_collision_avoidance_b200.envs.collision_avoidance_env import CollisionAvoidanceEnv
+        sens = [tc.sensor_dict["other_agents_states"], tc.sensor_dict["laserscan"]]
+        agents = [Agent(-2.0, 0.0, 3.0, 0.0, 0.4, 1.0, np.float64(0.0), tc.policy_dict["external"],
+                        tc.dynamics_dict["external"], sens, 0),
+                  Agent(2.0, 0.5, -3.0, 0.5, 0.4, 1.0, np.float64(np.pi), tc.policy_dict["noncoop"],
+                        tc.dynamics_dict["unicycle"], sens, 1),
+                  Agent(0.0, -2.0, 0.0, 3.0, 0.3, 0.8, np.float64(np.pi / 2), tc.policy_dict["RVO"],
+                        tc.dynamics_dict["unicycle"], sens, 2)]
+        env = CollisionAvoidanceEnv()
+        env.set_agents(agents)
+        env.reset()
+        for k in range(3):
+            env.step([np.array([0.0, 0.0]), None, None])  # sequence-typed actions
+        hist1 = env.agents[1].global_state_history[:3].copy()
+        laser1 = env.agents[1].sensor_data["laserscan"].copy()
+        assert env.agents[1].step_num == 3 and np.abs(hist1[:, 1:3]).sum() > 0
+        env.agents[0].set_state(-1.5, 0.2, 1.0, 0.0, 0.0)
+        obs, rew, over, _, info = env.step(np.zeros((3, 2)))  # ndarray actions
+        a1 = env.agents[1]
+        np.testing.assert_array_equal(a1.global_state_history[:3], hist1)  # earlier rows intact
+        assert a1.step_num == 4 and np.abs(a1.global_state_history[3, 1:3]).sum() > 0
+        # the sensor's history shifted down by one row (LaserScanSensor.py:84-101): it was NOT re-initialised
+        np.testing.assert_array_equal(a1.sensor_data["laserscan"][1:], laser1[:-1])
+        np.testing.assert_allclose(env.agents[0].pos_global_frame, [-1.5, 0.2])
+        env.close()
+    finally:
+        envs_pkg.set_config(old)
+
+
+def test_user_subclass_overriding_a_device_policy_is_rejected():
+    old = envs_pkg.Config
+    envs_pkg.set_config(cfgmod.make_config(2, evaluate=True))
+    try:
+        from gym_collision_avoidance_b200.envs import test_cases as tc
+        from gym_collision_avoidance_b200.envs.agent import Agent
+        from gym_collision_avoidance_b200.envs.collision_avoidance_env import CollisionAvoidanceEnv
+
+        class MyRVO(tc.policy_dict["RVO"]):
+            def find_next_action(self, obs, agents, i):
+                return np.array([0.1, 0.0])
+
+        class RenamedRVO(tc.policy_dict["RVO"]):  # no behaviour change: accepted
+            pass
+
+        env = CollisionAvoidanceEnv()
+        mk = lambda pol: [Agent(0, 0, 3, 0, 0.3, 1.0, np.float64(0.0), pol, tc.dynamics_dict["unicycle"],  # noqa: E731
+                                [tc.sensor_dict["other_agents_states"]], 0)]
+        env.set_agents(mk(MyRVO))
+        with pytest.raises(abi.CavoidError, match="overrides"):
+            env.reset()
+        env.set_agents(mk(RenamedRVO))
+        env.reset()
+        env.close()
+    finally:
+        envs_pkg.set_config(old)

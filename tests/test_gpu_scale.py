@@ -291,9 +291,9 @@ def test_max_turn_rate_and_external_dynamics_vs_oracle(mapping, monkeypatch):
 @pytest.mark.parametrize("prec", ["f64", "f32"])
 @pytest.mark.parametrize("N", [2, 5, 10, 12])
 def test_compile_time_n_kernels_forced_on_and_off(N, prec, monkeypatch):
-    """The compile-time-N kernels (cav_tpa_n.cu) and the generic thread-per-agent kernels run the same arithmetic:
-    one dense bank through all four on/off combinations must give bit-identical states, and (float64) the oracle's
-    to 1e-9.  float32 is only compared across kernels here: with a dense bank a heading change can land within one
+    """The compile-time-N pairwise+obs kernel (cav_tpa_n.cu) and the generic thread-per-agent one, and the thread-per-agent
+    policy kernel (k_policy_move_v2) and the sub-warp-group one, run the same arithmetic: one dense bank through all four
+    combinations must give bit-identical states, and (float64) the oracle's to 1e-9.  float32 is only compared across kernels here: with a dense bank a heading change can land within one
     ulp of the reference's turn-in-place threshold (RVOPolicy.py:101-104), where CUDA's and glibc's atan2f differ."""
     from gpu_common import GpuRunner
     E = 64
@@ -302,7 +302,7 @@ def test_compile_time_n_kernels_forced_on_and_off(N, prec, monkeypatch):
     first = None
     for pol_n in ("0", "1"):
         for obs_n in ("0", "1"):
-            monkeypatch.setenv("CAV_TPA_N_POLICY", pol_n)
+            monkeypatch.setenv("CAV_POLICY_GROUP", "1" if pol_n == "0" else "0")
             monkeypatch.setenv("CAV_TPA_N", obs_n)
             hs = HostState(c)
             orc = Oracle(c)

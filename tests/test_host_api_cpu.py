@@ -127,3 +127,89 @@ def test_image_map_loading_matches_the_reference_recipe(tmp_path):
     r, c = np.nonzero(want)
     assert all((bits[rr, cc >> 5] >> (cc & 31)) & 1 for rr, cc in zip(r[:200], c[:200])) and \
         int(sum(bin(int(w)).count("1") for w in bits.ravel())) == int(want.sum())
+
+
+def test_reference_config_subclasses():
+    """The reference's own Config subclasses (config.py:193-304) exist with the fields the step path reads."""
+    for name, n_agents, k_obs in (("EvaluateConfig", 19, 18), ("Example", 19, 18), ("Formations", 19, 18),
+                                   ("SmallTestSuite", 19, 18), ("LargeNumAgents", 19, 39), ("FullTestSuite", 19, 19),
+                                   ("CollectRegressionDataset", 4, 3)):
+        c = getattr(cfgmod, name)()
+        assert c.EVALUATE_MODE and not c.TRAIN_MODE and c.DT == 0.1 and c.MAX_TIME_RATIO == 8.0
+        assert (c.MAX_NUM_AGENTS_IN_ENVIRONMENT, c.MAX_NUM_OTHER_AGENTS_OBSERVED) == (n_agents, k_obs)
+        assert c.STATE_INFO_DICT["other_agents_states"]["size"] == (k_obs, 7)
+        cc = cfgmod.to_cav_config(c, 4)
+        assert cc.obs_len == 6 + 7 * k_obs and cc.game_over_mode == abi.CAV_GAME_OVER_ALL_DONE
+    assert cfgmod.Formations().LETTERS == ["C", "A", "D", "R", "L"]
+    assert cfgmod.CollectRegressionDataset().TEST_CASE_ARGS["policies"] == "CADRL"
+
+
+def test_preset_suites_formation_and_laserscanner_case(eval_config):
+    from gym_collision_avoidance_b200.envs import test_cases as tc
+    counts = {n: len(tc.preset_testCases(n)) for n in (1, 2, 3, 4, 5, 6, 10, 20)}
+    assert counts == {1: 2, 2: 8, 3: 9, 4: 9, 5: 2, 6: 4, 10: 1, 20: 1}
+    np.testing.assert_allclose(tc.preset_testCases(2)[0], [[-3, 0, 3, 0, 1, 0.3], [3, 0, -3, 0, 1, 0.3]])
+    np.testing.assert_allclose(tc.preset_testCases(20)[0], tc.gen_circle_test_case(20, 10))  # test_cases.py:884-889
+    with pytest.raises(AssertionError):
+        tc.preset_testCases(7)
+    # (the reference serves ONE list for 3 and 4 agents -- four 3-agent cases, then five 4-agent ones, test_cases.py:716)
+    assert [c.shape[0] for c in tc.preset_testCases(3)] == [3] * 4 + [4] * 5
+    agents = tc.small_test_suite(3, 2, policies="RVO")
+    assert len(agents) == 3 and all(a.policy.str == "RVO" for a in agents)
+    np.testing.assert_allclose([a.pos_global_frame for a in agents], tc.preset_testCases(3)[2][:, 0:2])
+    a, b = tc.get_testcase_two_agents_laserscanners()
+    assert [s.name for s in a.sensors] == ["laserscan"] and a.policy.is_still_learning and b.heading_global_frame == np.pi
+    six = tc.cadrl_test_case_to_agents(tc.preset_testCases(6)[0], policies="RVO")
+    np.random.seed(3)
+    tc.formation(six, "R")
+    goals = sorted(map(tuple, np.round([ag.goal_global_frame for ag in six], 6).tolist()))
+    assert goals == sorted(map(tuple, (2.0 * np.array(tc._LETTERS["R"])).tolist()))
+    assert all(ag.step_num == 0 and not ag.is_done for ag in six)
+
+
+def test_reference_wrapper_classes_over_a_dict_observation_env(eval_config):
+    """MultiagentDictToMultiagentArrayWrapper / MultiagentFlattenDictWrapper / FlattenDictWrapper (wrappers.py:11-173)
+    on an object with the environment's surface (observation_space {agent: {state: box}}, reset / step)."""
+    from gym_collision_avoidance_b200.envs import wrappers as W
+    from gym_collision_avoidance_b200.envs.collision_avoidance_env import _Space
+    cfg = eval_config
+    N = cfg.MAX_NUM_AGENTS_IN_ENVIRONMENT
+    rng = np.random.RandomState(0)
+
+    class FakeEnv(object):
+        def __init__(self):
+            self.observation_space = _Space()
+            for a in range(N):
+                self.observation_space.spaces[a] = _Space()
+                for s in cfg.STATES_IN_OBS:
+                    info = cfg.STATE_INFO_DICT[s]
+                    self.observation_space.spaces[a][s] = _Space(np.zeros(info["size"]), np.ones(info["size"]))
+            self.action_space, self.extra = "A", 7
+
+        def _obs(self):
+            return {a: {s: rng.rand(*np.atleast_1d(cfg.STATE_INFO_DICT[s]["size"])) for s in cfg.STATES_IN_OBS}
+                    for a in range(N)}
+
+        def reset(self):
+            self.last = self._obs()
+            return self.last, {}
+
+        def step(self, actions):
+            self.last = self._obs()
+            return self.last, np.zeros(N), False, False, {"k": 1}
+
+    env = W.MultiagentDictToMultiagentArrayWrapper(FakeEnv(), dict_keys=cfg.STATES_IN_OBS, max_num_agents=N)
+    assert env.extra == 7 and env.observation_space.shape == (N, 6 + 7 * (N - 1))
+    obs, info = env.reset()
+    np.testing.assert_array_equal(obs, W.dict_to_packed(cfg, env.unwrapped.last))
+    obs, rew, over, trunc, info = env.step({})
+    assert obs.shape == (N, 69) and info == {"k": 1} and over is False
+    np.testing.assert_array_equal(W.packed_to_dict(cfg, obs)[3]["other_agents_states"],
+                                  env.unwrapped.last[3]["other_agents_states"])
+    flat = W.MultiagentFlattenDictWrapper(FakeEnv(), cfg.STATES_IN_OBS, N)
+    o, _ = flat.reset()
+    assert o.shape == (N * 69,) and flat.singleAgentObservationInds(2) == [2 * 69, 3 * 69]
+    np.testing.assert_array_equal(flat.observationArrayToDict(o)[1]["dist_to_goal"], flat.unwrapped.last[1]["dist_to_goal"])
+    one = W.FlattenDictWrapper(FakeEnv(), cfg.STATES_IN_OBS)
+    o, _ = one.reset()
+    assert o.shape == (69,) and one.keyToArrayInds("radius") == [[5, 6]]
