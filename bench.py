@@ -12,6 +12,14 @@ environments are reset from the device-resident scenario bank and observed (auto
 --envs 4096 for configs[1] verbatim).  --gpus N (under torchrun) shards environments: every rank steps its own
 E environments (weak scaling), no data-path collective; one NCCL all-gather of the episode statistics at the end.
 
+State is float64 (the reference's NumPy arithmetic); the observation / reward columns are float32 by default -- the
+dtype the reference declares for its observation space (config.py:93-170), written directly by the kernels
+(cfg.obs_f32; --obs-f64 keeps float64 columns).
+
+Episode phase: the timed region starts W (+ --preroll) steps after a reset of every environment, i.e. with (nearly) all
+agents still live -- the most expensive phase of an episode (every live RVO agent runs an ORCA solve); `live_agent_steps`
+/ `live_fraction` report how many agent slots were live.  --preroll 150 measures the stationary mix instead.
+
 Timing: W untimed warm-up steps; K timed steps, each bracketed by CUDA events on the launching stream, with a
 256 MiB memset + a 256 MiB read pass between steps to flush the 126 MB L2 (outside the event brackets); value =
 agent-steps / sum of event times, max over ranks; a barrier + synchronize brackets the whole timed loop.
@@ -19,7 +27,8 @@ agent-steps / sum of event times, max over ranks; a barrier + synchronize bracke
 observations / rewards / done flags out, every step (wall clock, includes the copies).
 `roofline` times the dominant fused pairwise+obs kernel alone (CUDA events around its launches, L2 flushed).
 `cpu_baseline` / `--impl reference`: the C restatement of the reference's step (oracle/, kind "port"; the Python
-reference cannot travel to the GPU box) on all host threads, on a bounded sample of the same workload.
+reference cannot travel to the GPU box; its own rate measured in the build container is quoted from
+profiles/python_reference_baseline.json) on all host threads, on a bounded sample of the same workload.
 """
 import argparse
 import json
@@ -50,6 +59,10 @@ def parse():
     ap.add_argument("--cpu-steps", type=int, default=0, help="cpu_baseline sample steps (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--obs-f64", action="store_true", help="float64 observation / reward columns (default float32)")
+    ap.add_argument("--preroll", type=int, default=0, help="untimed steps before the warm-up (episode phase)")
+    ap.add_argument("--no-lookahead", action="store_true", help="e2e: wait for every step's download before the next launch")
+    ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to its GPU's NUMA node")
     return ap.parse_args()
 
 
@@ -66,6 +79,49 @@ def workload_name(a):
     return "%d envs/GPU x %d agents, %sPolicy, UnicycleDynamics, random start/goal bank%s, sorted-neighbour obs, " \
            "auto-reset, DT=0.1" % (a.envs, a.agents, "RVO" if a.policy == "RVO" else "NonCooperative",
                                    " + LaserScanSensor 512x3" if a.laser else "")
+
+
+def obs_f32(a):
+    return a.precision == "f64" and not a.obs_f64
+
+
+def config_dict(a, world):
+    """The `config` object of the JSON line -- identical for both arms (ours / --impl reference)."""
+    return {"workload": workload_name(a), "envs_per_gpu": a.envs, "agents": a.agents, "policy": a.policy,
+            "state_precision": a.precision, "obs_precision": "f32" if (a.precision == "f32" or obs_f32(a)) else "f64",
+            "orca_precision": "f32", "history_rows": a.history,
+            "episode_phase": "timed steps start %d steps after a full reset (all agents live at reset)" % (
+                max(a.warmup, 3) + a.preroll),
+            "parallelism": "envs sharded x%d, no per-step collective" % world,
+            "l2": "flushed between timed steps (256 MiB memset + 256 MiB read pass, outside the CUDA-event brackets)",
+            "cuda_graph": not a.no_graph}
+
+
+def bind_numa(local_rank):
+    """Bind this process (and so its pinned allocations, first touch) to the CPUs of the GPU's NUMA node: on the 8-GPU
+    boxes GPUs 0-3 hang off socket 0 and 4-7 off socket 1, and eight ranks downloading 46 MB per step across the
+    socket interconnect is what held the round-1 8-GPU e2e at 0.79 efficiency.  Returns a description (or None)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.split(":", 1)
+        node = int(open("/sys/bus/pci/devices/%s:%s/numa_node" % (dom[-4:].lower(), rest.lower())).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return "numa node %d (%d cpus)" % (node, len(cpus))
+    except Exception:
+        return None
 
 
 def scenario_bank(a, seed=1234):
@@ -87,7 +143,7 @@ def cpu_baseline_run(a, steps, envs=None, threads=0, budget_s=15.0):
         E = max(16, 2 * cores)
     cfg = workload_config(a)
     rows = scenario_bank(a)
-    c = to_cav_config(cfg, E, a.agents, precision=a.precision, history_len=a.history)
+    c = to_cav_config(cfg, E, a.agents, precision=a.precision, history_len=a.history)  # float64 columns: no rounding pass
     hs = HostState(c)
     bank = HostBank(rows, kinds=kinds_array(rows.shape[0], a.agents, a.policy))
     orc = cav_oracle.Oracle(c, threads=cores)
@@ -136,7 +192,7 @@ def cpu_baseline_run(a, steps, envs=None, threads=0, budget_s=15.0):
 def auto_cpu_steps(a):
     if a.cpu_steps:
         return a.cpu_steps
-    return 20 if a.laser else 2000
+    return 20 if a.laser else 2000  # upper bound; cpu_baseline_run caps the sample at ~15 s of wall time
 
 
 class ClockSampler(object):
@@ -247,22 +303,36 @@ def measured_peak():
 
 
 def measured_traffic(a):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture, or None."""
+    """(DRAM bytes per launch of the dominant kernel, source) from the committed `ncu --set full` capture of this
+    kernel build (profiles/roofline_traffic.json names the capture), or (None, None): ncu cannot run inside the bench."""
     try:
         d = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
-        return d.get("%s_%dx%d_%s" % (a.precision, a.envs, a.agents, a.policy))
+        key = "%s%s_%dx%d_%s" % (a.precision, "_obsf32" if obs_f32(a) else "", a.envs, a.agents, a.policy)
+        return d.get(key), d.get("source")
     except Exception:
-        return None
+        return None, None
 
 
 def pairwise_obs_bytes(c):
-    """Algorithmic bytes per agent-step of the fused pairwise+obs kernel (state read
-    3 x real4 + flags, write obs + reward + done + flags), with `real` = 4 or 8 bytes."""
+    """Algorithmic bytes per agent-step of the fused pairwise+obs kernel (state read 3 x real4 + flags,
+    write obs + reward + done + flags) with the ACTUAL element sizes: state `real` = 4 or 8 bytes, observation and
+    reward 4 bytes when the columns are float32 (precision f32, or obs_f32 next to float64 state)."""
     rb = 8 if c.precision == 1 else 4
+    ob = 4 if (c.precision != 1 or c.obs_f32) else 8
     K = c.max_num_other_agents_observed
     read = 3 * 4 * rb + 4
-    write = rb * (6 + 7 * K) + rb + 1 + 4
+    write = ob * (6 + 7 * K) + ob + 1 + 4
     return read + write
+
+
+def python_reference_rate(a):
+    """agent-steps/s of the UNMODIFIED Python reference measured in the build container (it cannot travel to the GPU box;
+    tools/measure_python_reference.py writes profiles/python_reference_baseline.json), or None."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "python_reference_baseline.json")))
+        return d.get("%dagents_%s" % (a.agents, a.policy))
+    except Exception:
+        return None
 
 
 def run_ours(a):
@@ -272,6 +342,7 @@ def run_ours(a):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    numa = None if a.no_numa else bind_numa(local)  # before any pinned allocation
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -280,7 +351,8 @@ def run_ours(a):
     cfg = workload_config(a)
     env = VecCollisionAvoidanceEnv(a.envs, cfg, a.agents, device=dev, precision=a.precision,
                                    scenario_bank=scenario_bank(a, seed=1234 + rank), policies=a.policy,
-                                   history_len=a.history, use_cuda_graph=not a.no_graph)
+                                   history_len=a.history, use_cuda_graph=not a.no_graph, obs_f32=obs_f32(a),
+                                   host_lookahead=False if a.no_lookahead else None)
     env.reset()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     flush_rd = torch.empty(64 << 20, dtype=torch.float32, device=dev)  # 256 MiB
@@ -290,10 +362,11 @@ def run_ours(a):
         kernels start from an L2 that holds neither their data nor a backlog of dirty flush lines."""
         flush.zero_()
         flush_rd.sum()
-    for _ in range(max(a.warmup, 3)):
+    for _ in range(a.preroll + max(a.warmup, 3)):
         env.step()
     torch.cuda.synchronize()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    live = torch.zeros((), dtype=torch.int64, device=dev)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -302,6 +375,7 @@ def run_ours(a):
     torch.cuda.synchronize()
     t_wall0 = time.perf_counter()
     for s in range(a.steps):
+        live += (env.state.flags.view(-1) & 0x20).eq(0).sum()  # agent slots that are live going into this step
         l2_flush()  # outside the timed bracket
         ev[s][0].record()
         env.step()
@@ -311,11 +385,15 @@ def run_ours(a):
         dist.barrier()
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop() if rank == 0 else None
-    dev_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
-    tmax = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    dev_ms_rank = sum(e0.elapsed_time(e1) for e0, e1 in ev)
+    per_rank_ms = torch.zeros(world, dtype=torch.float64, device=dev)
+    per_rank_ms[rank] = dev_ms_rank
+    live_t = live.to(torch.float64).reshape(1)
     if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    dev_ms = float(tmax.item())
+        dist.all_reduce(per_rank_ms, op=dist.ReduceOp.SUM)
+        dist.all_reduce(live_t, op=dist.ReduceOp.SUM)
+    per_rank_ms = [float(x) for x in per_rank_ms.tolist()]
+    dev_ms = max(per_rank_ms)
     launches = env.launches_per_step * a.steps
 
     # ---- roofline of the dominant kernel (fused pairwise+obs), timed alone ----
@@ -342,6 +420,7 @@ def run_ours(a):
 
     # ---- e2e through the public host-buffer API ----
     h_act = np.zeros((a.envs, a.agents, 2), np.float32)
+    env.reset()
     for _ in range(3):
         env.step_host(h_act)
     if world > 1:
@@ -361,36 +440,41 @@ def run_ours(a):
     out = None
     if rank == 0:
         value = world * a.envs * a.agents * a.steps / (dev_ms * 1e-3)
+        traffic, traffic_src = measured_traffic(a)
+        live_steps = float(live_t.item())
         out = {
             "metric": "agent-steps/sec", "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": a.steps,
-            "warmup": max(a.warmup, 3), "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": a.warmup, "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": a.precision, "data": "synthetic",
-            "config": {"workload": workload_name(a), "envs_per_gpu": a.envs, "agents": a.agents, "policy": a.policy,
-                       "state_precision": a.precision, "orca_precision": "f32", "history_rows": a.history,
-                       "parallelism": "envs sharded x%d, no per-step collective" % world,
-                       "l2": "flushed between timed steps (256 MiB memset + 256 MiB read pass, outside the CUDA-event brackets)",
-                       "cuda_graph": not a.no_graph},
+            "config": config_dict(a, world),
+            "live_agent_steps": live_steps, "live_fraction": live_steps / (world * a.envs * a.agents * a.steps),
+            "live_agent_steps_per_s": live_steps / (dev_ms * 1e-3),
+            "per_rank_ms_per_step": [x / a.steps for x in per_rank_ms],
             "wall_ms_per_step_incl_flush": t_wall / a.steps * 1e3,
-            "clocks": clocks,
+            "clocks": clocks, "numa_binding": numa,
             "e2e": {"value": e2e_val, "unit": "agent-steps/s", "h2d_bytes_per_step": world * env.h2d_bytes_per_step,
                     "d2h_bytes_per_step": world * env.d2h_bytes_per_step, "bytes_scope": "whole job (all ranks)",
-                    "steps": e2e_steps},
+                    "steps": e2e_steps, "ms_per_step": float(e2e_t.item()) / e2e_steps * 1e3,
+                    "lookahead": bool(env.host_lookahead),
+                    "note": "every call uploads the [E,N,2] action array from pinned memory and downloads the float32 obs / "
+                            "reward / done arrays; with lookahead (no external-policy agent reads the actions) the next "
+                            "step's kernels run under this step's download"},
             "gpu_launches": world * launches,
             "roofline": {"kernel": "k_pairwise_obs (fused pairwise collision+reward+sorted-neighbour obs+done)",
                          "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": measured_traffic(a), "peak_source": peak_src, "bytes_per_agent_step": bpa,
-                         "kernel_ms": k_ms, "policy_move_kernel_ms": pm_ms},
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "bytes_per_agent_step": bpa, "kernel_ms": k_ms, "policy_move_kernel_ms": pm_ms},
             "episode_stats": totals,
         }
-        if not a.no_cpu_baseline:
-            v, cores, sample, _ = cpu_baseline_run(a, auto_cpu_steps(a))
-            out["cpu_baseline"] = {"value": v, "unit": "agent-steps/s", "cores": cores, "kind": "port",
-                                   "sample": sample}
     env.close()
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
+        dist.destroy_process_group()  # the CPU leg below runs with no rank spinning in a collective
     if out is not None:
+        if not a.no_cpu_baseline:
+            v, cores, sample, _ = cpu_baseline_run(a, auto_cpu_steps(a))
+            out["cpu_baseline"] = {"value": v, "unit": "agent-steps/s", "cores": cores, "kind": "port",
+                                   "sample": sample, "python_reference": python_reference_rate(a)}
         print(json.dumps(out))
 
 
@@ -398,19 +482,18 @@ def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(3, a.steps)
-    # warm-up is inside cpu_baseline_run (3 steps); each "step" is a bounded sample of the workload
-    # (max(1024, 256 x cores) envs instead of --envs), the run is capped at ~30 s of wall time
-    v, cores, sample, sec_per_step = cpu_baseline_run(a, steps, budget_s=30.0)
-    steps = int(round(float(sample.split(" x ")[2].split(" ")[0])))
+    # K timed "steps", each a bounded sample of the workload (max(1024, 256 x cores) envs instead of --envs); the
+    # warm-up is inside cpu_baseline_run (3 steps + the team-size probe); capped at ~30 s of wall time
+    v, cores, sample, sec_per_step = cpu_baseline_run(a, max(3, a.steps), budget_s=30.0)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     out = {
         "impl": "reference", "metric": "agent-steps/sec", "value": v, "unit": "agent-steps/s",
-        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": 3,
+        "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": a.precision, "data": "synthetic",
-        "config": {"workload": workload_name(a), "agents": a.agents, "policy": a.policy,
-                   "state_precision": a.precision},
-        "cpu_baseline": {"value": v, "unit": "agent-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": config_dict(a, world),
+        "cpu_baseline": {"value": v, "unit": "agent-steps/s", "cores": cores, "kind": "port", "sample": sample,
+                         "python_reference": python_reference_rate(a)},
         "e2e": {"value": v, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

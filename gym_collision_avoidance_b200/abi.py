@@ -80,7 +80,7 @@ class CavConfig(ctypes.Structure):
         ("laser_min_range", _d), ("laser_max_range", _d), ("laser_range_resolution", _d),
         ("map_x_width", _d), ("map_y_width", _d), ("map_grid_cell_size", _d),
         ("obs_len", _i), ("obs_offset", _i * CAV_OBS_NUM_STATES),
-        ("store_history", _i), ("history_len", _i), ("track_aux", _i), ("reserved0", _i),
+        ("store_history", _i), ("history_len", _i), ("track_aux", _i), ("obs_f32", _i),
     ]
 
 

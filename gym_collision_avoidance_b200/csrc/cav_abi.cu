@@ -330,14 +330,19 @@ static WallMap wall_map(cav_handle_t h) {
     return wm;
 }
 
+// (state precision, observation precision) of a handle: float/float, double/double, or double/float (cfg.obs_f32)
+#define CAV_BY_PRECISION(h, CALL_F, CALL_D, CALL_DF) \
+    ((h)->cfg.precision != CAV_F64 ? (CALL_F) : ((h)->cfg.obs_f32 ? (CALL_DF) : (CALL_D)))
+
 static int do_pairwise_obs(cav_handle_t h, const uint8_t *mask, int obs_only, cudaStream_t st) {
     const WallMap wm = wall_map(h);
     // 'time_to_impact' ordering (three-level real key) lives in the sub-warp-group kernel only, for every N
     if (h->use_tpa && h->cfg.agent_sorting_method != CAV_SORT_TIME_TO_IMPACT) {
         if (h->use_tpa_n) {  // compile-time-N specialisation when the configuration allows it
-            const cudaError_t ce = (h->cfg.precision == CAV_F64)
-                                       ? run_pairwise_obs_tpa_n<double>(h->bufs, h->pd, h->plan, wm, mask, obs_only, h->sm_count, st)
-                                       : run_pairwise_obs_tpa_n<float>(h->bufs, h->pf, h->plan, wm, mask, obs_only, h->sm_count, st);
+            const cudaError_t ce = CAV_BY_PRECISION(
+                h, (run_pairwise_obs_tpa_n<float, float>(h->bufs, h->pf, h->plan, wm, mask, obs_only, h->sm_count, st)),
+                (run_pairwise_obs_tpa_n<double, double>(h->bufs, h->pd, h->plan, wm, mask, obs_only, h->sm_count, st)),
+                (run_pairwise_obs_tpa_n<double, float>(h->bufs, h->pd, h->plan, wm, mask, obs_only, h->sm_count, st)));
             if (ce == cudaSuccess) {
                 h->launches++;
                 return CAV_OK;
@@ -345,25 +350,24 @@ static int do_pairwise_obs(cav_handle_t h, const uint8_t *mask, int obs_only, cu
             if (ce != cudaErrorNotSupported) return fail(h, CAV_ERR_CUDA, "pairwise_obs_tpa_n: %s", cudaGetErrorString(ce));
             h->use_tpa_n = false;  // not applicable to this handle: stop asking
         }
-        if (h->cfg.precision == CAV_F64)
-            CAV_CUDA(h, "pairwise_obs_tpa",
-                     run_pairwise_obs_tpa<double>(h->bufs, h->pd, h->plan, wm, mask, obs_only, h->sm_count, st));
-        else
-            CAV_CUDA(h, "pairwise_obs_tpa",
-                     run_pairwise_obs_tpa<float>(h->bufs, h->pf, h->plan, wm, mask, obs_only, h->sm_count, st));
+        CAV_CUDA(h, "pairwise_obs_tpa",
+                 CAV_BY_PRECISION(
+                     h, (run_pairwise_obs_tpa<float, float>(h->bufs, h->pf, h->plan, wm, mask, obs_only, h->sm_count, st)),
+                     (run_pairwise_obs_tpa<double, double>(h->bufs, h->pd, h->plan, wm, mask, obs_only, h->sm_count, st)),
+                     (run_pairwise_obs_tpa<double, float>(h->bufs, h->pd, h->plan, wm, mask, obs_only, h->sm_count, st))));
         return CAV_OK;
     }
-    if (h->cfg.precision == CAV_F64)
-        CAV_CUDA(h, "pairwise_obs", run_pairwise_obs<double>(h->bufs, h->pd, h->plan, wm, mask, obs_only, h->sm_count, st));
-    else
-        CAV_CUDA(h, "pairwise_obs", run_pairwise_obs<float>(h->bufs, h->pf, h->plan, wm, mask, obs_only, h->sm_count, st));
+    CAV_CUDA(h, "pairwise_obs",
+             CAV_BY_PRECISION(h, (run_pairwise_obs<float, float>(h->bufs, h->pf, h->plan, wm, mask, obs_only, h->sm_count, st)),
+                              (run_pairwise_obs<double, double>(h->bufs, h->pd, h->plan, wm, mask, obs_only, h->sm_count, st)),
+                              (run_pairwise_obs<double, float>(h->bufs, h->pd, h->plan, wm, mask, obs_only, h->sm_count, st))));
     return CAV_OK;
 }
 static int do_laser(cav_handle_t h, const uint8_t *mask, cudaStream_t st) {
-    if (h->cfg.precision == CAV_F64)
-        CAV_CUDA(h, "laserscan", run_laserscan<double>(h->bufs, h->lp, mask, h->sm_count, st));
-    else
-        CAV_CUDA(h, "laserscan", run_laserscan<float>(h->bufs, h->lp, mask, h->sm_count, st));
+    CAV_CUDA(h, "laserscan",
+             CAV_BY_PRECISION(h, (run_laserscan<float, float>(h->bufs, h->lp, mask, h->sm_count, st)),
+                              (run_laserscan<double, double>(h->bufs, h->lp, mask, h->sm_count, st)),
+                              (run_laserscan<double, float>(h->bufs, h->lp, mask, h->sm_count, st))));
     return CAV_OK;
 }
 
@@ -374,10 +378,10 @@ int cav_reset(cav_handle_t h, const uint8_t *env_mask, const cav_scenario_bank_t
     if (bank->num_scenarios < 1) return fail(h, CAV_ERR_BAD_CONFIG, "cav_reset: empty scenario bank");
     cudaStream_t st = (cudaStream_t)stream;
     h->launches = 0;
-    if (h->cfg.precision == CAV_F64)
-        CAV_CUDA(h, "reset", run_reset<double>(h->bufs, h->rp, env_mask, *bank, scenario_idx, accumulate_stats, st));
-    else
-        CAV_CUDA(h, "reset", run_reset<float>(h->bufs, h->rp, env_mask, *bank, scenario_idx, accumulate_stats, st));
+    CAV_CUDA(h, "reset",
+             CAV_BY_PRECISION(h, (run_reset<float, float>(h->bufs, h->rp, env_mask, *bank, scenario_idx, accumulate_stats, st)),
+                              (run_reset<double, double>(h->bufs, h->rp, env_mask, *bank, scenario_idx, accumulate_stats, st)),
+                              (run_reset<double, float>(h->bufs, h->rp, env_mask, *bank, scenario_idx, accumulate_stats, st))));
     int rc = do_pairwise_obs(h, env_mask, 1, st);  // reset returns self._get_obs() (env.py:282)
     if (rc) return rc;
     if (h->has_laser) rc = do_laser(h, env_mask, st);

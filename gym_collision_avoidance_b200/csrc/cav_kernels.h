@@ -13,18 +13,19 @@ void launch_geometry(int N, int &G, int &SL, int &GPE, int &EPB, int &threads);
 template <typename T>
 cudaError_t run_policy_move(const cav_buffers_t &bufs, const KParams<T> &p, const float *ext, int phases, double dt,
                             int sm_count, cudaStream_t st);
-template <typename T>
+// OT = precision of the packed observation / reward columns in HBM: T, or float next to float64 state (cfg.obs_f32)
+template <typename T, typename OT>
 cudaError_t run_pairwise_obs(const cav_buffers_t &bufs, const KParams<T> &p, const ObsPlan &plan, const WallMap &wm,
                              const uint8_t *env_mask, int obs_only, int sm_count, cudaStream_t st);
 
 // one-thread-per-agent pairwise+obs kernel (cav_tpa.cu), any observation layout, N <= 24
-template <typename T>
+template <typename T, typename OT>
 cudaError_t run_pairwise_obs_tpa(const cav_buffers_t &bufs, const KParams<T> &p, const ObsPlan &plan,
                                  const WallMap &wm, const uint8_t *env_mask, int obs_only, int sm_count,
                                  cudaStream_t st);
 size_t tpa_smem_bytes(int N, int precision_f64, const ObsPlan &plan, int K);
 // compile-time-N, register-resident specialisation (cav_tpa_n.cu); cudaErrorNotSupported = use the generic kernel
-template <typename T>
+template <typename T, typename OT>
 cudaError_t run_pairwise_obs_tpa_n(const cav_buffers_t &bufs, const KParams<T> &p, const ObsPlan &plan, const WallMap &wm,
                                    const uint8_t *env_mask, int obs_only, int sm_count, cudaStream_t st);
 
@@ -41,7 +42,7 @@ struct LaserParams {
     double origin0, origin1, cell, inv_cell;
     double min_angle, max_angle, ang_step, min_range, max_range, range_res;
 };
-template <typename T>
+template <typename T, typename OT>
 cudaError_t run_laserscan(const cav_buffers_t &bufs, const LaserParams &lp, const uint8_t *env_mask, int sm_count,
                           cudaStream_t st);
 
@@ -49,7 +50,7 @@ struct ResetParams {
     int E, N, obs_len;
     double dt, near_goal_threshold, max_time_ratio;
 };
-template <typename T>
+template <typename T, typename OT>
 cudaError_t run_reset(const cav_buffers_t &bufs, const ResetParams &rp, const uint8_t *env_mask,
                       const cav_scenario_bank_t &bank, const int32_t *scenario_idx, int accumulate_stats,
                       cudaStream_t st);

@@ -22,7 +22,7 @@ struct LaserPtrs {
     const uint32_t *static_map_bits;
 };
 
-template <typename T>
+template <typename T, typename OT>
 __global__ void __launch_bounds__(256) k_laserscan(LaserPtrs b, LaserParams lp, const uint8_t *__restrict__ env_mask,
                                                      int APC, int chunks, int nwork) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(256) k_laserscan(LaserPtrs b, LaserParams lp, 
     const R4<T> *g_pv = reinterpret_cast<const R4<T> *>(b.pv);
     const R4<T> *g_goal = reinterpret_cast<const R4<T> *>(b.goal);
     const R4<T> *g_ht = reinterpret_cast<const R4<T> *>(b.ht);
-    T *g_obs = reinterpret_cast<T *>(b.obs);
+    OT *g_obs = reinterpret_cast<OT *>(b.obs);  // OT: precision of the packed observation in HBM
     const bool has_static = b.static_map_bits != nullptr;
 
     for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
@@ -146,9 +146,9 @@ __global__ void __launch_bounds__(256) k_laserscan(LaserPtrs b, LaserParams lp, 
             const double px = s_px[h], py = s_py[h], hd = s_hd[h], rr2 = s_rr2[h];
             const int ego_in = s_in[h], cgx = s_gx[h], cgy = s_gy[h];
             const uint32_t cnt = s_cnt[h];
-            T *o = g_obs + (base + h) * (size_t)lp.obs_len + lp.obs_off;
+            OT *o = g_obs + (base + h) * (size_t)lp.obs_len + lp.obs_off;
             // measurement history rows that will shift down: fetch them now, their latency hides behind the march
-            T older[3] = {(T)0, (T)0, (T)0};
+            OT older[3] = {(OT)0, (OT)0, (OT)0};
             const bool prefetched = cnt != 0u && lp.P <= 4;
             if (prefetched) {
 #pragma unroll
@@ -215,15 +215,15 @@ __global__ void __launch_bounds__(256) k_laserscan(LaserPtrs b, LaserParams lp, 
                 if (cum == 1) kstar = lp.nr - 1;
                 const double rng = kstar >= 0 ? lp.min_range + (double)kstar * lp.range_res : lp.max_range;
                 if (cnt == 0u) {  // first measurement fills every row (:84-85)
-                    for (int pp = 0; pp < lp.P; ++pp) o[(size_t)pp * lp.B + bi] = (T)rng;
+                    for (int pp = 0; pp < lp.P; ++pp) o[(size_t)pp * lp.B + bi] = (OT)rng;
                 } else if (prefetched) {  // np.roll(history, 1, axis=0); row 0 = newest (:86-88)
 #pragma unroll
                     for (int pp = 3; pp >= 1; --pp)
                         if (pp < lp.P) o[(size_t)pp * lp.B + bi] = older[pp - 1];
-                    o[bi] = (T)rng;
+                    o[bi] = (OT)rng;
                 } else {
                     for (int pp = lp.P - 1; pp >= 1; --pp) o[(size_t)pp * lp.B + bi] = o[(size_t)(pp - 1) * lp.B + bi];
-                    o[bi] = (T)rng;
+                    o[bi] = (OT)rng;
                 }
             }
         }
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(256) k_laserscan(LaserPtrs b, LaserParams lp, 
     }
 }
 
-template <typename T>
+template <typename T, typename OT>
 cudaError_t run_laserscan(const cav_buffers_t &bufs, const LaserParams &lp, const uint8_t *env_mask, int sm_count,
                           cudaStream_t st) {
     LaserPtrs p;
@@ -248,7 +248,7 @@ cudaError_t run_laserscan(const cav_buffers_t &bufs, const LaserParams &lp, cons
     const int nwork = lp.E * chunks;
     const size_t smem = (((size_t)lp.rows * lp.wpr * 4 + 15) & ~(size_t)15) + CAV_MAX_AGENTS * (4 * 8 + 4 * 4) +
                         (size_t)APC * CAV_MAX_AGENTS * 4 * 8 + APC * 4 + 64;
-    auto kern = k_laserscan<T>;
+    auto kern = k_laserscan<T, OT>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -258,8 +258,11 @@ cudaError_t run_laserscan(const cav_buffers_t &bufs, const LaserParams &lp, cons
     return cudaGetLastError();
 }
 
-template cudaError_t run_laserscan<float>(const cav_buffers_t &, const LaserParams &, const uint8_t *, int, cudaStream_t);
-template cudaError_t run_laserscan<double>(const cav_buffers_t &, const LaserParams &, const uint8_t *, int,
-                                           cudaStream_t);
+template cudaError_t run_laserscan<float, float>(const cav_buffers_t &, const LaserParams &, const uint8_t *, int,
+                                                 cudaStream_t);
+template cudaError_t run_laserscan<double, double>(const cav_buffers_t &, const LaserParams &, const uint8_t *, int,
+                                                   cudaStream_t);
+template cudaError_t run_laserscan<double, float>(const cav_buffers_t &, const LaserParams &, const uint8_t *, int,
+                                                  cudaStream_t);
 
 }  // namespace cav

@@ -30,7 +30,7 @@ __device__ __forceinline__ V warp_sum(V v) {
     return v;
 }
 
-template <typename T>
+template <typename T, typename OT>
 __global__ void __launch_bounds__(256) k_reset(ResetPtrs b, ResetParams rp, const uint8_t *__restrict__ env_mask,
                                                  cav_scenario_bank_t bank, const int32_t *__restrict__ scenario_idx,
                                                  int accumulate_stats) {
@@ -98,9 +98,9 @@ __global__ void __launch_bounds__(256) k_reset(ResetPtrs b, ResetParams rp, cons
         if (lane == 0 && b.num_active) b.num_active[e] = n;
         // ---- env.reset zeroes the whole observation (env.py:276-281): coalesced over the env's block ----
         {
-            T *o = reinterpret_cast<T *>(b.obs) + base * (size_t)rp.obs_len;
+            OT *o = reinterpret_cast<OT *>(b.obs) + base * (size_t)rp.obs_len;  // OT: observation precision in HBM
             const int total = N * rp.obs_len;
-            for (int k = lane; k < total; k += 32) o[k] = (T)0;
+            for (int k = lane; k < total; k += 32) o[k] = (OT)0;
         }
         // ---- Agent.reset (agent.py:59-138) ----
         for (int a = lane; a < N; a += 32) {
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(256) k_reset(ResetPtrs b, ResetParams rp, cons
     }
 }
 
-template <typename T>
+template <typename T, typename OT>
 cudaError_t run_reset(const cav_buffers_t &bufs, const ResetParams &rp, const uint8_t *env_mask,
                       const cav_scenario_bank_t &bank, const int32_t *scenario_idx, int accumulate_stats,
                       cudaStream_t st) {
@@ -172,13 +172,15 @@ cudaError_t run_reset(const cav_buffers_t &bufs, const ResetParams &rp, const ui
     const int wpb = 8;
     int grid = (rp.E + wpb - 1) / wpb;
     if (grid > 148 * 16) grid = 148 * 16;
-    k_reset<T><<<grid, wpb * 32, 0, st>>>(p, rp, env_mask, bank, scenario_idx, accumulate_stats);
+    k_reset<T, OT><<<grid, wpb * 32, 0, st>>>(p, rp, env_mask, bank, scenario_idx, accumulate_stats);
     return cudaGetLastError();
 }
 
-template cudaError_t run_reset<float>(const cav_buffers_t &, const ResetParams &, const uint8_t *,
-                                      const cav_scenario_bank_t &, const int32_t *, int, cudaStream_t);
-template cudaError_t run_reset<double>(const cav_buffers_t &, const ResetParams &, const uint8_t *,
-                                       const cav_scenario_bank_t &, const int32_t *, int, cudaStream_t);
+template cudaError_t run_reset<float, float>(const cav_buffers_t &, const ResetParams &, const uint8_t *,
+                                             const cav_scenario_bank_t &, const int32_t *, int, cudaStream_t);
+template cudaError_t run_reset<double, double>(const cav_buffers_t &, const ResetParams &, const uint8_t *,
+                                               const cav_scenario_bank_t &, const int32_t *, int, cudaStream_t);
+template cudaError_t run_reset<double, float>(const cav_buffers_t &, const ResetParams &, const uint8_t *,
+                                              const cav_scenario_bank_t &, const int32_t *, int, cudaStream_t);
 
 }  // namespace cav

@@ -378,7 +378,7 @@ struct ObsKeyOps {
     }
 };
 
-template <typename T, int G, int SL>
+template <typename T, int G, int SL, typename OT>
 __global__ void __launch_bounds__(512) k_pairwise_obs(DevBuffers b, KParams<T> p, ObsPlan plan, WallMap wm,
                                                         const uint8_t *__restrict__ env_mask, int obs_only, int EPB,
                                                         int GPE, int ntiles) {
@@ -414,8 +414,8 @@ __global__ void __launch_bounds__(512) k_pairwise_obs(DevBuffers b, KParams<T> p
     const R4<T> *g_pv = reinterpret_cast<const R4<T> *>(b.pv);
     const R4<T> *g_goal = reinterpret_cast<const R4<T> *>(b.goal);
     const R4<T> *g_ego = reinterpret_cast<const R4<T> *>(b.ego);
-    T *g_obs = reinterpret_cast<T *>(b.obs);
-    T *g_reward = reinterpret_cast<T *>(b.reward);
+    OT *g_obs = reinterpret_cast<OT *>(b.obs);  // OT: precision of the packed observation / reward in HBM
+    OT *g_reward = reinterpret_cast<OT *>(b.reward);
     T *g_mind = reinterpret_cast<T *>(b.min_dist);
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -516,7 +516,7 @@ __global__ void __launch_bounds__(512) k_pairwise_obs(DevBuffers b, KParams<T> p
                     __syncwarp(gm);
                     if (glane == 0) {
                         s_flags[li] = f;
-                        g_reward[base + li] = r;
+                        g_reward[base + li] = (OT)r;
                         if (g_mind) g_mind[base + li] = md;
                     }
                 }
@@ -565,9 +565,9 @@ __global__ void __launch_bounds__(512) k_pairwise_obs(DevBuffers b, KParams<T> p
                         }
                         if (rank == 0 && plan.oas7_goff >= 0) {
                             // Agent.other_agent_states (persists when nobody is observed): direct global write
-                            T *dst = g_obs + (base + li) * p.obs_len + plan.oas7_goff;
+                            OT *dst = g_obs + (base + li) * p.obs_len + plan.oas7_goff;
 #pragma unroll
-                            for (int k = 0; k < 7; ++k) dst[k] = row[k];
+                            for (int k = 0; k < 7; ++k) dst[k] = (OT)row[k];
                         }
                     }
                 }
@@ -583,10 +583,10 @@ __global__ void __launch_bounds__(512) k_pairwise_obs(DevBuffers b, KParams<T> p
                     if (plan.c_state[CAV_OBS_RADIUS] >= 0) my_obs[plan.c_state[CAV_OBS_RADIUS]] = glh.z;
                 }
                 __syncwarp(gm);
-                T *dst = g_obs + (base + li) * p.obs_len;
+                OT *dst = g_obs + (base + li) * p.obs_len;
                 for (int sg = 0; sg < plan.nseg; ++sg) {
                     const int go = plan.goff[sg], co = plan.coff[sg], ln = plan.len[sg];
-                    for (int k = glane; k < ln; k += G) dst[go + k] = my_obs[co + k];
+                    for (int k = glane; k < ln; k += G) dst[go + k] = (OT)my_obs[co + k];
                 }
                 __syncwarp(gm);  // my_obs is reused by this group's next agent
             }
@@ -680,13 +680,13 @@ static cudaError_t launch_pm(const cav_buffers_t &bufs, const KParams<T> &p, con
     return cudaGetLastError();
 }
 
-template <typename T, int G, int SL>
+template <typename T, typename OT, int G, int SL>
 static cudaError_t launch_po(const cav_buffers_t &bufs, const KParams<T> &p, const ObsPlan &plan, const WallMap &wm,
                              const uint8_t *env_mask, int obs_only, int EPB, int GPE, int threads, int sm_count,
                              cudaStream_t st) {
     const int ntiles = (p.E + EPB - 1) / EPB;
     const size_t smem = smem_pairwise_obs<T>(EPB * p.N, EPB, threads / G, plan.compact_len);
-    auto kern = k_pairwise_obs<T, G, SL>;
+    auto kern = k_pairwise_obs<T, G, SL, OT>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -696,41 +696,44 @@ static cudaError_t launch_po(const cav_buffers_t &bufs, const KParams<T> &p, con
     return cudaGetLastError();
 }
 
-#define CAV_DISPATCH_SHAPE(FN, ...)                                 \
+#define CAV_DISPATCH_SHAPE(FN, TT, ...)                             \
     do {                                                            \
-        if (SL == 2) return FN<T, 32, 2>(__VA_ARGS__);              \
+        if (SL == 2) return FN<TT, 32, 2>(__VA_ARGS__);             \
         switch (G) {                                                \
-            case 1: return FN<T, 1, 1>(__VA_ARGS__);                \
-            case 2: return FN<T, 2, 1>(__VA_ARGS__);                \
-            case 4: return FN<T, 4, 1>(__VA_ARGS__);                \
-            case 8: return FN<T, 8, 1>(__VA_ARGS__);                \
-            case 16: return FN<T, 16, 1>(__VA_ARGS__);              \
-            default: return FN<T, 32, 1>(__VA_ARGS__);              \
+            case 1: return FN<TT, 1, 1>(__VA_ARGS__);               \
+            case 2: return FN<TT, 2, 1>(__VA_ARGS__);               \
+            case 4: return FN<TT, 4, 1>(__VA_ARGS__);               \
+            case 8: return FN<TT, 8, 1>(__VA_ARGS__);               \
+            case 16: return FN<TT, 16, 1>(__VA_ARGS__);             \
+            default: return FN<TT, 32, 1>(__VA_ARGS__);             \
         }                                                           \
     } while (0)
+#define CAV_COMMA ,
 
 template <typename T>
 cudaError_t run_policy_move(const cav_buffers_t &bufs, const KParams<T> &p, const float *ext, int phases, double dt,
                             int sm_count, cudaStream_t st) {
     int G, SL, GPE, EPB, threads;
     launch_geometry(p.N, G, SL, GPE, EPB, threads);
-    CAV_DISPATCH_SHAPE(launch_pm, bufs, p, ext, phases, dt, EPB, GPE, threads, sm_count, st);
+    CAV_DISPATCH_SHAPE(launch_pm, T, bufs, p, ext, phases, dt, EPB, GPE, threads, sm_count, st);
 }
-template <typename T>
+template <typename T, typename OT>
 cudaError_t run_pairwise_obs(const cav_buffers_t &bufs, const KParams<T> &p, const ObsPlan &plan, const WallMap &wm,
                              const uint8_t *env_mask, int obs_only, int sm_count, cudaStream_t st) {
     int G, SL, GPE, EPB, threads;
     launch_geometry(p.N, G, SL, GPE, EPB, threads);
-    CAV_DISPATCH_SHAPE(launch_po, bufs, p, plan, wm, env_mask, obs_only, EPB, GPE, threads, sm_count, st);
+    CAV_DISPATCH_SHAPE(launch_po, T CAV_COMMA OT, bufs, p, plan, wm, env_mask, obs_only, EPB, GPE, threads, sm_count, st);
 }
 
 template cudaError_t run_policy_move<float>(const cav_buffers_t &, const KParams<float> &, const float *, int, double,
                                             int, cudaStream_t);
 template cudaError_t run_policy_move<double>(const cav_buffers_t &, const KParams<double> &, const float *, int,
                                              double, int, cudaStream_t);
-template cudaError_t run_pairwise_obs<float>(const cav_buffers_t &, const KParams<float> &, const ObsPlan &,
-                                             const WallMap &, const uint8_t *, int, int, cudaStream_t);
-template cudaError_t run_pairwise_obs<double>(const cav_buffers_t &, const KParams<double> &, const ObsPlan &,
-                                              const WallMap &, const uint8_t *, int, int, cudaStream_t);
+template cudaError_t run_pairwise_obs<float, float>(const cav_buffers_t &, const KParams<float> &, const ObsPlan &,
+                                                    const WallMap &, const uint8_t *, int, int, cudaStream_t);
+template cudaError_t run_pairwise_obs<double, double>(const cav_buffers_t &, const KParams<double> &, const ObsPlan &,
+                                                      const WallMap &, const uint8_t *, int, int, cudaStream_t);
+template cudaError_t run_pairwise_obs<double, float>(const cav_buffers_t &, const KParams<double> &, const ObsPlan &,
+                                                     const WallMap &, const uint8_t *, int, int, cudaStream_t);
 
 }  // namespace cav

@@ -31,7 +31,8 @@ namespace cav {
 //   float32 state: 23 + 32 + 6 bits -- exact.   float64 state: 24 + top 34 bits of p_orth + 6 bits; keys whose kint
 //   fields are equal are re-compared exactly (kint as a real, full p_orth, index) by a bounded bubble pass, so the
 //   final order is exactly the reference's stable two-key sort also for clamped / truncated fields.
-template <typename T>
+// OT: precision of the packed observation / reward in HBM (the staging arena stays in T; see k_pairwise_obs_tpa_n)
+template <typename T, typename OT>
 __global__ void __launch_bounds__(128) k_pairwise_obs_tpa(TpaBuffers b, KParams<T> p, ObsPlan plan, WallMap wm,
                                                             const uint8_t *__restrict__ env_mask, int obs_only, int EPB,
                                                             int ntiles, int region_bytes, ChunkPlan chunks) {
@@ -62,8 +63,8 @@ __global__ void __launch_bounds__(128) k_pairwise_obs_tpa(TpaBuffers b, KParams<
     const R4<T> *g_pv = reinterpret_cast<const R4<T> *>(b.pv);
     const R4<T> *g_goal = reinterpret_cast<const R4<T> *>(b.goal);
     const R4<T> *g_ego = reinterpret_cast<const R4<T> *>(b.ego);
-    T *g_obs = reinterpret_cast<T *>(b.obs);
-    T *g_reward = reinterpret_cast<T *>(b.reward);
+    OT *g_obs = reinterpret_cast<OT *>(b.obs);
+    OT *g_reward = reinterpret_cast<OT *>(b.reward);
     T *g_mind = reinterpret_cast<T *>(b.min_dist);
     const int K = p.K;
     const int CL = plan.compact_len;
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(128) k_pairwise_obs_tpa(TpaBuffers b, KParams<
                     }
                 }
                 r = r < p.reward_min ? p.reward_min : (r > p.reward_max ? p.reward_max : r);  // np.clip
-                g_reward[gi] = r;
+                g_reward[gi] = (OT)r;
                 if (g_mind) g_mind[gi] = md;
                 // done (env.py:514-536)
                 const bool d = (f & (CAV_FLAG_AT_GOAL | CAV_FLAG_RAN_OUT_OF_TIME | CAV_FLAG_IN_COLLISION)) != 0;
@@ -248,7 +249,7 @@ __global__ void __launch_bounds__(128) k_pairwise_obs_tpa(TpaBuffers b, KParams<
             constexpr int CW = TpaChunk<T>::CW;
             constexpr int AST = CW + 1;
             constexpr int APL = 32 / CW;  // agents per store instruction
-            T *gwarp = g_obs + (base + (size_t)(warp << 5)) * (size_t)p.obs_len;
+            OT *gwarp = g_obs + (base + (size_t)(warp << 5)) * (size_t)p.obs_len;
             const int sub = lane / CW, kk = lane - sub * CW;
             const bool all_active = (vmask == 0xffffffffu);
 #pragma unroll 1
@@ -294,14 +295,14 @@ __global__ void __launch_bounds__(128) k_pairwise_obs_tpa(TpaBuffers b, KParams<
                                 row[6] = r6;
                                 if (r == 0 && plan.oas7_goff >= 0) {
                                     // Agent.other_agent_states persists when nobody is observed: direct write
-                                    T *dst = g_obs + gi * (size_t)p.obs_len + plan.oas7_goff;
-                                    dst[0] = r0;
-                                    dst[1] = r1;
-                                    dst[2] = r2;
-                                    dst[3] = r3;
-                                    dst[4] = ro;
-                                    dst[5] = r5;
-                                    dst[6] = r6;
+                                    OT *dst = g_obs + gi * (size_t)p.obs_len + plan.oas7_goff;
+                                    dst[0] = (OT)r0;
+                                    dst[1] = (OT)r1;
+                                    dst[2] = (OT)r2;
+                                    dst[3] = (OT)r3;
+                                    dst[4] = (OT)ro;
+                                    dst[5] = (OT)r5;
+                                    dst[6] = (OT)r6;
                                 }
                             } else {
 #pragma unroll
@@ -314,19 +315,19 @@ __global__ void __launch_bounds__(128) k_pairwise_obs_tpa(TpaBuffers b, KParams<
                 if (c0 + kk < c1) {
                     const int gk = obs_gmap(plan, c0 + kk);
                     const T *src = arena + sub * AST + kk;
-                    T *dst = gwarp + sub * p.obs_len + gk;
+                    OT *dst = gwarp + sub * p.obs_len + gk;
                     const int dstep = APL * p.obs_len;
                     if (all_active) {
 #pragma unroll 4
                         for (int j = sub; j < 32; j += APL) {
-                            *dst = *src;
+                            *dst = (OT)*src;
                             src += APL * AST;
                             dst += dstep;
                         }
                     } else {
 #pragma unroll 1
                         for (int j = sub; j < 32; j += APL) {
-                            if ((vmask >> j) & 1u) *dst = *src;
+                            if ((vmask >> j) & 1u) *dst = (OT)*src;
                             src += APL * AST;
                             dst += dstep;
                         }
@@ -412,7 +413,7 @@ size_t tpa_smem_pairwise_obs(int N, int EPB, int nt, int region_bytes) {
            a16((size_t)nwarps * region_bytes) + a16((size_t)cap) + a16(sizeof(int) * EPB) + 64;
 }
 
-template <typename T>
+template <typename T, typename OT>
 cudaError_t run_pairwise_obs_tpa(const cav_buffers_t &bufs, const KParams<T> &p, const ObsPlan &plan,
                                  const WallMap &wm, const uint8_t *env_mask, int obs_only, int sm_count,
                                  cudaStream_t st) {
@@ -421,7 +422,7 @@ cudaError_t run_pairwise_obs_tpa(const cav_buffers_t &bufs, const KParams<T> &p,
     const int ntiles = (p.E + EPB - 1) / EPB;
     const int rb = tpa_region_bytes<T>(p.N, plan, p.K);
     const size_t smem = tpa_smem_pairwise_obs<T>(p.N, EPB, threads, rb);
-    auto kern = k_pairwise_obs_tpa<T>;
+    auto kern = k_pairwise_obs_tpa<T, OT>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -440,9 +441,11 @@ size_t tpa_smem_bytes(int N, int precision_f64, const ObsPlan &plan, int K) {
                          : tpa_smem_pairwise_obs<float>(N, EPB, threads, tpa_region_bytes<float>(N, plan, K));
 }
 
-template cudaError_t run_pairwise_obs_tpa<float>(const cav_buffers_t &, const KParams<float> &, const ObsPlan &,
-                                                 const WallMap &, const uint8_t *, int, int, cudaStream_t);
-template cudaError_t run_pairwise_obs_tpa<double>(const cav_buffers_t &, const KParams<double> &, const ObsPlan &,
-                                                  const WallMap &, const uint8_t *, int, int, cudaStream_t);
+template cudaError_t run_pairwise_obs_tpa<float, float>(const cav_buffers_t &, const KParams<float> &, const ObsPlan &,
+                                                        const WallMap &, const uint8_t *, int, int, cudaStream_t);
+template cudaError_t run_pairwise_obs_tpa<double, double>(const cav_buffers_t &, const KParams<double> &, const ObsPlan &,
+                                                          const WallMap &, const uint8_t *, int, int, cudaStream_t);
+template cudaError_t run_pairwise_obs_tpa<double, float>(const cav_buffers_t &, const KParams<double> &, const ObsPlan &,
+                                                         const WallMap &, const uint8_t *, int, int, cudaStream_t);
 
 }  // namespace cav

@@ -44,13 +44,13 @@ struct TpaNBounds<double> {
 // consecutive lanes on consecutive addresses -- 128 B (float32) / 256 B (float64) per store instruction, the whole
 // 8 KB block in 65 stores instead of ~100 partial-row ones.  float64 stages the row in two column ranges to keep the
 // slice at 8 KB per warp (5 CTAs / SM).
-template <typename T, int NT>
+template <typename T, int NT, typename OT = T>
 struct TpaNShape {
     static constexpr int NO = NT - 1;
     static constexpr int EPW = 32 / NT;
     static constexpr int LW = EPW * NT;
     static constexpr int CL = 6 + 7 * NO;
-    static constexpr int P = (sizeof(T) == 8 && NO >= 2) ? 2 : 1;  // staging passes
+    static constexpr int P = (sizeof(OT) == 8 && NO >= 2) ? 2 : 1;  // staging passes
     static constexpr int RA = P == 1 ? NO : NO / 2;                // neighbour rows in pass 0
     static constexpr int W0 = 6 + 7 * RA;
     static constexpr int W1 = 7 * (NO - RA);
@@ -60,17 +60,19 @@ struct TpaNShape {
     static constexpr int WARPS = sizeof(T) == 8 ? 4 : 2;
     static constexpr int EPB = WARPS * EPW;
     // float32, single pass, staging stride == packed row length: the slice is a flat image of the HBM block
-    static constexpr bool FLAT4 = sizeof(T) == 4 && P == 1 && WS == CL;
+    static constexpr bool FLAT4 = sizeof(OT) == 4 && P == 1 && WS == CL;
     static constexpr size_t r16(size_t x) { return (x + 15) & ~(size_t)15; }
-    static constexpr size_t WARP_BYTES = r16(sizeof(R4<T>) * LW) + r16(sizeof(T) * LW) + r16(sizeof(T) * (LW * WS + 4));
+    static constexpr size_t WARP_BYTES = r16(sizeof(R4<T>) * LW) + r16(sizeof(T) * LW) + r16(sizeof(OT) * (LW * WS + 4));
 };
 
-template <typename T, int NT>
-__global__ void __launch_bounds__(32 * TpaNShape<T, NT>::WARPS, (TpaNBounds<T>::MINB * 4) / TpaNShape<T, NT>::WARPS)
+// T = state precision, OT = precision of the packed observation and of the reward (float when the state is float, or when
+// cfg.obs_f32 asks for the reference's DECLARED observation dtype -- np.float32, config.py:93-170 -- next to float64 state)
+template <typename T, int NT, typename OT>
+__global__ void __launch_bounds__(32 * TpaNShape<T, NT, OT>::WARPS, (TpaNBounds<T>::MINB * 4) / TpaNShape<T, NT, OT>::WARPS)
     k_pairwise_obs_tpa_n(TpaBuffers b, KParams<T> p, WallMap wm,
                                                               const uint8_t *__restrict__ env_mask, int obs_only,
                                                               int ntiles) {
-    using S = TpaNShape<T, NT>;
+    using S = TpaNShape<T, NT, OT>;
     constexpr int NO = S::NO, EPW = S::EPW, LW = S::LW, CL = S::CL, WS = S::WS, RA = S::RA;
     constexpr int KSHIFT = KeyCodec<T>::PB + 6;
     constexpr unsigned LWMASK = LW >= 32 ? 0xffffffffu : ((1u << LW) - 1u);
@@ -82,12 +84,13 @@ __global__ void __launch_bounds__(32 * TpaNShape<T, NT>::WARPS, (TpaNBounds<T>::
     sp += a16(sizeof(R4<T>) * LW);
     T *s_rad = reinterpret_cast<T *>(sp);
     sp += a16(sizeof(T) * LW);
-    T *const stage0 = reinterpret_cast<T *>(sp);  // [LW][WS] (+ up to 3 values of phase shift, see FLAT4)
+    OT *const stage0 = reinterpret_cast<OT *>(sp);  // [LW][WS] (+ up to 3 values of phase shift, see FLAT4)
     const R4<T> *g_pv = reinterpret_cast<const R4<T> *>(b.pv);
     const R4<T> *g_goal = reinterpret_cast<const R4<T> *>(b.goal);
     const R4<T> *g_ego = reinterpret_cast<const R4<T> *>(b.ego);
-    T *g_obs = reinterpret_cast<T *>(b.obs);
-    T *g_reward = reinterpret_cast<T *>(b.reward);
+    OT *g_obs = reinterpret_cast<OT *>(b.obs);
+    OT *g_reward = reinterpret_cast<OT *>(b.reward);
+    bool bulk_pending = false;  // lane 0: a bulk copy out of the staging slice may still be reading it
     T *g_mind = reinterpret_cast<T *>(b.min_dist);
     const int el = lane / NT, h = lane - el * NT;  // env within the warp, agent within the env
     const int eb = el * NT;
@@ -216,7 +219,7 @@ __global__ void __launch_bounds__(32 * TpaNShape<T, NT>::WARPS, (TpaNBounds<T>::
                     }
                 }
                 r = r < p.reward_min ? p.reward_min : (r > p.reward_max ? p.reward_max : r);  // np.clip
-                g_reward[gi] = r;
+                g_reward[gi] = (OT)r;
                 if (g_mind) g_mind[gi] = md;
                 done_now = (f & (CAV_FLAG_AT_GOAL | CAV_FLAG_RAN_OUT_OF_TIME | CAV_FLAG_IN_COLLISION)) != 0;
                 f = done_now ? (f | CAV_FLAG_DONE) : (f & ~(uint32_t)CAV_FLAG_DONE);
@@ -245,49 +248,63 @@ __global__ void __launch_bounds__(32 * TpaNShape<T, NT>::WARPS, (TpaNBounds<T>::
         }
         // ---- packed observation through the warp's staging slice ----
         if (vmask != 0u) {
-            T *gwarp = g_obs + wbase * (size_t)CL;
+            OT *gwarp = g_obs + wbase * (size_t)CL;
             // FLAT4: shift the slice so that shared and global addresses agree modulo 16 bytes (obs is 16-byte aligned)
             const int mis = S::FLAT4 ? (int)((wbase * (size_t)CL) & 3) : 0;
-            T *stage = stage0 + mis;
-            T *my = stage + lane * WS;
-            auto fill_row = [&](int r, T *dst) {  // r is a compile-time constant at every call site
+            OT *stage = stage0 + mis;
+            OT *my = stage + lane * WS;
+            if (S::FLAT4) {  // the previous tile's bulk copy must have finished READING the slice before it is rewritten
+                if (bulk_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                bulk_pending = false;
+                __syncwarp();
+            }
+            auto fill_row = [&](int r, OT *dst) {  // r is a compile-time constant at every call site
                 if (r < nc) {
                     const int o = (int)(key[r] & 63ull);
                     const R4<T> pvo = s_pv[eb + o];
                     const T ro = s_rad[eb + o];
                     const T rx = pvo.x - pvh.x, ry = pvo.y - pvh.y;
-                    dst[0] = rx * prx + ry * pry;
-                    dst[1] = rx * orx + ry * ory;
-                    dst[2] = pvo.z * prx + pvo.w * pry;
-                    dst[3] = pvo.z * orx + pvo.w * ory;
-                    dst[4] = ro;
-                    dst[5] = glh.z + ro;
-                    dst[6] = dcv[r] - glh.z - ro;  // np.linalg.norm(..) - r - r (:125)
+                    dst[0] = (OT)(rx * prx + ry * pry);
+                    dst[1] = (OT)(rx * orx + ry * ory);
+                    dst[2] = (OT)(pvo.z * prx + pvo.w * pry);
+                    dst[3] = (OT)(pvo.z * orx + pvo.w * ory);
+                    dst[4] = (OT)ro;
+                    dst[5] = (OT)(glh.z + ro);
+                    dst[6] = (OT)(dcv[r] - glh.z - ro);  // np.linalg.norm(..) - r - r (:125)
                 } else {
 #pragma unroll
-                    for (int k = 0; k < 7; ++k) dst[k] = (T)0;  // zero rows (:108)
+                    for (int k = 0; k < 7; ++k) dst[k] = (OT)0;  // zero rows (:108)
                 }
             };
             // columns [c0, c0 + W) of every agent of the warp: element idx = agent * W + column
             auto stream_out = [&](auto c0_, auto w_) {
                 constexpr int c0 = decltype(c0_)::value, W = decltype(w_)::value;
                 constexpr int TOT = LW * W;
-                __syncwarp();
                 if (vmask == LWMASK && S::FLAT4) {
-                    // one contiguous block, same 16-byte phase in shared and global memory: 128-bit body
+                    // One contiguous block with the same 16-byte phase in shared and global memory: its 16-byte-aligned
+                    // body (8 KB at N = 10) leaves as ONE bulk asynchronous copy (cp.async.bulk shared -> global, the TMA
+                    // engine; SASS UBLKCP) issued by lane 0 instead of 17 LDS.128 + STG.128 per lane; up to 3 values of
+                    // head and tail go through ordinary stores.  Writers fence their shared-memory stores towards the
+                    // async proxy, the warp converges, lane 0 issues; the slice is reused only after wait_group.read.
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
                     const int head = (4 - mis) & 3;
-                    if (lane < head) gwarp[lane] = stage[lane];
-                    const float4 *src4 = reinterpret_cast<const float4 *>(stage + head);
-                    float4 *dst4 = reinterpret_cast<float4 *>(gwarp + head);
                     const int nvec = (TOT - head) >> 2;
-#pragma unroll
-                    for (int v0 = 0; v0 < TOT / 4; v0 += 32) {
-                        const int v = v0 + lane;
-                        if (v < nvec) dst4[v] = src4[v];
+                    if (lane == 0) {
+                        const unsigned src = (unsigned)__cvta_generic_to_shared(stage + head);
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gwarp + head),
+                                     "r"(src), "r"(nvec * 16)
+                                     : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        bulk_pending = true;
                     }
+                    if (lane < head) gwarp[lane] = stage[lane];
                     const int t = head + 4 * nvec + lane;
                     if (t < TOT) gwarp[t] = stage[t];
-                } else if (vmask == LWMASK) {
+                    return;
+                }
+                __syncwarp();
+                if (vmask == LWMASK) {
                     // element idx = 32 t + lane sits in agent row j = idx / W; W > 32, so j is q_t or q_t + 1 with
                     // compile-time q_t and a per-lane carry (no division in the unrolled code)
 #pragma unroll
@@ -312,12 +329,12 @@ __global__ void __launch_bounds__(32 * TpaNShape<T, NT>::WARPS, (TpaNBounds<T>::
             };
             // pass 0: the six scalars (agent.py:323-327, default STATES_IN_OBS order) + rows [0, RA)
             if (active) {
-                my[0] = (CAV_KIND_POLICY(kind) == CAV_POLICY_LEARNING) ? (T)1 : (T)0;  // is_learning
-                my[1] = (T)nc;                                                          // num_other_agents
-                my[2] = egh.x;                                                          // dist_to_goal
-                my[3] = egh.y;                                                          // heading_ego_frame
-                my[4] = glh.w;                                                          // pref_speed
-                my[5] = glh.z;                                                          // radius
+                my[0] = (CAV_KIND_POLICY(kind) == CAV_POLICY_LEARNING) ? (OT)1 : (OT)0;  // is_learning
+                my[1] = (OT)nc;                                                           // num_other_agents
+                my[2] = (OT)egh.x;                                                        // dist_to_goal
+                my[3] = (OT)egh.y;                                                        // heading_ego_frame
+                my[4] = (OT)glh.w;                                                        // pref_speed
+                my[5] = (OT)glh.z;                                                        // radius
 #pragma unroll
                 for (int r = 0; r < RA; ++r) fill_row(r, my + 6 + 7 * r);
             }
@@ -332,6 +349,7 @@ __global__ void __launch_bounds__(32 * TpaNShape<T, NT>::WARPS, (TpaNBounds<T>::
         }
         __syncwarp();
     }
+    if (S::FLAT4 && bulk_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 // true when the plan is the default layout this kernel hard-codes
@@ -346,29 +364,29 @@ static bool standard_layout(const ObsPlan &plan, const KParams<float> *, int N, 
     return plan.c_state[CAV_OBS_OTHER_AGENTS_STATES] == 6;
 }
 
-template <typename T, int NT>
+template <typename T, int NT, typename OT>
 static cudaError_t launch_n(const cav_buffers_t &bufs, const KParams<T> &p, const WallMap &wm, const uint8_t *env_mask,
                             int obs_only, int sm_count, cudaStream_t st) {
-    using S = TpaNShape<T, NT>;
+    using S = TpaNShape<T, NT, OT>;
     const int ntiles = (p.E + S::EPB - 1) / S::EPB;
     const size_t smem = S::WARP_BYTES * S::WARPS;
     if (smem > 48 * 1024) {  // per device, so not cached in a process-wide flag (no current shape needs it: <= 38.4 KB)
-        cudaError_t e = cudaFuncSetAttribute(k_pairwise_obs_tpa_n<T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_pairwise_obs_tpa_n<T, NT, OT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
     const int grid = ntiles < sm_count * 16 ? ntiles : sm_count * 16;
-    k_pairwise_obs_tpa_n<T, NT><<<grid, 32 * S::WARPS, smem, st>>>(make_tpa(bufs), p, wm, env_mask, obs_only, ntiles);
+    k_pairwise_obs_tpa_n<T, NT, OT><<<grid, 32 * S::WARPS, smem, st>>>(make_tpa(bufs), p, wm, env_mask, obs_only, ntiles);
     return cudaGetLastError();
 }
 
 // Returns cudaErrorNotSupported when no specialisation applies (the caller then runs the generic kernel).
-template <typename T>
+template <typename T, typename OT>
 cudaError_t run_pairwise_obs_tpa_n(const cav_buffers_t &bufs, const KParams<T> &p, const ObsPlan &plan, const WallMap &wm,
                                    const uint8_t *env_mask, int obs_only, int sm_count, cudaStream_t st) {
     if (!standard_layout(plan, nullptr, p.N, p.K, p.obs_len, p.sorting)) return cudaErrorNotSupported;
     switch (p.N) {
 #define CAV_CASE(NN) \
-    case NN: return launch_n<T, NN>(bufs, p, wm, env_mask, obs_only, sm_count, st);
+    case NN: return launch_n<T, NN, OT>(bufs, p, wm, env_mask, obs_only, sm_count, st);
         CAV_CASE(2)
         CAV_CASE(3)
         CAV_CASE(4)
@@ -382,9 +400,11 @@ cudaError_t run_pairwise_obs_tpa_n(const cav_buffers_t &bufs, const KParams<T> &
     }
 }
 
-template cudaError_t run_pairwise_obs_tpa_n<float>(const cav_buffers_t &, const KParams<float> &, const ObsPlan &,
-                                                   const WallMap &, const uint8_t *, int, int, cudaStream_t);
-template cudaError_t run_pairwise_obs_tpa_n<double>(const cav_buffers_t &, const KParams<double> &, const ObsPlan &,
-                                                    const WallMap &, const uint8_t *, int, int, cudaStream_t);
+template cudaError_t run_pairwise_obs_tpa_n<float, float>(const cav_buffers_t &, const KParams<float> &, const ObsPlan &,
+                                                          const WallMap &, const uint8_t *, int, int, cudaStream_t);
+template cudaError_t run_pairwise_obs_tpa_n<double, double>(const cav_buffers_t &, const KParams<double> &, const ObsPlan &,
+                                                            const WallMap &, const uint8_t *, int, int, cudaStream_t);
+template cudaError_t run_pairwise_obs_tpa_n<double, float>(const cav_buffers_t &, const KParams<double> &, const ObsPlan &,
+                                                           const WallMap &, const uint8_t *, int, int, cudaStream_t);
 
 }  // namespace cav

@@ -253,8 +253,9 @@ def parse_precision(p):
 
 
 def to_cav_config(cfg, num_envs, num_agents=None, precision="f64", store_history=None, history_len=0,
-                  track_aux=False):
-    """Flatten a reference-style Config object into ``cav_config_t``."""
+                  track_aux=False, obs_f32=False):
+    """Flatten a reference-style Config object into ``cav_config_t``.  ``obs_f32``: float64 state with float32
+    observation / reward columns (the reference's declared observation dtype)."""
     c = abi.CavConfig()
     c.struct_size = ctypes.sizeof(abi.CavConfig)
     c.precision = parse_precision(precision)
@@ -304,4 +305,5 @@ def to_cav_config(cfg, num_envs, num_agents=None, precision="f64", store_history
     c.store_history = int(sh and history_len > 0)
     c.history_len = int(history_len)
     c.track_aux = int(bool(track_aux))
+    c.obs_f32 = int(bool(obs_f32) and c.precision == abi.CAV_F64)
     return c

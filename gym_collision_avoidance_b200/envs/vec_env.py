@@ -48,7 +48,7 @@ class VecCollisionAvoidanceEnv(object):
     def __init__(self, num_envs, config=None, num_agents=None, device="cuda:0", precision="f64", scenario_bank=None,
                  bank_kinds=None, bank_num_active=None, policies="RVO", dynamics="unicycle", auto_reset=True,
                  use_cuda_graph=True, history_len=0, track_aux=False, seed=0, num_scenarios=None,
-                 scenario_source="host"):
+                 scenario_source="host", obs_f32=False, host_lookahead=None):
         if config is None:
             config = _config.make_config(num_agents or 10, evaluate=True)
         self.config = config
@@ -56,8 +56,11 @@ class VecCollisionAvoidanceEnv(object):
         self.num_agents = int(num_agents if num_agents is not None else config.MAX_NUM_AGENTS_IN_ENVIRONMENT)
         self.device = torch.device(device)
         self.auto_reset = bool(auto_reset)
+        # obs_f32: float64 state with float32 `obs` / `reward` columns written by the kernels themselves (the dtype the
+        # reference declares for its observation space, config.py:93-170): half the HBM and PCIe bytes of the
+        # observation, no cast pass in the host-buffer API
         self.c = _config.to_cav_config(config, self.num_envs, self.num_agents, precision=precision,
-                                       history_len=history_len, track_aux=track_aux)
+                                       history_len=history_len, track_aux=track_aux, obs_f32=obs_f32)
         self.obs_offsets, self.obs_len = _config.obs_layout(config)
         if scenario_source not in ("host", "device"):
             raise ValueError("scenario_source must be 'host' or 'device'")
@@ -88,18 +91,40 @@ class VecCollisionAvoidanceEnv(object):
         self.state = st
         self.ext_actions = torch.zeros((self.num_envs, self.num_agents, 2), dtype=torch.float32, device=self.device)
         self.agent_dones = torch.zeros_like(st.done)  # which_agents_done of the step (kept across auto-reset)
-        # pinned host mirrors for the host-buffer API
+        kinds_np = np.asarray(bank_kinds, dtype=np.uint32) & 0xff
+        self.has_external_agents = bool(np.isin(kinds_np, [abi.CAV_POLICY_EXTERNAL, abi.CAV_POLICY_LEARNING]).any())
+        # ---- host-buffer API (step_host): pinned mirrors, a copy stream, optional one-step lookahead ----
+        # The host API hands observations / rewards out as float32.  With float32 columns (precision f32 or obs_f32) the
+        # download reads the state columns directly; with float64 columns a cast pass into float32 mirrors runs first.
+        self._obs_is_f32 = st.obs.dtype == torch.float32
+        # lookahead: with no external / learning agent the caller's actions are never read, so the next step can be
+        # launched BEFORE the current results are waited for; its kernels then run under the current step's download
+        # (46 MB at 16384 x 10: ~0.87 ms over PCIe 5 x16 against ~0.1 ms of kernels).  Results are snapshotted on the
+        # device into two alternating staging sets, so the running step never overwrites what is being downloaded.
+        self.host_lookahead = (not self.has_external_agents) if host_lookahead is None else bool(host_lookahead)
+        if self.host_lookahead and self.has_external_agents:
+            raise abi.CavoidError("host_lookahead needs an environment without external / learning agents")
+        nslot = 2 if self.host_lookahead else 1
         self._h_actions = torch.zeros((self.num_envs, self.num_agents, 2), dtype=torch.float32).pin_memory()
         self._h_actions_np = self._h_actions.numpy()
-        # the host API hands observations / rewards out as float32, the dtype the reference's observation space
-        # declares (Config.STATE_INFO_DICT[...]['dtype'] = np.float32, config.py:93-170); device tensors keep `real`
-        self._d_obs32 = st.obs if st.obs.dtype == torch.float32 else torch.zeros_like(st.obs, dtype=torch.float32)
-        self._d_rew32 = (st.reward if st.reward.dtype == torch.float32
-                         else torch.zeros_like(st.reward, dtype=torch.float32))
-        self._h_obs = torch.zeros(tuple(st.obs.shape), dtype=torch.float32).pin_memory()
-        self._h_reward = torch.zeros(tuple(st.reward.shape), dtype=torch.float32).pin_memory()
-        self._h_game_over = torch.zeros(tuple(st.game_over.shape), dtype=torch.uint8).pin_memory()
-        self._h_agent_dones = torch.zeros(tuple(st.done.shape), dtype=torch.uint8).pin_memory()
+        f32 = torch.float32
+        self._d_stage = []
+        self._h_out = []
+        for k in range(nslot):
+            need_stage = self.host_lookahead or not self._obs_is_f32
+            self._d_stage.append(None if not need_stage else (
+                torch.zeros(tuple(st.obs.shape), dtype=f32, device=self.device),
+                torch.zeros(tuple(st.reward.shape), dtype=f32, device=self.device),
+                torch.zeros_like(st.game_over), torch.zeros_like(st.done)))
+            self._h_out.append((torch.zeros(tuple(st.obs.shape), dtype=f32).pin_memory(),
+                                torch.zeros(tuple(st.reward.shape), dtype=f32).pin_memory(),
+                                torch.zeros(tuple(st.game_over.shape), dtype=torch.uint8).pin_memory(),
+                                torch.zeros(tuple(st.done.shape), dtype=torch.uint8).pin_memory()))
+        self._h_obs, self._h_reward, self._h_game_over, self._h_agent_dones = self._h_out[0]
+        self._copy_stream = torch.cuda.Stream(device=self.device)
+        self._ev_ready = [torch.cuda.Event() for _ in range(nslot)]   # results of a slot are on the device
+        self._ev_home = [torch.cuda.Event() for _ in range(nslot)]    # ... and in pinned host memory
+        self._ahead = None  # slot of a step that has been launched but not yet handed to the caller
         self._graph = None
         self._warm = False
         self._use_graph = bool(use_cuda_graph)
@@ -125,6 +150,7 @@ class VecCollisionAvoidanceEnv(object):
         st.episode.zero_()
         st.stats.zero_()
         st.game_over.zero_()
+        self._ahead = None
         self.cav.reset(self.bank)
         self.agent_dones.zero_()
         return st.obs, {}
@@ -170,14 +196,47 @@ class VecCollisionAvoidanceEnv(object):
             if isinstance(actions, np.ndarray):
                 actions = torch.from_numpy(np.ascontiguousarray(actions, dtype=np.float32))
             self.ext_actions.copy_(actions.reshape(self.ext_actions.shape), non_blocking=True)
-        self._launch()
-        self.steps += 1
+        if self._ahead is not None:
+            self._ahead = None  # step_host already ran this step (lookahead): its results are in the state columns
+        else:
+            self._launch()
+            self.steps += 1
         st = self.state
         return st.obs, st.reward, st.game_over, {"which_agents_done": self.agent_dones}
 
+    def _launch_to_host(self, slot):
+        """Enqueue one step and the download of its results into pinned slot `slot` (nothing waits here)."""
+        self._launch()
+        self.steps += 1
+        st = self.state
+        main = torch.cuda.current_stream(self.device)
+        stage = self._d_stage[slot]
+        if stage is not None:  # device-side snapshot (and float64 -> float32 cast when the columns are float64)
+            stage[0].copy_(st.obs)
+            stage[1].copy_(st.reward)
+            stage[2].copy_(st.game_over)
+            stage[3].copy_(self.agent_dones)
+            src = stage
+        else:
+            src = (st.obs, st.reward, st.game_over, self.agent_dones)
+        self._ev_ready[slot].record(main)
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._ev_ready[slot])
+            for h, d in zip(self._h_out[slot], src):
+                h.copy_(d, non_blocking=True)
+            self._ev_home[slot].record(self._copy_stream)
+        if stage is None:
+            main.wait_event(self._ev_home[slot])  # the next step must not overwrite columns that are still being read
+
     def step_host(self, actions=None):
-        """Host-buffer API: pinned-host actions in, pinned-host ``(obs, rewards, game_over, which_agents_done)``
-        out (float32 obs / rewards; host<->device copies on the current stream, then one synchronize)."""
+        """Host-buffer API: pinned-host actions in, pinned-host ``(obs, rewards, game_over, which_agents_done)`` out
+        (float32 obs / rewards), one call per step.  The returned tensors are owned by the env and are overwritten two
+        calls later (lookahead) / by the next call.
+
+        With ``host_lookahead`` (default when no agent has an external or learning policy -- ``actions`` are then never
+        read) the NEXT step is launched before this one's results are waited for, so its kernels run under this
+        step's device->host copy; the device state is then one step ahead of what has been returned (``step()``
+        returns that step without running another one; ``reset()`` discards it)."""
         if actions is not None:
             # plain single-threaded memcpy into the pinned staging buffer: torch's CPU copy_ fans a 1.3 MB copy out
             # over the intra-op thread pool, whose spinning workers then starve the CUDA graph launch (measured on
@@ -186,18 +245,19 @@ class VecCollisionAvoidanceEnv(object):
                 actions = actions.detach().cpu().numpy()
             np.copyto(self._h_actions_np, np.asarray(actions, dtype=np.float32).reshape(self._h_actions_np.shape))
             self.ext_actions.copy_(self._h_actions, non_blocking=True)
-        self._launch()
-        self.steps += 1
-        st = self.state
-        if self._d_obs32 is not st.obs:
-            self._d_obs32.copy_(st.obs)
-            self._d_rew32.copy_(st.reward)
-        self._h_obs.copy_(self._d_obs32, non_blocking=True)
-        self._h_reward.copy_(self._d_rew32, non_blocking=True)
-        self._h_game_over.copy_(st.game_over, non_blocking=True)
-        self._h_agent_dones.copy_(self.agent_dones, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
-        return self._h_obs, self._h_reward, self._h_game_over, self._h_agent_dones
+        if not self.host_lookahead:
+            self._launch_to_host(0)
+            self._ev_home[0].synchronize()
+            return self._h_out[0]
+        if self._ahead is None:  # first call after reset() / step(): run the step this call is about
+            self._launch_to_host(0)
+            self._ahead = 0
+        cur = self._ahead
+        self._launch_to_host(cur ^ 1)  # the step the NEXT call will return
+        self._ahead = cur ^ 1
+        self._ev_home[cur].synchronize()
+        self._h_obs, self._h_reward, self._h_game_over, self._h_agent_dones = self._h_out[cur]
+        return self._h_out[cur]
 
     @property
     def h2d_bytes_per_step(self):
@@ -205,8 +265,8 @@ class VecCollisionAvoidanceEnv(object):
 
     @property
     def d2h_bytes_per_step(self):
-        return (self._h_obs.numel() * self._h_obs.element_size() + self._h_reward.numel() * self._h_reward.element_size()
-                + self._h_game_over.numel() + self._h_agent_dones.numel())
+        h = self._h_out[0]
+        return sum(t.numel() * t.element_size() for t in h)
 
     # ------------------------------------------------------------------------------------------------------
     def episode_stats(self):

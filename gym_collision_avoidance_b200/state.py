@@ -12,16 +12,18 @@ from . import abi
 
 
 def column_specs(c):
-    """name -> (shape, kind) for a cav_config_t ``c``; kind in {'real','f32','u32','i32','u8','u64'}."""
+    """name -> (shape, kind) for a cav_config_t ``c``; kind in {'real','f32','u32','i32','u8','u64'}.  With ``c.obs_f32``
+    (float64 state, float32 observation) the ``obs`` and ``reward`` columns are float32."""
     E, N = c.num_envs, c.num_agents
+    ok = "f32" if (c.obs_f32 and c.precision == abi.CAV_F64) else "real"
     specs = {
         "pv": ((E, N, 4), "real"), "goal": ((E, N, 4), "real"), "ht": ((E, N, 4), "real"),
         "ego": ((E, N, 4), "real"),
         "flags": ((E, N), "u32"), "kinds": ((E, N), "u32"), "step_num": ((E, N), "i32"),
         "num_active": ((E,), "i32"),
-        "actions": ((E, N, 2), "f32"), "reward": ((E, N), "real"), "min_dist": ((E, N), "real"),
+        "actions": ((E, N, 2), "f32"), "reward": ((E, N), ok), "min_dist": ((E, N), "real"),
         "done": ((E, N), "u8"), "game_over": ((E,), "u8"),
-        "obs": ((E, N, c.obs_len), "real"),
+        "obs": ((E, N, c.obs_len), ok),
         "episode": ((E,), "i32"), "stats": ((abi.CAV_STAT_NUM,), "u64"),
     }
     if N > abi.CAV_KD_MAX_LEAF:  # RVO2's persistent kd-tree agent permutation (cavoid.h: kd_order)

@@ -182,7 +182,9 @@ typedef struct cav_config {
     int32_t store_history; /* Config.STORE_HISTORY: write one CAV_HISTORY_ROW row per live agent-step */
     int32_t history_len;   /* T: rows per agent in `history` (rows >= T are dropped) */
     int32_t track_aux;     /* keep speed / delta_heading / vel_ego / past_actions / past_global_velocities */
-    int32_t reserved0;
+    int32_t obs_f32;       /* precision == CAV_F64 only: `obs` and `reward` are float32 columns -- the dtype the reference
+                            * DECLARES for its observation space (np.float32, envs/config.py:93-170) -- written directly by
+                            * the kernels from the float64 state (half the bytes to HBM and to the host); 0 = `real` */
 } cav_config_t;
 
 /* Device buffers (all borrowed).  "real4" = 4 consecutive reals, 16-byte aligned. */
@@ -196,11 +198,12 @@ typedef struct cav_buffers {
     int32_t *step_num;   /* [E*N] Agent.step_num */
     int32_t *num_active; /* [E] number of agents present in env e (<= N), or NULL = N everywhere */
     float *actions;      /* [E*N*2] float32 actions chosen this step (env.py:305-307 all_actions) */
-    void *reward;        /* real [E*N] (env.py:394-456) */
+    void *reward;        /* real [E*N] (env.py:394-456); float32 when cfg.obs_f32 */
     void *min_dist;      /* real [E*N] dist_btwn_nearest_agent (env.py:482-487); may be NULL */
     uint8_t *done;       /* [E*N] which_agents_done (env.py:529-536) */
     uint8_t *game_over;  /* [E] (env.py:538-551) */
-    void *obs;           /* real [E*N*obs_len] packed observation, STATES_IN_OBS order; 16-byte aligned */
+    void *obs;           /* real [E*N*obs_len] packed observation, STATES_IN_OBS order; 16-byte aligned; float32 when
+                          * cfg.obs_f32 */
     uint32_t *laser_count;          /* [E*N] LaserScanSensor.num_measurements_made; NULL when no laserscan */
     const uint32_t *static_map_bits; /* [rows * ceil(cols/32)] row-major bitmap of Map.static_map, or NULL (empty) */
     void *history;       /* real [E*N*T*CAV_HISTORY_ROW] or NULL (agent.py:257-260,275-289) */

@@ -467,13 +467,66 @@ void cavo_set_faithful_dostep(int on) { g_faithful_dostep = on; }
 
 #define DISPATCH(fn, ...) (cfg->precision == CAV_F64 ? fn##_f64(__VA_ARGS__) : fn##_f32(__VA_ARGS__))
 
+/* cfg.obs_f32 (float64 state, float32 `obs` / `reward` columns): the restatement computes in REAL; the float32 columns
+ * are widened into scratch doubles before a phase and rounded back after it.  Values that merely persist (laserscan
+ * history rows, rows of absent agents) survive the round trip unchanged: float(double(float x)) == float x. */
+typedef struct {
+    cav_config_t cfg;
+    cav_buffers_t b;
+    double *obs, *rew;
+    float *fobs, *frew;
+    size_t no, nr;
+} widen_t;
+static void widen_begin(const cav_config_t **cfg, const cav_buffers_t **b, widen_t *w) {
+    w->obs = NULL;
+    if (!((*cfg)->obs_f32 && (*cfg)->precision == CAV_F64)) return;
+    w->cfg = **cfg;
+    w->cfg.obs_f32 = 0;
+    w->b = **b;
+    w->no = (size_t)w->cfg.num_envs * w->cfg.num_agents * w->cfg.obs_len;
+    w->nr = (size_t)w->cfg.num_envs * w->cfg.num_agents;
+    w->fobs = (float *)w->b.obs;
+    w->frew = (float *)w->b.reward;
+    w->obs = (double *)malloc(sizeof(double) * w->no);
+    w->rew = (double *)malloc(sizeof(double) * w->nr);
+    for (size_t i = 0; i < w->no; ++i) w->obs[i] = (double)w->fobs[i];
+    for (size_t i = 0; i < w->nr; ++i) w->rew[i] = (double)w->frew[i];
+    w->b.obs = w->obs;
+    w->b.reward = w->rew;
+    *cfg = &w->cfg;
+    *b = &w->b;
+}
+static void widen_end(widen_t *w) {
+    if (!w->obs) return;
+    for (size_t i = 0; i < w->no; ++i) w->fobs[i] = (float)w->obs[i];
+    for (size_t i = 0; i < w->nr; ++i) w->frew[i] = (float)w->rew[i];
+    free(w->obs);
+    free(w->rew);
+}
+
 int cavo_policy(const cav_config_t *cfg, const cav_buffers_t *b, const float *ext) { return DISPATCH(policy, cfg, b, ext); }
 int cavo_dynamics(const cav_config_t *cfg, const cav_buffers_t *b, double dt) { return DISPATCH(dynamics, cfg, b, dt); }
-int cavo_pairwise_obs(const cav_config_t *cfg, const cav_buffers_t *b) { return DISPATCH(pairwise_obs, cfg, b); }
-int cavo_laserscan(const cav_config_t *cfg, const cav_buffers_t *b) { return DISPATCH(laserscan, cfg, b); }
+int cavo_pairwise_obs(const cav_config_t *cfg, const cav_buffers_t *b) {
+    widen_t w;
+    widen_begin(&cfg, &b, &w);
+    const int rc = DISPATCH(pairwise_obs, cfg, b);
+    widen_end(&w);
+    return rc;
+}
+int cavo_laserscan(const cav_config_t *cfg, const cav_buffers_t *b) {
+    widen_t w;
+    widen_begin(&cfg, &b, &w);
+    const int rc = DISPATCH(laserscan, cfg, b);
+    widen_end(&w);
+    return rc;
+}
 int cavo_reset(const cav_config_t *cfg, const cav_buffers_t *b, const uint8_t *mask, const cav_scenario_bank_t *bank,
                const int32_t *scenario_idx, int accumulate_stats) {
-    return DISPATCH(reset, cfg, b, mask, bank, scenario_idx, accumulate_stats);
+    widen_t w;
+    widen_begin(&cfg, &b, &w);
+    const int rc = DISPATCH(reset, cfg, b, mask, bank, scenario_idx, accumulate_stats);
+    widen_end(&w);
+    return rc;
 }
 /* CollisionAvoidanceEnv.step, collision_avoidance_env.py:156-234 */
 int cavo_step(const cav_config_t *cfg, const cav_buffers_t *b, const float *ext, double dt) {

@@ -47,9 +47,9 @@ class Golden(object):
         cfg.EVALUATE_MODE = evaluate
         return cfg
 
-    def cav_config(self, num_envs, precision="f64", track_aux=True, history_len=0):
+    def cav_config(self, num_envs, precision="f64", track_aux=True, history_len=0, obs_f32=False):
         return to_cav_config(self.py_config(), num_envs, self.N, precision=precision, track_aux=track_aux,
-                             history_len=history_len, store_history=history_len > 0)
+                             history_len=history_len, store_history=history_len > 0, obs_f32=obs_f32)
 
     def static_map_bits(self):
         """uint32 bitmap of the fixture's static map (None when the fixture has none)."""

@@ -99,6 +99,33 @@ def test_step_vs_oracle_same_state(name, prec, tol, mapping):
     common.compare_states(got, want, g.n, tol, tol)
 
 
+@pytest.mark.parametrize("name", ["rvo10_c0", "rvo4_c7", "rvo3_in8slots", "mixed5_train", "dense6_clip3_last", "tti8_clip4",
+                                  "horizon8", "laser6", "walls6", "rvo20_rand", "circle12_r6", "single_agent_train"])
+def test_f64_state_with_f32_observation_columns(name, mapping):
+    """cfg.obs_f32: float64 state, `obs` and `reward` written as float32 by the kernels (the reference's DECLARED
+    observation dtype, config.py:93-170).  State / flags as in the float64 tests; the float32 columns equal the float64
+    values of the reference rounded to float32, up to one float32 ulp where CUDA's and glibc's float64 libm differ in the
+    last bit (tolerance 2e-7 relative + 1e-7 absolute, far inside north_star's 1e-5); laser beams exact."""
+    from gpu_common import GpuRunner
+    g = common.Golden(name)
+    c = g.cav_config(g.T, "f64", track_aux=True, obs_f32=True)
+    st = _inject_all(g, c)
+    assert st.obs.dtype == np.float32 and st.reward.dtype == np.float32 and st.pv.dtype == np.float64
+    ext = np.ascontiguousarray(g.z["ext_actions"][:g.T], dtype=np.float32)
+    want = st.copy()
+    Oracle(c).step(want, ext)
+    out = GpuRunner(c).step(st, ext)
+    assert out.obs.dtype == np.float32
+    tol = 1e-9 if name in SYMMETRIC else 1e-12
+    common.compare_states(out, want, g.n, tol, tol, cols=[k for k in want.arrays if k not in (
+        "obs", "reward", "stats", "episode", "kinds", "num_active")])
+    f32 = common.Tol(2e-7, 1e-7)
+    common.compare_obs(g, out.obs, want.obs, f32)
+    common.assert_close("reward", out.reward[:, :g.n], want.reward[:, :g.n], 2e-7, 1e-7)
+    # and against the reference's golden float64 observation
+    common.compare_obs(g, out.obs, g.z["obs"][1:g.T + 1], f32)
+
+
 @pytest.mark.parametrize("name", ["rvo10_c0", "mixed5_train", "dense6_clip3_last"])
 def test_phase_entry_points_vs_oracle(name, mapping):
     """cav_k_policy / cav_k_dynamics / cav_k_pairwise_obs each equal the oracle's phase on the same state."""

@@ -130,3 +130,73 @@ def test_trajectories_match_the_oracle_history_in_reference_format():
             assert g[0, 0] == 0.0 and np.allclose(g[:, 3:5], rows[e, i, 2:4])  # rows start at t = 0; goal columns
             assert np.allclose(np.diff(g[:, 0]), 0.1)                                              # t advances by dt
     env.close()
+
+
+@pytest.mark.parametrize("prec,obs_f32", [("f64", True), ("f64", False), ("f32", False)])
+def test_step_host_lookahead_returns_the_same_steps(prec, obs_f32):
+    """step_host with one-step lookahead (the next step's kernels run under this step's download) hands out exactly the
+    arrays the plain wait-every-step path does, step for step; step() after step_host returns the step that is already
+    in flight instead of running another one; reset() discards it."""
+    N, E = 10, 256
+    rows = random_scenario_bank(64, N, seed=11)
+    cfg = make_config(N, evaluate=True)
+    mk = lambda la: VecCollisionAvoidanceEnv(E, cfg, N, precision=prec, scenario_bank=rows, policies="RVO",  # noqa: E731
+                                             obs_f32=obs_f32, host_lookahead=la)
+    plain, ahead = mk(False), mk(True)
+    assert plain.state.obs.dtype == (torch.float32 if (obs_f32 or prec == "f32") else torch.float64)
+    for e in (plain, ahead):
+        e.reset()
+    act = np.zeros((E, N, 2), np.float32)
+    for s in range(25):
+        a = [t.numpy().copy() for t in plain.step_host(act)]
+        b = [t.numpy().copy() for t in ahead.step_host(act)]
+        for k, (x, y) in enumerate(zip(a, b)):
+            assert x.dtype == y.dtype and np.array_equal(x, y), (s, k)
+        assert a[0].dtype == np.float32 and a[0].shape == (E, N, 69)
+    assert ahead.steps == plain.steps + 1 and ahead._ahead is not None
+    o1 = plain.step()
+    o2 = ahead.step()  # already computed
+    assert ahead.steps == plain.steps and ahead._ahead is None
+    torch.cuda.synchronize()
+    assert torch.equal(o1[0], o2[0]) and torch.equal(o1[2], o2[2])
+    for e in (plain, ahead):
+        e.reset()
+    a = plain.step_host(act)[0].numpy().copy()
+    b = ahead.step_host(act)[0].numpy().copy()
+    assert np.array_equal(a, b)
+    with pytest.raises(abi.CavoidError):
+        VecCollisionAvoidanceEnv(E, cfg, N, scenario_bank=rows, policies=["learning"] + ["RVO"] * (N - 1),
+                                 host_lookahead=True)
+    for e in (plain, ahead):
+        e.close()
+
+
+def test_dummy_vec_env_drop_in():
+    """DummyVecEnv([make_env] * E) (reference vec_env.py:86-159): reset / step_async / step_wait over one batched
+    environment, observations packed like MultiagentDictToMultiagentArrayWrapper, auto-reset on done."""
+    from gym_collision_avoidance_b200 import envs as envs_pkg
+    from gym_collision_avoidance_b200.envs.vec_env import DummyVecEnv
+    from gym_collision_avoidance_b200.envs.wrappers import MultiagentDictToMultiagentArrayWrapper
+    from gym_collision_avoidance_b200.envs.collision_avoidance_env import CollisionAvoidanceEnv
+    old = envs_pkg.Config
+    cfg = envs_pkg.set_config(make_config(4, evaluate=True))
+    try:
+        def make_env():
+            env = CollisionAvoidanceEnv()
+            return MultiagentDictToMultiagentArrayWrapper(env, dict_keys=cfg.STATES_IN_OBS, max_num_agents=4)
+        venv = DummyVecEnv([make_env] * 32, policies="RVO", seed=5)
+        obs = venv.reset()
+        assert obs.shape == (32, 4, 6 + 7 * 3) and obs.dtype == np.float32
+        assert np.all(obs[:, :, 4] > 0)  # pref_speed of every agent
+        n_done = 0
+        for s in range(150):
+            obs, rews, dones, infos = venv.step(None)
+            assert rews.shape == (32, 4) and dones.shape == (32,) and dones.dtype == bool and len(infos) == 32
+            n_done += int(dones.sum())
+            if dones.any():
+                e = int(np.argmax(dones))
+                assert np.all(obs[e, :, 1] == 3)  # fresh episode: every agent observes its three neighbours again
+        assert n_done > 0
+        venv.close()
+    finally:
+        envs_pkg.set_config(old)
