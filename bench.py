@@ -330,7 +330,7 @@ def python_reference_rate(a):
     tools/measure_python_reference.py writes profiles/python_reference_baseline.json), or None."""
     try:
         d = json.load(open(os.path.join(ROOT, "profiles", "python_reference_baseline.json")))
-        return d.get("%dagents_%s" % (a.agents, a.policy))
+        return d.get("%dagents_%s%s" % (a.agents, a.policy, "_laser" if a.laser else ""))
     except Exception:
         return None
 

@@ -31,6 +31,7 @@ CAV_FLAG_RAN_OUT_OF_TIME = 0x10
 CAV_FLAG_DONE = 0x20
 CAV_FLAG_COLLIDED_AGENT = 0x40
 CAV_FLAG_COLLIDED_WALL = 0x80
+CAV_FLAG_RVO_NON_COOP = 0x100
 
 CAV_SORT_CLOSEST_FIRST, CAV_SORT_CLOSEST_LAST, CAV_SORT_TIME_TO_IMPACT = range(3)
 CAV_GAME_OVER_ALL_DONE, CAV_GAME_OVER_AGENT0, CAV_GAME_OVER_LEARNING_AGENTS = range(3)
@@ -81,6 +82,7 @@ class CavConfig(ctypes.Structure):
         ("map_x_width", _d), ("map_y_width", _d), ("map_grid_cell_size", _d),
         ("obs_len", _i), ("obs_offset", _i * CAV_OBS_NUM_STATES),
         ("store_history", _i), ("history_len", _i), ("track_aux", _i), ("obs_f32", _i),
+        ("rvo_anti_collab_t", _d), ("rvo_seed", ctypes.c_uint64),
     ]
 
 

@@ -88,6 +88,9 @@ static void fill_params(const cav_config_t &c, KParams<T> &p) {
     p.rvo_radius_scale = (T)c.rvo_radius_scale;
     p.rvo_inv_dt = (T)1 / (T)c.dt;  // 1/self.dt, RVOPolicy.py:105
     p.rvo_max_neighbors = c.rvo_max_neighbors;
+    p.rvo_anti_collab_t = (T)c.rvo_anti_collab_t;
+    p.rvo_anti_p = (float)fabs(c.rvo_collab_coeff);
+    p.rvo_seed = c.rvo_seed;
     p.store_history = c.store_history;
     p.history_len = c.history_len;
     p.obs_len = c.obs_len;
@@ -164,8 +167,8 @@ int cav_create(const cav_config_t *cfg, cav_handle_t *out) {
         return fail(nullptr, CAV_ERR_BAD_CONFIG, "cav_create: unknown agent_sorting_method %d", cfg->agent_sorting_method);
     if (cfg->game_over_mode < 0 || cfg->game_over_mode > 2)
         return fail(nullptr, CAV_ERR_BAD_CONFIG, "cav_create: bad game_over_mode");
-    if (cfg->rvo_collab_coeff < 0.0)
-        return fail(nullptr, CAV_ERR_UNSUPPORTED, "cav_create: anti-collaborative RVO (collab coeff < 0) is not built");
+    if (cfg->rvo_collab_coeff < 0.0 && !(cfg->rvo_anti_collab_t > 0.0))
+        return fail(nullptr, CAV_ERR_BAD_CONFIG, "cav_create: anti-collaborative RVO needs rvo_anti_collab_t > 0");
     if (cfg->store_history && cfg->history_len < 1)
         return fail(nullptr, CAV_ERR_BAD_CONFIG, "cav_create: store_history needs history_len >= 1");
     cav_handle_s *h = new (std::nothrow) cav_handle_s;

@@ -56,6 +56,25 @@ CAV_HDI unsigned float_bits(float f) {
 #endif
 }
 
+// One uniform [0, 1) draw from Philox4x32-10 (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3", SC'11; the
+// Random123 constants) with counter (c0, c1, c2, c3) and the 64-bit key `seed`: first output word / 2^32.  Used for the
+// anti-collaborative RVO agents' policy re-draw (RVOPolicy.py:77-88); oracle/cav_oracle.c carries the same function in C.
+CAV_HDI double philox_u01(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1;
+        c3 = (uint32_t)p0;
+        c0 = n0;
+        c2 = n2;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return (double)c0 * (1.0 / 4294967296.0);
+}
+
 // Map.world_coordinates_to_map_indices (Map.py:28-29,36-37): floor(origin -/+ v/cell).  v*inv_cell replaces the division
 // unless the result is within 1e-9 of an integer, where the exact quotient decides -- so the cell is the reference's
 // for EVERY input (tests/test_geometry_native_cpu.py: random and adversarial values against NumPy's expression).

@@ -184,6 +184,9 @@ struct KParams {
     float rvo_time_step, rvo_collab, rvo_neighbor_dist;
     T rvo_max_delta_heading, rvo_radius_scale, rvo_inv_dt;  // 1/self.dt (RVOPolicy.py:105)
     int rvo_max_neighbors;
+    T rvo_anti_collab_t;      // Config.RVO_ANTI_COLLAB_T (anti-collaborative RVO only)
+    float rvo_anti_p;         // |rvo_collab| when negative: probability of the adversarial choice
+    unsigned long long rvo_seed;
     int store_history, history_len;
     int obs_len;
 };

@@ -15,6 +15,7 @@ struct TpaBuffers {
     uint8_t *done, *game_over;
     void *obs;
     void *history, *aux0, *past_actions, *past_vel;
+    const int32_t *episode;
 };
 
 // Agent.take_action for one agent by one thread (agent.py:192-241: UnicycleDynamics.py:27-47 / MaxTurnRate :30-43 /

@@ -264,7 +264,7 @@ __device__ __forceinline__ void orca_group(unsigned gm, int glane, int n, int eg
         const int e = s * G + glane;
         const int o = (e < ego) ? e : e + 1;
         key[s] = ~0ull;
-        if (e < n - 1 && maxNeighbors > 0 && collab > 0.0f) {
+        if (e < n - 1 && maxNeighbors > 0 && collab != 0.0f) {
             const float4 ot = s_f4[o];
             const float dx = me.x - ot.x, dy = me.y - ot.y;  // absSq(position_ - agent->position_), Agent.cpp:427
             const float distSq = fdot(dx, dy, dx, dy);
@@ -277,63 +277,101 @@ __device__ __forceinline__ void orca_group(unsigned gm, int glane, int n, int eg
     bool valid[SL];
     int nl = 0;
     const float invTimeHorizon = 1.0f / timeHorizon;
+    if (collab < 0.0f) {
+        // Anti-collaborative (Agent.cpp:368-415): the two legs of the CLOSEST neighbour's velocity obstacle facing inward
+        // (ranks 0 and 1; needs G * SL >= 2, see pick_shape), preferred velocity v_other + (-collab) * normalize(relPos).
+        const unsigned long long k0 = gshfl<G>(gm, key[0], 0);  // rank 0 = the closest neighbour
 #pragma unroll
-    for (int s = 0; s < SL; ++s) {
-        const int rank = s * G + glane;
-        valid[s] = (key[s] != ~0ull) && rank < maxNeighbors;
-        ln[s] = Line{0.f, 0.f, 1.f, 0.f};
-        if (valid[s]) {
-            const int o = (int)(key[s] & 0xffull);
+        for (int s = 0; s < SL; ++s) {
+            valid[s] = false;
+            ln[s] = Line{0.f, 0.f, 1.f, 0.f};
+        }
+        if (k0 != ~0ull && maxNeighbors > 0) {
+            const int o = (int)(k0 & 0xffull);
             const float4 ot = s_f4[o];
             const float rpx = ot.x - me.x, rpy = ot.y - me.y;
-            const float rvx = me.z - ot.z, rvy = me.w - ot.w;
             const float distSq = fdot(rpx, rpy, rpx, rpy);
             const float combinedRadius = rad_me + s_frad[o];
             const float combinedRadiusSq = combinedRadius * combinedRadius;
-            float ux, uy;
-            if (distSq > combinedRadiusSq) {
-                const float wx = rvx - invTimeHorizon * rpx, wy = rvy - invTimeHorizon * rpy;
-                const float wLengthSq = fdot(wx, wy, wx, wy);
-                const float dotProduct1 = fdot(wx, wy, rpx, rpy);
-                if (dotProduct1 < 0.0f && dotProduct1 * dotProduct1 > combinedRadiusSq * wLengthSq) {
-                    const float wLength = sqrtf(wLengthSq);
+            const float leg = sqrtf(distSq - combinedRadiusSq);
+            const float inv = 1.0f / distSq;
+            if (glane < 2) {  // rank = glane (slot 0)
+                valid[0] = true;
+                ln[0].px = ot.z + rpx;
+                ln[0].py = ot.w + rpy;
+                if (glane == 0) {
+                    ln[0].dx = (-(rpx * leg - rpy * combinedRadius)) * inv;
+                    ln[0].dy = (-(rpx * combinedRadius + rpy * leg)) * inv;
+                } else {
+                    ln[0].dx = (rpx * leg + rpy * combinedRadius) * inv;
+                    ln[0].dy = (-rpx * combinedRadius + rpy * leg) * inv;
+                }
+            }
+            nl = 2;
+            const float invn = 1.0f / sqrtf(distSq);
+            const float sc = -collab;
+            prefx = ot.z + sc * (rpx * invn);
+            prefy = ot.w + sc * (rpy * invn);
+        }
+    } else {
+    #pragma unroll
+        for (int s = 0; s < SL; ++s) {
+            const int rank = s * G + glane;
+            valid[s] = (key[s] != ~0ull) && rank < maxNeighbors;
+            ln[s] = Line{0.f, 0.f, 1.f, 0.f};
+            if (valid[s]) {
+                const int o = (int)(key[s] & 0xffull);
+                const float4 ot = s_f4[o];
+                const float rpx = ot.x - me.x, rpy = ot.y - me.y;
+                const float rvx = me.z - ot.z, rvy = me.w - ot.w;
+                const float distSq = fdot(rpx, rpy, rpx, rpy);
+                const float combinedRadius = rad_me + s_frad[o];
+                const float combinedRadiusSq = combinedRadius * combinedRadius;
+                float ux, uy;
+                if (distSq > combinedRadiusSq) {
+                    const float wx = rvx - invTimeHorizon * rpx, wy = rvy - invTimeHorizon * rpy;
+                    const float wLengthSq = fdot(wx, wy, wx, wy);
+                    const float dotProduct1 = fdot(wx, wy, rpx, rpy);
+                    if (dotProduct1 < 0.0f && dotProduct1 * dotProduct1 > combinedRadiusSq * wLengthSq) {
+                        const float wLength = sqrtf(wLengthSq);
+                        const float inv = 1.0f / wLength;
+                        const float uwx = wx * inv, uwy = wy * inv;
+                        ln[s].dx = uwy;
+                        ln[s].dy = -uwx;
+                        const float sc = combinedRadius * invTimeHorizon - wLength;
+                        ux = sc * uwx;
+                        uy = sc * uwy;
+                    } else {
+                        const float leg = sqrtf(distSq - combinedRadiusSq);
+                        const float inv = 1.0f / distSq;
+                        if (fdet(rpx, rpy, wx, wy) > 0.0f) {
+                            ln[s].dx = (rpx * leg - rpy * combinedRadius) * inv;
+                            ln[s].dy = (rpx * combinedRadius + rpy * leg) * inv;
+                        } else {
+                            ln[s].dx = (-(rpx * leg + rpy * combinedRadius)) * inv;
+                            ln[s].dy = (-(-rpx * combinedRadius + rpy * leg)) * inv;
+                        }
+                        const float dotProduct2 = fdot(rvx, rvy, ln[s].dx, ln[s].dy);
+                        ux = dotProduct2 * ln[s].dx - rvx;
+                        uy = dotProduct2 * ln[s].dy - rvy;
+                    }
+                } else {
+                    const float invTimeStep = 1.0f / timeStep;
+                    const float wx = rvx - invTimeStep * rpx, wy = rvy - invTimeStep * rpy;
+                    const float wLength = sqrtf(fdot(wx, wy, wx, wy));
                     const float inv = 1.0f / wLength;
                     const float uwx = wx * inv, uwy = wy * inv;
                     ln[s].dx = uwy;
                     ln[s].dy = -uwx;
-                    const float sc = combinedRadius * invTimeHorizon - wLength;
+                    const float sc = combinedRadius * invTimeStep - wLength;
                     ux = sc * uwx;
                     uy = sc * uwy;
-                } else {
-                    const float leg = sqrtf(distSq - combinedRadiusSq);
-                    const float inv = 1.0f / distSq;
-                    if (fdet(rpx, rpy, wx, wy) > 0.0f) {
-                        ln[s].dx = (rpx * leg - rpy * combinedRadius) * inv;
-                        ln[s].dy = (rpx * combinedRadius + rpy * leg) * inv;
-                    } else {
-                        ln[s].dx = (-(rpx * leg + rpy * combinedRadius)) * inv;
-                        ln[s].dy = (-(-rpx * combinedRadius + rpy * leg)) * inv;
-                    }
-                    const float dotProduct2 = fdot(rvx, rvy, ln[s].dx, ln[s].dy);
-                    ux = dotProduct2 * ln[s].dx - rvx;
-                    uy = dotProduct2 * ln[s].dy - rvy;
                 }
-            } else {
-                const float invTimeStep = 1.0f / timeStep;
-                const float wx = rvx - invTimeStep * rpx, wy = rvy - invTimeStep * rpy;
-                const float wLength = sqrtf(fdot(wx, wy, wx, wy));
-                const float inv = 1.0f / wLength;
-                const float uwx = wx * inv, uwy = wy * inv;
-                ln[s].dx = uwy;
-                ln[s].dy = -uwx;
-                const float sc = combinedRadius * invTimeStep - wLength;
-                ux = sc * uwx;
-                uy = sc * uwy;
+                ln[s].px = me.z + collab * ux;
+                ln[s].py = me.w + collab * uy;
             }
-            ln[s].px = me.z + collab * ux;
-            ln[s].py = me.w + collab * uy;
+            nl += __popc(gballot<G>(gm, valid[s]));
         }
-        nl += __popc(gballot<G>(gm, valid[s]));
     }
     float rx, ry;
     const int fail = lp2_group<G, SL>(gm, glane, ln, valid, nl, maxSpeed, prefx, prefy, false, rx, ry);

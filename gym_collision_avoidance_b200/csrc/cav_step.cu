@@ -33,6 +33,7 @@ struct DevBuffers {
     uint8_t *done, *game_over;
     void *obs;
     void *history, *aux0, *past_actions, *past_vel;
+    const int32_t *episode;
 };
 
 static inline DevBuffers make_dev(const cav_buffers_t &b) {
@@ -55,6 +56,7 @@ static inline DevBuffers make_dev(const cav_buffers_t &b) {
     d.aux0 = b.aux0;
     d.past_actions = b.past_actions;
     d.past_vel = b.past_vel;
+    d.episode = b.episode;
     return d;
 }
 
@@ -178,8 +180,29 @@ __global__ void __launch_bounds__(512) k_policy_move(DevBuffers b, KParams<T> p,
                     const T sc = gl.w / nrm;  // :67
                     const float prefx = (float)(sc * gx), prefy = (float)(sc * gy);
                     float nvx, nvy;
+                    // RVOPolicy.py:76-90: anti-collaborative agents re-draw their mode every rvo_anti_collab_t seconds
+                    float ego_collab = p.rvo_collab;
+                    if (p.rvo_collab < 0.0f) {
+                        uint32_t fl = f;
+                        const T tm = pymod<T>(s_ht[li].z, p.rvo_anti_collab_t);
+                        const T r1 = M<T>::rint_(tm * (T)1000) / (T)1000,
+                                r2 = M<T>::rint_((p.rvo_anti_collab_t - tm) * (T)1000) / (T)1000;
+                        if (r1 < p.dt || r2 < p.dt) {
+                            const double u = philox_u01(p.rvo_seed, (uint32_t)(e0 + g_el), (uint32_t)a,
+                                                        (uint32_t)(b.episode ? b.episode[e0 + g_el] : 0),
+                                                        (uint32_t)b.step_num[base + li]);
+                            fl = (u < 1.0 - (double)p.rvo_anti_p) ? (fl | CAV_FLAG_RVO_NON_COOP)
+                                                                   : (fl & ~(uint32_t)CAV_FLAG_RVO_NON_COOP);
+                            __syncwarp(gm);  // every lane of the group has read s_flags[li]
+                            if (glane == 0) {
+                                s_flags[li] = fl;
+                                b.flags[base + li] = fl;
+                            }
+                        }
+                        if (fl & CAV_FLAG_RVO_NON_COOP) ego_collab = 0.0f;
+                    }
                     orca_group<G, SL>(gm, glane, n, a, s_f4 + eb, s_frad + eb, prefx, prefy, (float)gl.w,
-                                      p.rvo_inv_time_horizon_num, p.rvo_time_step, p.rvo_collab, p.rvo_neighbor_dist,
+                                      p.rvo_inv_time_horizon_num, p.rvo_time_step, ego_collab, p.rvo_neighbor_dist,
                                       p.rvo_max_neighbors, kd, nvx, nvy);
                     // Agent::update (Agent.cpp:470-475) in float, then RVOPolicy.py:96-111 in `real`
                     const float4 me = s_f4[li];
@@ -632,7 +655,7 @@ __global__ void __launch_bounds__(512) k_pairwise_obs(DevBuffers b, KParams<T> p
 // host-side launchers
 // =============================================================================================================
 static void pick_shape(int N, int &G, int &SL) {
-    const int others = N - 1 > 1 ? N - 1 : 1;
+    const int others = N - 1 > 2 ? N - 1 : 2;  // >= 2 line slots per group: the anti-collaborative branch builds two
     SL = others > 32 ? 2 : 1;
     G = 1;
     while (G * SL < others && G < 32) G <<= 1;

@@ -27,6 +27,7 @@ static inline TpaBuffers make_tpa(const cav_buffers_t &b) {
     d.aux0 = b.aux0;
     d.past_actions = b.past_actions;
     d.past_vel = b.past_vel;
+    d.episode = b.episode;
     return d;
 }
 

@@ -23,13 +23,28 @@ namespace cav {
 #ifndef CAV_TPA_N_MINB_F32
 #define CAV_TPA_N_MINB_F32 5
 #endif
+#ifndef CAV_TPA_N_MINB_F64
+#define CAV_TPA_N_MINB_F64 5
+#endif
+#ifndef CAV_TPA_N_WARPS_F64
+#define CAV_TPA_N_WARPS_F64 4
+#endif
+#ifndef CAV_TPA_N_WARPS_F32
+#define CAV_TPA_N_WARPS_F32 2
+#endif
+// Centre distances of the N-1 neighbours: carried through the sorting network next to the keys in registers (0), or
+// parked in a per-warp shared-memory table [slot][lane] and fetched by neighbour index after the sort (1) -- 2 x (N-1)
+// fewer live registers and half the selects per compare-exchange for float64 state.
+#ifndef CAV_TPA_N_DC_SMEM
+#define CAV_TPA_N_DC_SMEM 0
+#endif
 template <typename T>
 struct TpaNBounds {
     static constexpr int MINB = CAV_TPA_N_MINB_F32;
 };
 template <>
 struct TpaNBounds<double> {
-    static constexpr int MINB = 5;
+    static constexpr int MINB = CAV_TPA_N_MINB_F64;
 };
 
 // Thread mapping: environments never straddle a warp.  A warp owns EPW = 32 / N consecutive environments, i.e. the
@@ -57,12 +72,14 @@ struct TpaNShape {
     static constexpr int WM = W0 > W1 ? W0 : W1;
     static constexpr int WS = WM | 1;                               // staging row stride, odd
     // warps per CTA, measured at 16384 x 10: float64 38.9 / 40.7 / 45.7 us with 4 / 2 / 1; float32 26.0 / 23.6 / 27.9 us
-    static constexpr int WARPS = sizeof(T) == 8 ? 4 : 2;
+    static constexpr int WARPS = sizeof(T) == 8 ? CAV_TPA_N_WARPS_F64 : CAV_TPA_N_WARPS_F32;
     static constexpr int EPB = WARPS * EPW;
     // float32, single pass, staging stride == packed row length: the slice is a flat image of the HBM block
     static constexpr bool FLAT4 = sizeof(OT) == 4 && P == 1 && WS == CL;
     static constexpr size_t r16(size_t x) { return (x + 15) & ~(size_t)15; }
-    static constexpr size_t WARP_BYTES = r16(sizeof(R4<T>) * LW) + r16(sizeof(T) * LW) + r16(sizeof(OT) * (LW * WS + 4));
+    static constexpr size_t DC_BYTES = CAV_TPA_N_DC_SMEM ? r16(sizeof(T) * (NO > 0 ? NO : 1) * 32) : 0;
+    static constexpr size_t WARP_BYTES =
+        r16(sizeof(R4<T>) * LW) + r16(sizeof(T) * LW) + r16(sizeof(OT) * (LW * WS + 4)) + DC_BYTES;
 };
 
 // T = state precision, OT = precision of the packed observation and of the reward (float when the state is float, or when
@@ -85,6 +102,9 @@ __global__ void __launch_bounds__(32 * TpaNShape<T, NT, OT>::WARPS, (TpaNBounds<
     T *s_rad = reinterpret_cast<T *>(sp);
     sp += a16(sizeof(T) * LW);
     OT *const stage0 = reinterpret_cast<OT *>(sp);  // [LW][WS] (+ up to 3 values of phase shift, see FLAT4)
+    sp += a16(sizeof(OT) * (LW * WS + 4));
+    T *const s_dc = reinterpret_cast<T *>(sp);  // [NO][32] centre distances (CAV_TPA_N_DC_SMEM)
+    auto dc_of = [&](int o, int hh) -> T { return s_dc[(o - (o > hh ? 1 : 0)) * 32 + lane]; };
     const R4<T> *g_pv = reinterpret_cast<const R4<T> *>(b.pv);
     const R4<T> *g_goal = reinterpret_cast<const R4<T> *>(b.goal);
     const R4<T> *g_ego = reinterpret_cast<const R4<T> *>(b.ego);
@@ -125,7 +145,9 @@ __global__ void __launch_bounds__(32 * TpaNShape<T, NT, OT>::WARPS, (TpaNBounds<
         const T prx = egh.z, pry = egh.w;
         const T orx = -pry, ory = prx;  // ref_orth, agent.py:347
         unsigned long long key[NO > 0 ? NO : 1];
+#if !CAV_TPA_N_DC_SMEM
         T dcv[NO > 0 ? NO : 1];
+#endif
         int nc = 0;
         bool done_now = false;
         if (active) {
@@ -136,7 +158,9 @@ __global__ void __launch_bounds__(32 * TpaNShape<T, NT, OT>::WARPS, (TpaNBounds<
             for (int j = 0; j < NO; ++j) {
                 const int o = j + (j >= h ? 1 : 0);
                 key[j] = ~0ull;
+#if !CAV_TPA_N_DC_SMEM
                 dcv[j] = (T)0;
+#endif
                 if (o < n) {
                     const R4<T> pvo = s_pv[eb + o];
                     const T ro = s_rad[eb + o];
@@ -149,7 +173,11 @@ __global__ void __launch_bounds__(32 * TpaNShape<T, NT, OT>::WARPS, (TpaNBounds<
                         const T d2o = dc - glh.z - ro;             // :87
                         const T po = (rx * orx + ry * ory) + (T)0;
                         key[j] = make_key<T>(M<T>::rint_(d2o * (T)100), po, o, false);
+#if CAV_TPA_N_DC_SMEM
+                        s_dc[j * 32 + lane] = dc;
+#else
                         dcv[j] = dc;
+#endif
                         ++nc;
                     }
                 }
@@ -158,11 +186,13 @@ __global__ void __launch_bounds__(32 * TpaNShape<T, NT, OT>::WARPS, (TpaNBounds<
             sort_network<NO>([&](int i, int j) {
                 const bool sw = key[j] < key[i];
                 const unsigned long long ka = key[i], kb = key[j];
-                const T da = dcv[i], db = dcv[j];
                 key[i] = sw ? kb : ka;
                 key[j] = sw ? ka : kb;
+#if !CAV_TPA_N_DC_SMEM
+                const T da = dcv[i], db = dcv[j];
                 dcv[i] = sw ? db : da;
                 dcv[j] = sw ? da : db;
+#endif
             });
             // exact re-comparison inside runs of equal kint (truncated p_orth / clamped kint, see KeyCodec): rare
             bool tie = false;
@@ -178,17 +208,24 @@ __global__ void __launch_bounds__(32 * TpaNShape<T, NT, OT>::WARPS, (TpaNBounds<
                         if ((ka >> KSHIFT) == (kb >> KSHIFT) && kb != ~0ull) {
                             const int oa = (int)(ka & 63ull), ob = (int)(kb & 63ull);
                             const R4<T> pa = s_pv[eb + oa], pb = s_pv[eb + ob];
-                            const T kia = M<T>::rint_((dcv[r] - glh.z - s_rad[eb + oa]) * (T)100);
-                            const T kib = M<T>::rint_((dcv[r + 1] - glh.z - s_rad[eb + ob]) * (T)100);
+#if CAV_TPA_N_DC_SMEM
+                            const T dca = dc_of(oa, h), dcb = dc_of(ob, h);
+#else
+                            const T dca = dcv[r], dcb = dcv[r + 1];
+#endif
+                            const T kia = M<T>::rint_((dca - glh.z - s_rad[eb + oa]) * (T)100);
+                            const T kib = M<T>::rint_((dcb - glh.z - s_rad[eb + ob]) * (T)100);
                             const T poa = (pa.x - pvh.x) * orx + (pa.y - pvh.y) * ory;
                             const T pob = (pb.x - pvh.x) * orx + (pb.y - pvh.y) * ory;
                             const bool b_first = (kib < kia) || (kib == kia && (pob < poa || (pob == poa && ob < oa)));
                             if (b_first) {
-                                const T da = dcv[r];
                                 key[r] = kb;
                                 key[r + 1] = ka;
+#if !CAV_TPA_N_DC_SMEM
+                                const T da = dcv[r];
                                 dcv[r] = dcv[r + 1];
                                 dcv[r + 1] = da;
+#endif
                                 swapped = true;
                             }
                         }
@@ -270,7 +307,11 @@ __global__ void __launch_bounds__(32 * TpaNShape<T, NT, OT>::WARPS, (TpaNBounds<
                     dst[3] = (OT)(pvo.z * orx + pvo.w * ory);
                     dst[4] = (OT)ro;
                     dst[5] = (OT)(glh.z + ro);
+#if CAV_TPA_N_DC_SMEM
+                    dst[6] = (OT)(dc_of(o, h) - glh.z - ro);  // np.linalg.norm(..) - r - r (:125)
+#else
                     dst[6] = (OT)(dcv[r] - glh.z - ro);  // np.linalg.norm(..) - r - r (:125)
+#endif
                 } else {
 #pragma unroll
                     for (int k = 0; k < 7; ++k) dst[k] = (OT)0;  // zero rows (:108)

@@ -177,7 +177,8 @@ class CollisionAvoidanceEnv(object):
             self._cav.close()
         self._hist_len = max(hist_len, 64)
         c = _config.to_cav_config(C, 1, C.MAX_NUM_AGENTS_IN_ENVIRONMENT, precision="f64",
-                                  history_len=self._hist_len, store_history=bool(C.STORE_HISTORY), track_aux=True)
+                                  history_len=self._hist_len, store_history=bool(C.STORE_HISTORY), track_aux=True,
+                                  seed=int(np.random.randint(0, 2 ** 31 - 1)) if C.RVO_COLLAB_COEFF < 0 else 0)
         self._c = c
         self._cav = Cavoid(c, self.device)
         if C.USE_STATIC_MAP:

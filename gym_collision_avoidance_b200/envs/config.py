@@ -253,7 +253,7 @@ def parse_precision(p):
 
 
 def to_cav_config(cfg, num_envs, num_agents=None, precision="f64", store_history=None, history_len=0,
-                  track_aux=False, obs_f32=False):
+                  track_aux=False, obs_f32=False, seed=0):
     """Flatten a reference-style Config object into ``cav_config_t``.  ``obs_f32``: float64 state with float32
     observation / reward columns (the reference's declared observation dtype)."""
     c = abi.CavConfig()
@@ -306,4 +306,6 @@ def to_cav_config(cfg, num_envs, num_agents=None, precision="f64", store_history
     c.history_len = int(history_len)
     c.track_aux = int(bool(track_aux))
     c.obs_f32 = int(bool(obs_f32) and c.precision == abi.CAV_F64)
+    c.rvo_anti_collab_t = float(getattr(cfg, "RVO_ANTI_COLLAB_T", 1.0))
+    c.rvo_seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     return c

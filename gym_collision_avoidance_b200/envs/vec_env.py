@@ -60,7 +60,7 @@ class VecCollisionAvoidanceEnv(object):
         # reference declares for its observation space, config.py:93-170): half the HBM and PCIe bytes of the
         # observation, no cast pass in the host-buffer API
         self.c = _config.to_cav_config(config, self.num_envs, self.num_agents, precision=precision,
-                                       history_len=history_len, track_aux=track_aux, obs_f32=obs_f32)
+                                       history_len=history_len, track_aux=track_aux, obs_f32=obs_f32, seed=seed)
         self.obs_offsets, self.obs_len = _config.obs_layout(config)
         if scenario_source not in ("host", "device"):
             raise ValueError("scenario_source must be 'host' or 'device'")

@@ -82,6 +82,7 @@ typedef enum {
 #define CAV_FLAG_DONE 0x20u                     /* is_done (set by the done check, env.py:514-553) */
 #define CAV_FLAG_COLLIDED_AGENT 0x40u           /* this step's collision_with_agent[i] (env.py:490-493) */
 #define CAV_FLAG_COLLIDED_WALL 0x80u            /* this step's collision_with_wall[i] (env.py:494-506) */
+#define CAV_FLAG_RVO_NON_COOP 0x100u            /* RVOPolicy.use_non_coop_policy (RVOPolicy.py:32,77-88; anti-collaborative RVO) */
 
 /* AGENT_SORTING_METHOD (OtherAgentsStatesSensor.py:33-52). */
 typedef enum { CAV_SORT_CLOSEST_FIRST = 0, CAV_SORT_CLOSEST_LAST = 1, CAV_SORT_TIME_TO_IMPACT = 2 } cav_sorting_t;
@@ -160,7 +161,7 @@ typedef struct cav_config {
 
     /* RVO (RVOPolicy.py:13-28; envs/config.py:83-86) */
     double rvo_time_horizon;      /* Config.RVO_TIME_HORIZON */
-    double rvo_collab_coeff;      /* Config.RVO_COLLAB_COEFF (>= 0; the anti-collaborative branch is not built) */
+    double rvo_collab_coeff;      /* Config.RVO_COLLAB_COEFF; < 0 = anti-collaborative RVO (RVOPolicy.py:77-88, Agent.cpp:368-415) */
     double rvo_neighbor_dist;     /* neighborDist = Config.SENSING_HORIZON */
     double rvo_max_delta_heading; /* pi/6 */
     double rvo_radius_scale;      /* 1 + 5e-2 */
@@ -185,6 +186,12 @@ typedef struct cav_config {
     int32_t obs_f32;       /* precision == CAV_F64 only: `obs` and `reward` are float32 columns -- the dtype the reference
                             * DECLARES for its observation space (np.float32, envs/config.py:93-170) -- written directly by
                             * the kernels from the float64 state (half the bytes to HBM and to the host); 0 = `real` */
+    /* anti-collaborative RVO (rvo_collab_coeff < 0): every rvo_anti_collab_t seconds of agent time the agent re-draws
+     * whether it ignores the others (probability 1 - |coeff|) or steers INTO its closest neighbour (RVOPolicy.py:77-88).
+     * The reference draws from NumPy's global stream; here the draw is Philox4x32-10 keyed by (rvo_seed; env, agent,
+     * episode, step_num): same distribution, reproducible, independent of launch geometry. */
+    double rvo_anti_collab_t; /* Config.RVO_ANTI_COLLAB_T */
+    uint64_t rvo_seed;
 } cav_config_t;
 
 /* Device buffers (all borrowed).  "real4" = 4 consecutive reals, 16-byte aligned. */

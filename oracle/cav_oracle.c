@@ -360,6 +360,31 @@ void cavo_orca_solve_kd(int n, int ego, const float *pos, const float *vel, cons
             ln.py = vy + collab * uy;
             lines[nl++] = ln;
         }
+    } else if (collab < 0.0f && nn > 0) {
+        /* R/Agent.cpp:368-415: negative collaboration -- steer INTO the closest neighbour.  The closest one is the first
+         * of the list (ascending distSq; the strict `<` of the reference's scan keeps the first of equals).  Two
+         * half-planes: the legs of its velocity obstacle facing INWARD, both through v_other + relativePosition; the
+         * preferred velocity becomes v_other + (-collab) * normalize(relativePosition). */
+        const int o = nb_idx[0];
+        const float rpx = pos[2 * o] - pos[2 * ego], rpy = pos[2 * o + 1] - pos[2 * ego + 1];
+        const float distSq = o_dot(rpx, rpy, rpx, rpy);
+        const float combinedRadius = rad[ego] + rad[o];
+        const float combinedRadiusSq = combinedRadius * combinedRadius;
+        const float leg = sqrtf(distSq - combinedRadiusSq);
+        const float inv = 1.0f / distSq; /* Vector2 / float = multiply by the reciprocal, R/Vector2.h:115-120 */
+        orca_line_t ln;
+        ln.px = vel[2 * o] + rpx;
+        ln.py = vel[2 * o + 1] + rpy;
+        ln.dx = (-(rpx * leg - rpy * combinedRadius)) * inv; /* left leg */
+        ln.dy = (-(rpx * combinedRadius + rpy * leg)) * inv;
+        lines[nl++] = ln;
+        ln.dx = (rpx * leg + rpy * combinedRadius) * inv; /* right leg */
+        ln.dy = (-rpx * combinedRadius + rpy * leg) * inv;
+        lines[nl++] = ln;
+        const float invn = 1.0f / sqrtf(distSq); /* normalize(v) = v / abs(v) */
+        const float s_ = -collab;
+        prefx = vel[2 * o] + s_ * (rpx * invn);
+        prefy = vel[2 * o + 1] + s_ * (rpy * invn);
     }
     float rx, ry;
     const int fail = orca_lp2(lines, nl, maxSpeed, prefx, prefy, 0, &rx, &ry);
@@ -387,6 +412,28 @@ void cavo_orca_solve_perm(int n, int ego, const float *pos, const float *vel, co
     if (rebuild || t.pos != pos || t.perm != perm) cavo_kd_build(&t, pos, perm, n);
     cavo_orca_solve_kd(n, ego, pos, vel, rad, maxSpeed, prefx, prefy, timeHorizon, timeStep, collab, neighborDist,
                        maxNeighbors, &t, out_vx, out_vy, NULL, NULL);
+}
+
+/* Philox4x32-10 (Salmon et al., SC'11; Random123 constants), first output word / 2^32: the anti-collaborative RVO agents'
+ * policy re-draw.  The reference draws np.random.choice from NumPy's global stream (RVOPolicy.py:84), which a batched
+ * environment cannot share; the product (csrc/cav_hd.cuh philox_u01) and this restatement use the same counter-based
+ * draw keyed by (seed; env, agent, episode, step_num), so they agree draw for draw, and the distribution is the reference's. */
+static double cavo_philox_u01(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1;
+        c3 = (uint32_t)p0;
+        c0 = n0;
+        c2 = n2;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return (double)c0 * (1.0 / 4294967296.0);
+}
+double cavo_philox_u01_export(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
+    return cavo_philox_u01(seed, c0, c1, c2, c3);
 }
 
 /* ------------------------------------------------------------------------------------------------------------

@@ -131,6 +131,24 @@ static void SFX(policy_env)(const cav_config_t *cfg, const cav_buffers_t *b, con
             const float prefx = (float)(sc * gx), prefy = (float)(sc * gy);
             const float maxSpeed = (float)goal[i].w; /* :70 */
             float nvx, nvy;
+            /* RVOPolicy.py:76-90: the ego's collaboration coefficient.  Negative = anti-collaborative: every
+             * RVO_ANTI_COLLAB_T seconds of agent time (within DT of a multiple of it) the agent re-draws whether it ignores
+             * the others (use_non_coop_policy, probability 1 - |coeff| -> coefficient 0: no half-planes at all) or
+             * steers into its closest neighbour (the negative coefficient, R/Agent.cpp:368-415). */
+            float ego_collab = (float)cfg->rvo_collab_coeff;
+            if (cfg->rvo_collab_coeff < 0) {
+                const REAL T_ = (REAL)cfg->rvo_anti_collab_t;
+                const REAL tm = SFX(pymod)(ht[i].z, T_);
+                const REAL r1 = R_RINT(tm * (REAL)1000) / (REAL)1000, r2 = R_RINT((T_ - tm) * (REAL)1000) / (REAL)1000;
+                if (r1 < (REAL)cfg->dt || r2 < (REAL)cfg->dt) {
+                    const int ep = b->episode ? b->episode[e] : 0;
+                    const double u = cavo_philox_u01(cfg->rvo_seed, (uint32_t)e, (uint32_t)i, (uint32_t)ep,
+                                                     (uint32_t)b->step_num[(size_t)e * N + i]);
+                    if (u < 1.0 - fabs(cfg->rvo_collab_coeff)) flags[i] |= CAV_FLAG_RVO_NON_COOP;
+                    else flags[i] &= ~(uint32_t)CAV_FLAG_RVO_NON_COOP;
+                }
+                if (flags[i] & CAV_FLAG_RVO_NON_COOP) ego_collab = 0.0f;
+            }
             const int reps = g_faithful_dostep ? n : 1;
             for (int r = 0; r < reps; ++r) { /* reps>1 only burns the reference's redundant solves */
                 const int who = g_faithful_dostep ? r : i;
@@ -144,7 +162,7 @@ static void SFX(policy_env)(const cav_config_t *cfg, const cav_buffers_t *b, con
                     ms = (float)goal[who].w;
                 }
                 cavo_orca_solve_kd(n, who, fpos, fvel, frad, ms, px_, py_, (float)cfg->rvo_time_horizon, (float)cfg->dt,
-                                   who == i ? (float)cfg->rvo_collab_coeff : 0.5f, (float)cfg->rvo_neighbor_dist,
+                                   who == i ? ego_collab : 0.5f, (float)cfg->rvo_neighbor_dist,
                                    cfg->rvo_max_neighbors, tree, &tx, &ty, NULL, NULL);
                 if (who == i) {
                     nvx = tx;
@@ -658,7 +676,7 @@ static void SFX(reset_env)(const cav_config_t *cfg, const cav_buffers_t *b, cons
         ht[i].w = 0; /* turning_dir */
         REAL vex, vey;
         SFX(update_ego)(pv[i], goal[i], ht[i].x, &ego[i], &vex, &vey);
-        b->flags[g] = 0;
+        b->flags[g] = CAV_FLAG_RVO_NON_COOP; /* RVOPolicy.__init__: use_non_coop_policy = True (RVOPolicy.py:32) */
         b->step_num[g] = 0;
         b->done[g] = 0;
         b->actions[2 * g] = b->actions[2 * g + 1] = 0;

@@ -250,8 +250,8 @@ def compare_states(got, want, n, rtol, atol, cols=None):
             continue
         a, b = a[:, :n], b[:, :n]
         if k == "flags":
-            if not np.array_equal(a & 0xff, b & 0xff):
-                bad = np.argwhere((a & 0xff) != (b & 0xff))[:5]
+            if not np.array_equal(a & 0x1ff, b & 0x1ff):
+                bad = np.argwhere((a & 0x1ff) != (b & 0x1ff))[:5]
                 raise AssertionError("flags mismatch at %s: got %s want %s" % (bad.tolist(), a[tuple(bad[0])],
                                                                                 b[tuple(bad[0])]))
         elif a.dtype.kind in "iu":

@@ -66,8 +66,9 @@ def test_create_rejects_bad_config_without_gpu(libpath):
     bad.agent_sorting_method = 7  # not a cav_sorting_t
     assert L.cav_create(ctypes.byref(bad), ctypes.byref(h)) == -1
     bad = abi.CavConfig.from_buffer_copy(c)
-    bad.rvo_collab_coeff = -0.5
-    assert L.cav_create(ctypes.byref(bad), ctypes.byref(h)) == -7  # CAV_ERR_UNSUPPORTED: no CPU fallback exists
+    bad.rvo_collab_coeff = -0.5  # anti-collaborative RVO needs its re-draw period
+    bad.rvo_anti_collab_t = 0.0
+    assert L.cav_create(ctypes.byref(bad), ctypes.byref(h)) == -1
     assert L.cav_create(None, ctypes.byref(h)) == -2  # CAV_ERR_NULL_POINTER
     assert L.cav_step(None, None, 0.0, None) == -6  # CAV_ERR_BAD_HANDLE
     assert L.cav_destroy(None) == -6

@@ -49,13 +49,48 @@ def test_f64_vs_oracle_across_agent_counts(N, mapping, monkeypatch):
     """Both kernel families: one-thread-per-agent (N <= 24 by default; forced up to 32 here) and sub-warp groups
     (G = 1, 2, 4, 8, 16, 32 lanes per agent, and SL = 2 neighbours per lane for N > 33).  Dense banks so that
     collisions, LP3 fallbacks and done agents occur."""
-    if mapping == "tpa" and N > 25:
-        pytest.skip("thread-per-agent mapping is only built for N <= 25")
+    if mapping == "tpa" and N > 32:
+        pytest.skip("thread-per-agent kernels: policy + move for N <= 32, pairwise + obs for N <= 24")
     monkeypatch.setenv("CAV_TPA_MAX_N", "32" if mapping == "tpa" else "0")
     E = 96 if N <= 20 else 24
     c = to_cav_config(make_config(N, evaluate=True), E, N, precision="f64", track_aux=True)
     bank = _bank(E, N, seed=100 + N, dense=True)
     _run_both(c, bank, steps=12 if N <= 20 else 6)
+
+
+@pytest.mark.parametrize("mapping", ["tpa", "group"])
+@pytest.mark.parametrize("N,coeff", [(2, -0.6), (6, -0.6), (10, -0.3), (12, -0.6), (40, -0.8)])
+def test_anti_collaborative_rvo_redraw_matches_oracle(N, coeff, mapping, monkeypatch):
+    """RVO_COLLAB_COEFF < 0 (RVOPolicy.py:77-88, Agent.cpp:368-415): every RVO_ANTI_COLLAB_T seconds each agent re-draws
+    between "ignore the others" (probability 1 - |coeff|) and "steer into the closest neighbour".  The draw is the same
+    counter-based Philox value on the device and in the oracle, so states agree step for step (each step starts from the
+    oracle's state); the observed frequency of the two modes follows the reference's distribution.  (The branch's
+    arithmetic itself is pinned against the reference by the goldens anticollab6 / anticollab12_mixed, coefficient -1.)"""
+    from gpu_common import GpuRunner
+    monkeypatch.setenv("CAV_TPA_MAX_N", "32" if mapping == "tpa" else "0")
+    E = 96 if N <= 12 else 16
+    cfg = make_config(N, evaluate=True, RVO_COLLAB_COEFF=coeff, RVO_ANTI_COLLAB_T=0.5)
+    c = to_cav_config(cfg, E, N, precision="f64", track_aux=True, seed=1234 + N)
+    bank = _bank(E, N, seed=60 + N)
+    hs = HostState(c)
+    orc = Oracle(c)
+    orc.reset(hs, bank)
+    r = GpuRunner(c)
+    r.cav.reset(r.bank(bank))
+    common.compare_states(r.download(), hs, N, 1e-12, 1e-12)
+    assert (hs.flags & abi.CAV_FLAG_RVO_NON_COOP).all()  # use_non_coop_policy starts True (RVOPolicy.py:32)
+    non_coop = total = 0
+    for s in range(26):
+        r.upload(hs)
+        orc.step(hs)
+        r.cav.step()
+        common.compare_states(r.download(), hs, N, 1e-9, 1e-9)
+        live = (hs.flags & abi.CAV_FLAG_DONE) == 0
+        if s % 5 == 0:  # t = 0, 0.5, 1.0 ...: a fresh draw for every live agent
+            non_coop += int(((hs.flags & abi.CAV_FLAG_RVO_NON_COOP) != 0)[live].sum())
+            total += int(live.sum())
+    p = 1.0 - abs(coeff)
+    assert total > 300 and abs(non_coop / total - p) < 4.0 * np.sqrt(p * (1 - p) / total) + 0.01
 
 
 @pytest.mark.parametrize("mapping", ["tpa", "group"])

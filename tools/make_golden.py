@@ -165,6 +165,7 @@ def run_scenario(name, N, agents_fn, pre=(), post=(), max_steps=400, ext_action_
             AGENT_SORTING_METHOD=Config.AGENT_SORTING_METHOD, USE_STATIC_MAP=bool(Config.USE_STATIC_MAP),
             LASERSCAN_LENGTH=int(Config.LASERSCAN_LENGTH), LASERSCAN_NUM_PAST=int(Config.LASERSCAN_NUM_PAST),
             RVO_TIME_HORIZON=Config.RVO_TIME_HORIZON, RVO_COLLAB_COEFF=Config.RVO_COLLAB_COEFF,
+            RVO_ANTI_COLLAB_T=Config.RVO_ANTI_COLLAB_T,
             REWARD_AT_GOAL=Config.REWARD_AT_GOAL, REWARD_COLLISION_WITH_AGENT=Config.REWARD_COLLISION_WITH_AGENT,
             REWARD_COLLISION_WITH_WALL=Config.REWARD_COLLISION_WITH_WALL, REWARD_TIME_STEP=Config.REWARD_TIME_STEP,
             REWARD_WIGGLY_BEHAVIOR=Config.REWARD_WIGGLY_BEHAVIOR,
@@ -411,6 +412,22 @@ _circle("circle20_r10", 20, 10.0)   # preset_testCases(20) (test_cases.py:884-88
 _circle("circle16_r8", 16, 8.0)
 _circle("circle12_r6", 12, 6.0)
 _circle("circle10_r5", 10, 5.0, stop_after=150)     # single leaf (n <= MAX_LEAF_SIZE): index order
+
+
+# ---- anti-collaborative RVO (RVOPolicy.py:77-88, R/Agent.cpp:368-415) with RVO_COLLAB_COEFF = -1: the policy re-draw is
+# then deterministic (np.random.choice([True, False], p=[0, 1]) is always False), so the reference pins the arithmetic of
+# the "steer into the closest neighbour" branch bit for bit; other coefficients are random in the reference ----
+@scenario
+def anticollab6():
+    run_scenario("anticollab6", 6, lambda tc, C: mk_agents(tc, fixture_rows(tc, 6, 1), "RVO"),
+                 post=EVAL_POST + ["self.RVO_COLLAB_COEFF = -1.0"], stop_after=120)
+
+
+@scenario
+def anticollab12_mixed():  # N > 10 (kd-tree order), anti-collaborative RVO agents among non-cooperative ones
+    run_scenario("anticollab12_mixed", 12,
+                 lambda tc, C: mk_agents(tc, _rand_rows(12, 77, 6.0), ["RVO", "noncoop"] * 6),
+                 post=EVAL_POST + ["self.RVO_COLLAB_COEFF = -1.0"], stop_after=80)
 
 
 @scenario
