@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(256) k_reset(ResetPtrs b, ResetParams rp, cons
             st4(g_goal + gi, gl);
             st4(g_ht + gi, ht);
             st4(g_ego + gi, ego);
-            b.flags[gi] = CAV_FLAG_RVO_NON_COOP;  // RVOPolicy.__init__: use_non_coop_policy = True (RVOPolicy.py:32)
+            b.flags[gi] = (a < n) ? CAV_FLAG_RVO_NON_COOP : 0u;  // RVOPolicy.__init__: use_non_coop_policy = True (RVOPolicy.py:32)
             b.step_num[gi] = 0;
             b.done[gi] = 0;
             reinterpret_cast<float2 *>(b.actions)[gi] = make_float2(0.f, 0.f);

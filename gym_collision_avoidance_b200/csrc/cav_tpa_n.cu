@@ -17,9 +17,11 @@
 
 namespace cav {
 
-// Resident CTAs per SM the compiler must allow.  float64 at N = 10 wants 138 registers unconstrained (3 CTAs / SM);
-// capping at 5 CTAs (<= 102 registers, ~170 B of spills) measured best at 16384 x 10: 44.8 us vs 51.3 (1), 49.1 (4),
-// 48.0 (6) and 49.8 for the generic kernel.  float32 needs 96 registers unconstrained, i.e. 5 CTAs already.
+// Resident 128-thread equivalents per SM the compiler must allow.  Round 1 (distances in registers): float64 at N = 10
+// wanted 138 registers, capped at 5 (<= 102 registers, ~170 B of spills: 44.8 us vs 51.3 / 49.1 / 48.0 us with 1 / 4 / 6).
+// Round 2 sweep at 16384 x 10, float64 state + float32 observation (profiles/r02c_libsweep.txt): the spills were the
+// long-scoreboard stalls -- parking the nine centre distances in shared memory (CAV_TPA_N_DC_SMEM) leaves 92 registers
+// and no spill, and with 2-warp CTAs 33.8 -> 27.6 us (cap 5; 28.4 / 28.9 us with 6 / 7; 32.4 us with 4-warp CTAs).
 #ifndef CAV_TPA_N_MINB_F32
 #define CAV_TPA_N_MINB_F32 5
 #endif
@@ -27,7 +29,7 @@ namespace cav {
 #define CAV_TPA_N_MINB_F64 5
 #endif
 #ifndef CAV_TPA_N_WARPS_F64
-#define CAV_TPA_N_WARPS_F64 4
+#define CAV_TPA_N_WARPS_F64 2
 #endif
 #ifndef CAV_TPA_N_WARPS_F32
 #define CAV_TPA_N_WARPS_F32 2
@@ -36,7 +38,7 @@ namespace cav {
 // parked in a per-warp shared-memory table [slot][lane] and fetched by neighbour index after the sort (1) -- 2 x (N-1)
 // fewer live registers and half the selects per compare-exchange for float64 state.
 #ifndef CAV_TPA_N_DC_SMEM
-#define CAV_TPA_N_DC_SMEM 0
+#define CAV_TPA_N_DC_SMEM 1
 #endif
 template <typename T>
 struct TpaNBounds {

@@ -59,7 +59,7 @@ def test_f64_vs_oracle_across_agent_counts(N, mapping, monkeypatch):
 
 
 @pytest.mark.parametrize("mapping", ["tpa", "group"])
-@pytest.mark.parametrize("N,coeff", [(2, -0.6), (6, -0.6), (10, -0.3), (12, -0.6), (40, -0.8)])
+@pytest.mark.parametrize("N,coeff", [(3, -0.6), (6, -0.6), (10, -0.3), (12, -0.6), (40, -0.8)])
 def test_anti_collaborative_rvo_redraw_matches_oracle(N, coeff, mapping, monkeypatch):
     """RVO_COLLAB_COEFF < 0 (RVOPolicy.py:77-88, Agent.cpp:368-415): every RVO_ANTI_COLLAB_T seconds each agent re-draws
     between "ignore the others" (probability 1 - |coeff|) and "steer into the closest neighbour".  The draw is the same
