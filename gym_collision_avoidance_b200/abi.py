@@ -102,7 +102,7 @@ class CavScenarioBank(ctypes.Structure):
 
 class CavScenarioGen(ctypes.Structure):
     _fields_ = [("seed", ctypes.c_uint64), ("side_length", ctypes.c_double * 2), ("speed_bnds", ctypes.c_double * 2),
-                ("radius_bnds", ctypes.c_double * 2)]
+                ("radius_bnds", ctypes.c_double * 2), ("random_heading", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 # every symbol include/cavoid.h declares

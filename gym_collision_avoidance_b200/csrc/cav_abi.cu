@@ -291,18 +291,36 @@ int cav_bind(cav_handle_t h, const cav_buffers_t *bufs) {
     if (!valid(h)) return fail(nullptr, CAV_ERR_BAD_HANDLE, name ": bad handle");   \
     if (!(h)->bound) return fail(h, CAV_ERR_NOT_BOUND, name ": cav_bind has not been called")
 
+// CAV_DEBUG_SYNC=1 (debugging only; breaks graph capture): name every launch on stderr and wait for it
+static bool debug_sync() {
+    static const bool on = [] {
+        const char *e = getenv("CAV_DEBUG_SYNC");
+        return e && atoi(e) != 0;
+    }();
+    return on;
+}
+static cudaError_t debug_after(const char *name, cudaError_t ce) {
+    if (!debug_sync() || ce != cudaSuccess) return ce;
+    fprintf(stderr, "[cavoid] %s launched ... ", name);
+    fflush(stderr);
+    ce = cudaDeviceSynchronize();
+    fprintf(stderr, "%s\n", ce == cudaSuccess ? "done" : cudaGetErrorString(ce));
+    return ce;
+}
+
 #define CAV_CUDA(h, name, expr)                                                                \
     do {                                                                                       \
-        cudaError_t ce_ = (expr);                                                              \
+        cudaError_t ce_ = debug_after(name, (expr));                                           \
         if (ce_ != cudaSuccess) return fail(h, CAV_ERR_CUDA, name ": %s", cudaGetErrorString(ce_)); \
         (h)->launches++;                                                                       \
     } while (0)
 
 static int do_policy_move(cav_handle_t h, const float *ext, int phases, double dt, cudaStream_t st) {
     if (h->use_v2_policy) {
-        const cudaError_t ce = (h->cfg.precision == CAV_F64)
-                                   ? run_policy_move_v2<double>(h->bufs, h->pd, ext, phases, dt, h->sm_count, st)
-                                   : run_policy_move_v2<float>(h->bufs, h->pf, ext, phases, dt, h->sm_count, st);
+        const cudaError_t ce = debug_after(
+            "policy_move_v2", (h->cfg.precision == CAV_F64)
+                                  ? run_policy_move_v2<double>(h->bufs, h->pd, ext, phases, dt, h->sm_count, st)
+                                  : run_policy_move_v2<float>(h->bufs, h->pf, ext, phases, dt, h->sm_count, st));
         if (ce == cudaSuccess) {
             h->launches++;
             return CAV_OK;
@@ -342,10 +360,10 @@ static int do_pairwise_obs(cav_handle_t h, const uint8_t *mask, int obs_only, cu
     // 'time_to_impact' ordering (three-level real key) lives in the sub-warp-group kernel only, for every N
     if (h->use_tpa && h->cfg.agent_sorting_method != CAV_SORT_TIME_TO_IMPACT) {
         if (h->use_tpa_n) {  // compile-time-N specialisation when the configuration allows it
-            const cudaError_t ce = CAV_BY_PRECISION(
+            const cudaError_t ce = debug_after("pairwise_obs_tpa_n", CAV_BY_PRECISION(
                 h, (run_pairwise_obs_tpa_n<float, float>(h->bufs, h->pf, h->plan, wm, mask, obs_only, h->sm_count, st)),
                 (run_pairwise_obs_tpa_n<double, double>(h->bufs, h->pd, h->plan, wm, mask, obs_only, h->sm_count, st)),
-                (run_pairwise_obs_tpa_n<double, float>(h->bufs, h->pd, h->plan, wm, mask, obs_only, h->sm_count, st)));
+                (run_pairwise_obs_tpa_n<double, float>(h->bufs, h->pd, h->plan, wm, mask, obs_only, h->sm_count, st))));
             if (ce == cudaSuccess) {
                 h->launches++;
                 return CAV_OK;
@@ -405,7 +423,7 @@ int cav_generate_scenarios(cav_handle_t h, const cav_scenario_gen_t *gen, double
     CAV_CUDA(h, "generate_scenarios",
              run_generate_scenarios(rows, case_kind, num_scenarios, h->cfg.num_agents, gen->seed, gen->side_length[0],
                                     gen->side_length[1], gen->speed_bnds, gen->radius_bnds, 0.2 /* GETTING_CLOSE_RANGE,
-                                    CADRL/scripts/multi/global_var.py:8 */, (cudaStream_t)stream));
+                                    CADRL/scripts/multi/global_var.py:8 */, gen->random_heading, (cudaStream_t)stream));
     return CAV_OK;
 }
 

@@ -58,6 +58,6 @@ cudaError_t run_reset(const cav_buffers_t &bufs, const ResetParams &rp, const ui
 // device-side scenario banks (cav_scenario.cu)
 cudaError_t run_generate_scenarios(double *rows, int32_t *kind_out, int S, int N, uint64_t seed, double side_lo,
                                    double side_hi, const double speed_bnds[2], const double radius_bnds[2],
-                                   double close_range, cudaStream_t st);
+                                   double close_range, int random_heading, cudaStream_t st);
 
 }  // namespace cav

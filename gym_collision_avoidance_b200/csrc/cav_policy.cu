@@ -14,6 +14,11 @@
 //   * every loop of the solve is rolled: the whole kernel is a few KB of code;
 //   * one sqrt and one reciprocal per half-plane whatever branch of Agent.cpp:299-365 a lane is in
 //     (orca_line_shared), a branch-free linearProgram1 loop (lp1_flat);
+//   * measured and dropped (git history, commit "Warp-cooperative linearProgram2"): rounds in which every lane finds ITS
+//     next violated line and the owners' (i, j) line pairs are spread over lane groups with shuffle folds -- bit-identical
+//     on a CPU emulation of the warp, but 5 % SLOWER than the lane-private loops once those had their float64 spills
+//     removed (78.8 vs 74.7 us at 16384 x 10, all agents live): ~30 shuffles + 4 __syncwarp per round outweigh the
+//     ~3-of-30-lanes inefficiency of a loop whose body is software-pipelined four deep;
 //   * N > 10: the reference's kd-tree decides the neighbour order at exactly equal distances -- the environment's
 //     persistent agent permutation (`kd_order`) is re-partitioned by ONE lane per environment (cav_kdtree.cuh,
 //     operation for operation KdTree.cpp:47-111) while the other lanes wait at a __syncwarp, then every lane inserts
@@ -86,120 +91,6 @@ __device__ __forceinline__ R4<double> ld4_again<double>(const R4<double> *p) {
     asm volatile("ld.global.v2.f64 {%0,%1}, [%2];" : "=d"(a), "=d"(b) : "l"(p));
     asm volatile("ld.global.v2.f64 {%0,%1}, [%2+16];" : "=d"(c), "=d"(d) : "l"(p));
     return R4<double>{a, b, c, d};
-}
-
-#ifndef CAV_PM_COOP
-#define CAV_PM_COOP 1  // warp-cooperative linearProgram2 / linearProgram1 (0: every lane runs its own serial loops)
-#endif
-
-// linearProgram2 (Agent.cpp:550-581, closest-point mode) for all 32 lanes of a warp at once; lane L's half-planes are
-// lines[k * stride + L], k < nl (nl = 0 for lanes with nothing to solve: they only lend a hand).
-//
-// Why: with one thread per agent, linearProgram1 is SIMT poison -- ncu on the per-lane version: ~3 of 30 lanes violate a
-// given line, so the warp walked ~38 (i, j) line pairs per step at 10 % lane efficiency, 29 % of the kernel's
-// instructions, although the lanes together needed only ~100 pair evaluations (3 per lane).  Here the warp works in
-// ROUNDS: (1) every unfinished lane finds ITS next violated line i* against its current optimum (lanes are at different
-// i*: no waiting for the slowest index); (2) the lanes that found one -- the round's k owners -- each get a group of
-// G = 32 / 2^ceil(log2 k) lanes, and the group splits the owner's i* earlier lines j < i* among its lanes: each (i*, j)
-// pair yields one bound t on the line parameter, a pure min / max / or reduction (Agent.cpp:495-517), combined across the
-// group with shuffles; (3) the owner finishes linearProgram1 (clamp, new optimum or failure) and the next round starts.
-// Rounds = the largest number of linearProgram1 calls any lane makes (~3), not the number of distinct line indices (~8).
-// Same arithmetic per pair as the reference; only the ORDER of the min / max folds differs, which cannot change their
-// value (a lane-private serial loop and this one give bit-identical velocities in tests/test_gpu_*.py).
-// Returns nl on success, else the index of the line on which linearProgram1 failed (result = optimum before that line).
-__device__ __forceinline__ int lp2_coop(const float4 *lines, int stride, int lane, int nl, float radius, float ox, float oy,
-                                        float &rx, float &ry) {
-    if (fdot(ox, oy, ox, oy) > radius * radius) {
-        const float inv = 1.0f / sqrtf(fdot(ox, oy, ox, oy));
-        rx = (ox * inv) * radius;
-        ry = (oy * inv) * radius;
-    } else {
-        rx = ox;
-        ry = oy;
-    }
-    int cur = 0;      // lines [0, cur) are satisfied by (rx, ry) or already handled
-    int fail = nl;    // set to the failing line's index once linearProgram1 fails
-    const unsigned lt = (1u << lane) - 1u;
-#pragma unroll 1
-    for (;;) {
-        // (1) next violated line of this lane
-        int istar = nl;
-#pragma unroll 1
-        for (int i = cur; i < nl; ++i) {
-            const float4 li = lines[i * stride + lane];
-            if (fdet(li.z, li.w, li.x - rx, li.y - ry) > 0.0f) {
-                istar = i;
-                break;
-            }
-        }
-        const bool owner = istar < nl;
-        const unsigned m = __ballot_sync(0xffffffffu, owner);
-        if (m == 0u) break;
-        // owner prologue: linearProgram1 up to the loop (Agent.cpp:479-489)
-        float4 L = make_float4(0.f, 0.f, 1.f, 0.f);
-        float tLeft = 0.f, tRight = 0.f;
-        bool ok = true;
-        if (owner) {
-            L = lines[istar * stride + lane];
-            const float dotProduct = fdot(L.x, L.y, L.z, L.w);
-            const float discriminant = dotProduct * dotProduct + radius * radius - fdot(L.x, L.y, L.x, L.y);
-            ok = !(discriminant < 0.0f);
-            const float sqrtDiscriminant = sqrtf(discriminant);
-            tLeft = -dotProduct - sqrtDiscriminant;
-            tRight = -dotProduct + sqrtDiscriminant;
-        }
-        // (2) groups: k owners -> 2^lg lanes each
-        const int k = __popc(m);
-        const int lg = 5 - (k > 1 ? 32 - __clz(k - 1) : 0);  // log2 of the group size
-        const int grp = lane >> lg, sub = lane & ((1 << lg) - 1);
-        const int ol = (grp < k) ? (int)__fns(m, 0, grp + 1) : 0;  // lane of the grp-th owner
-        const int iS = __shfl_sync(0xffffffffu, istar, ol);
-        const float4 Lo = make_float4(__shfl_sync(0xffffffffu, L.x, ol), __shfl_sync(0xffffffffu, L.y, ol),
-                                      __shfl_sync(0xffffffffu, L.z, ol), __shfl_sync(0xffffffffu, L.w, ol));
-        float tl = -CUDART_INF_F, tr = CUDART_INF_F;
-        bool bad = false;
-        if (grp < k) {
-#pragma unroll 1
-            for (int j = sub; j < iS; j += (1 << lg)) {
-                const float4 lj = lines[j * stride + ol];
-                const float denominator = fdet(Lo.z, Lo.w, lj.z, lj.w);
-                const float numerator = fdet(lj.z, lj.w, Lo.x - lj.x, Lo.y - lj.y);
-                const bool parallel = fabsf(denominator) <= CAV_RVO_EPSILON;
-                bad = bad || (parallel && numerator < 0.0f);
-                const float t = numerator / denominator;
-                const float trn = min_keep(tr, t), tln = max_keep(tl, t);
-                tr = (!parallel && denominator >= 0.0f) ? trn : tr;
-                tl = (!parallel && !(denominator >= 0.0f)) ? tln : tl;
-            }
-        }
-        for (int off = (1 << lg) >> 1; off > 0; off >>= 1) {  // fold the group (warp-uniform trip count)
-            tr = min_keep(tr, __shfl_xor_sync(0xffffffffu, tr, off));
-            tl = max_keep(tl, __shfl_xor_sync(0xffffffffu, tl, off));
-            bad = bad || __shfl_xor_sync(0xffffffffu, bad ? 1 : 0, off) != 0;
-        }
-        // (3) owners collect their group's bounds (group = rank among the owners) and finish linearProgram1
-        const int src = (__popc(m & lt)) << lg;
-        const float gtr = __shfl_sync(0xffffffffu, tr, src & 31), gtl = __shfl_sync(0xffffffffu, tl, src & 31);
-        const bool gbad = __shfl_sync(0xffffffffu, bad ? 1 : 0, src & 31) != 0;
-        if (owner) {
-            tRight = min_keep(tRight, gtr);
-            tLeft = max_keep(tLeft, gtl);
-            if (!ok || gbad || tLeft > tRight) {
-                fail = istar;  // result stays the optimum before this line (Agent.cpp:574-577)
-                cur = nl;
-                nl = 0;        // this lane is finished
-            } else {
-                const float t = fdot(L.z, L.w, ox - L.x, oy - L.y);
-                const float tc = (t < tLeft) ? tLeft : ((t > tRight) ? tRight : t);
-                rx = L.x + tc * L.z;
-                ry = L.y + tc * L.w;
-                cur = istar + 1;
-            }
-        } else {
-            cur = nl;  // no violated line left
-        }
-    }
-    return fail;
 }
 
 template <typename T, int NT>
@@ -310,13 +201,8 @@ __global__ void __launch_bounds__(32 * CAV_PM_WARPS, CAV_PM_MINB)
             }
         }
         float nvx = 0.f, nvy = 0.f;
-        int lp_fail = 0;
-#if CAV_PM_COOP
-        lp_fail = lp2_coop(s_lines, LW, lane, nl, maxSpeed, prefx, prefy, nvx, nvy);  // the whole warp, converged
-#else
-        if (rvo) lp_fail = lp2_flat(SmemLines{s_lines + lane, LW}, nl, maxSpeed, prefx, prefy, false, nvx, nvy);
-#endif
         if (rvo) {
+            const int lp_fail = lp2_flat(SmemLines{s_lines + lane, LW}, nl, maxSpeed, prefx, prefy, false, nvx, nvy);
             if (lp_fail < nl) {  // infeasible: linearProgram3 (Agent.cpp:419-421)
                 Line projbuf[CT ? (NT > 2 ? NT - 1 : 2) : 31];
                 lp3_flat(SmemLines{s_lines + lane, LW}, nl, lp_fail, maxSpeed, LocalLines{projbuf}, nvx, nvy);

@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(64) k_generate_scenarios(double *__restrict__ 
 
 cudaError_t run_generate_scenarios(double *rows, int32_t *kind_out, int S, int N, uint64_t seed, double side_lo,
                                    double side_hi, const double speed_bnds[2], const double radius_bnds[2],
-                                   double close_range, cudaStream_t st) {
+                                   double close_range, int random_heading, cudaStream_t st) {
     GenParams p;
     p.S = S;
     p.N = N;
@@ -48,6 +48,7 @@ cudaError_t run_generate_scenarios(double *rows, int32_t *kind_out, int S, int N
     p.radius_hi = radius_bnds[1];
     p.close_range = close_range;
     p.seed = seed;
+    p.random_heading = random_heading;
     k_generate_scenarios<<<(S + 63) / 64, 64, 0, st>>>(rows, kind_out, p);
     return cudaGetLastError();
 }

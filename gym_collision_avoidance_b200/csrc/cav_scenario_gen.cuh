@@ -80,6 +80,7 @@ struct GenParams {
     int S, N;
     double side_lo, side_hi, speed_lo, speed_hi, radius_lo, radius_hi, close_range;
     uint64_t seed;
+    int random_heading;  // training mode: heading ~ U(-pi, pi) (test_cases.py:558-559) instead of toward the goal
 };
 
 struct V2 {
@@ -229,7 +230,8 @@ CAV_HD void ring_case(Philox &g, const GenParams &p, Rows &tc, bool swap) {
 }
 
 // One scenario: side draw + mixture (get_testcase_random -> generate_rand_test_case_multi), rows[N][CAV_BANK_ROW],
-// heading toward the goal (EVALUATE_MODE, test_cases.py:553-557).  Returns the case kind (0 swap, 1 circle, 2 random).
+// heading toward the goal (EVALUATE_MODE, test_cases.py:553-557) or, in training mode, drawn from U(-pi, pi) per agent
+// after the case like cadrl_test_case_to_agents does (:558-559).  Returns the case kind (0 swap, 1 circle, 2 random).
 CAV_HD inline int generate_scenario(double *rows, const GenParams &p, uint64_t scenario) {
     Philox g(p.seed, scenario);
     Rows tc{rows};
@@ -252,7 +254,8 @@ CAV_HD inline int generate_scenario(double *rows, const GenParams &p, uint64_t s
     }
     for (int i = 0; i < p.N; ++i) {
         double *r = tc.r + i * CAV_BANK_ROW;
-        r[6] = atan2(r[3] - r[1], r[2] - r[0]);
+        r[6] = p.random_heading ? (-3.14159265358979323846 + 2.0 * 3.14159265358979323846 * g.rand())
+                                : atan2(r[3] - r[1], r[2] - r[0]);
         r[7] = 0.0;
     }
     return kind;

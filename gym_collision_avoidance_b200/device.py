@@ -154,7 +154,7 @@ class Cavoid(object):
         self.launches += self.L.cav_last_launch_count(self._h)
 
     def generate_scenarios(self, bank, seed, side_length=None, speed_bnds=(0.5, 2.0), radius_bnds=(0.2, 0.8),
-                           stream=None):
+                           stream=None, random_heading=False):
         """Fill `bank.rows` on the device with reference-distributed random scenarios (cav_generate_scenarios).
         side_length = (lo, hi) of the uniform side draw; default: the reference's Config.TEST_CASE_ARGS."""
         n = self.c.num_agents
@@ -165,6 +165,7 @@ class Cavoid(object):
         g.side_length[0], g.side_length[1] = float(side_length[0]), float(side_length[1])
         g.speed_bnds[0], g.speed_bnds[1] = float(speed_bnds[0]), float(speed_bnds[1])
         g.radius_bnds[0], g.radius_bnds[1] = float(radius_bnds[0]), float(radius_bnds[1])
+        g.random_heading = int(bool(random_heading))
         if tuple(bank.rows.shape[1:]) != (n, abi.CAV_BANK_ROW) or bank.rows.dtype != torch.float64:
             raise abi.CavoidError("bank rows must be float64 [S, %d, %d]" % (n, abi.CAV_BANK_ROW))
         ck = getattr(bank, "case_kind", None)

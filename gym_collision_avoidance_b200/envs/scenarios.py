@@ -187,11 +187,12 @@ def default_side_length(num_agents, rng):
 
 
 def random_scenario_bank(num_scenarios, num_agents, seed=0, side_length=None, speed_bnds=(0.5, 2.0),
-                         radius_bnds=(0.2, 0.8)):
+                         radius_bnds=(0.2, 0.8), random_heading=False):
     """[S, N, 8] float64 bank rows ``[px, py, gx, gy, pref_speed, radius, heading, 0]``: scenario s is what the
     reference's ``get_testcase_random`` builds from the stream ``RandomState(seed)`` after s earlier scenarios (side
     length draw, then ``generate_rand_test_case_multi``), heading toward the goal (EVALUATE_MODE, reference
-    test_cases.py:553-557).  ``side_length`` fixes the side instead of drawing it (dense test banks)."""
+    test_cases.py:553-557) or -- ``random_heading``, the reference's training mode (:558-559) -- one ``uniform(-pi, pi)``
+    draw per agent after the case.  ``side_length`` fixes the side instead of drawing it (dense test banks)."""
     rng = np.random.RandomState(seed)
     out = np.zeros((num_scenarios, num_agents, 8))
     s = 0
@@ -203,5 +204,7 @@ def random_scenario_bank(num_scenarios, num_agents, seed=0, side_length=None, sp
             continue  # drop the diverged case, keep consuming the same stream
         out[s, :, :6] = tc
         out[s, :, 6] = np.arctan2(tc[:, 3] - tc[:, 1], tc[:, 2] - tc[:, 0])
+        if random_heading:
+            out[s, :, 6] = [rng.uniform(-np.pi, np.pi) for _ in range(num_agents)]
         s += 1
     return out

@@ -77,11 +77,13 @@ class VecCollisionAvoidanceEnv(object):
             self.bank.kinds = torch.from_numpy(np.ascontiguousarray(bank_kinds).view(np.int32).copy()).to(self.device)
             if bank_num_active is not None:
                 self.bank.num_active = torch.from_numpy(np.asarray(bank_num_active, np.int32)).to(self.device)
-            self.cav.generate_scenarios(self.bank, seed)
+            self.cav.generate_scenarios(self.bank, seed, random_heading=not config.EVALUATE_MODE)
         else:
             if scenario_bank is None:
                 S = num_scenarios or max(256, min(4096, self.num_envs))
-                scenario_bank = random_scenario_bank(S, self.num_agents, seed=seed)
+                # training mode (EVALUATE_MODE False): random initial headings like cadrl_test_case_to_agents
+                scenario_bank = random_scenario_bank(S, self.num_agents, seed=seed,
+                                                     random_heading=not config.EVALUATE_MODE)
             scenario_bank = np.asarray(scenario_bank, dtype=np.float64)
             S = scenario_bank.shape[0]
             if bank_kinds is None:
@@ -142,7 +144,7 @@ class VecCollisionAvoidanceEnv(object):
         stays valid); they take effect at the following resets."""
         if not hasattr(self.bank, "case_kind"):
             raise abi.CavoidError("regenerate_scenarios needs scenario_source='device'")
-        self.cav.generate_scenarios(self.bank, seed)
+        self.cav.generate_scenarios(self.bank, seed, random_heading=not self.config.EVALUATE_MODE)
 
     def reset(self):
         """Reset every environment (reference ``reset`` -> ``_get_obs``); returns ``(obs, {})``."""

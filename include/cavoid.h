@@ -253,7 +253,9 @@ int cav_create(const cav_config_t *cfg, cav_handle_t *out);
 /* Bytes of `real` for this handle (4 or 8). */
 size_t cav_real_bytes(cav_handle_t h);
 
-/* Scratch the library needs beyond cav_buffers_t (currently 0; kept so callers can pre-size). */
+/* Device scratch the library needs beyond cav_buffers_t: none -- every kernel works out of registers and its own shared
+ * memory, so this returns 0 for every configuration.  (SURVEY.md §8b lists the entry point; it stays so that a caller
+ * written against that list links, and so that a later kernel that does need scratch can ask for it.) */
 size_t cav_workspace_bytes(cav_handle_t h);
 
 /* Attaches caller-owned device columns (replaces the per-Agent Python attribute storage, agent.py:59-138). */
@@ -273,7 +275,9 @@ int cav_reset(cav_handle_t h, const uint8_t *env_mask, const cav_scenario_bank_t
 int cav_step(cav_handle_t h, const float *ext_actions, double dt, cav_stream_t stream);
 
 /* Per-phase entry points (unit parity against the oracle); cav_step == policy+move fused, then pairwise_obs,
- * then laserscan when observed.
+ * then laserscan when observed.  SURVEY.md §8b also sketches a `cav_k_done`: there is none, by design --
+ * _check_which_agents_done (env.py:514-553) needs exactly the flags the collision / reward pass has just computed, so it
+ * is the tail of cav_k_pairwise_obs (done + game_over written there) instead of one more launch and one more read of flags.
  *   cav_k_policy      : env.py:304-323 action selection (+ rvo2 doStep)        -> bufs.actions
  *   cav_k_dynamics    : env.py:326-327 Agent.take_action (agent.py:192-241) reading bufs.actions
  *   cav_k_pairwise_obs: env.py:394-512 collisions+rewards, OtherAgentsStatesSensor.sense
@@ -301,6 +305,9 @@ typedef struct cav_scenario_gen {
     double side_length[2]; /* side ~ U(lo, hi): Config.TEST_CASE_ARGS['side_length'] (config.py:56-59) */
     double speed_bnds[2];  /* config.py:54 */
     double radius_bnds[2]; /* config.py:55 */
+    int32_t random_heading; /* 0: initial heading toward the goal (Config.EVALUATE_MODE, test_cases.py:553-557);
+                             * 1: heading ~ U(-pi, pi) per agent (training mode, :558-559) */
+    int32_t reserved;
 } cav_scenario_gen_t;
 int cav_generate_scenarios(cav_handle_t h, const cav_scenario_gen_t *gen, double *rows, int32_t *case_kind,
                            int32_t num_scenarios, cav_stream_t stream);

@@ -41,6 +41,7 @@ void host_generate_scenarios(double *rows, int32_t *kind, int S, int N, uint64_t
     p.radius_hi = radius_hi;
     p.close_range = close_range;
     p.seed = seed;
+    p.random_heading = 0;
     for (int s = 0; s < S; ++s) kind[s] = generate_scenario(rows + (size_t)s * N * CAV_BANK_ROW, p, (uint64_t)s);
 }
 }

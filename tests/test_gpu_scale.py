@@ -169,6 +169,57 @@ def test_masked_reset_and_episode_stats_match_oracle():
     common.compare_states(got, hs, N, 1e-6, 1e-6, cols=("pv", "ht", "flags", "step_num", "obs"))
 
 
+@pytest.mark.parametrize("E,N,policy,laser,obs_f32", [(16384, 10, "RVO", False, True), (16384, 10, "RVO", False, False),
+                                                       (4096, 10, "RVO", False, True), (32768, 10, "noncoop", False, True),
+                                                       (1024, 20, "RVO", True, True), (8192, 20, "RVO", False, False)])
+def test_full_size_vs_oracle(E, N, policy, laser, obs_f32):
+    """BASELINE.json's configs at their FULL sizes (16384 x 10 RVO = the headline, configs[1] 4096 x 10, configs[2]
+    32768 x 10 NonCooperative, configs[3]'s per-GPU share 1024 x 20 RVO + LaserScanSensor 512 x 3, and 8192 x 20): reset
+    from the bank, then steps that each start from the oracle's state on both sides (teacher-forced: a free run lets
+    1-ulp libm differences pick different sides of head-on encounters) -- every environment and agent compared with the
+    oracle: flags / done / game_over / counters exact, float64 state 1e-9, float32 observation columns 2e-7 relative,
+    laser beams exact.  Steps are taken 0, 1 and ~40 steps into the episodes (agents reaching goals, collisions)."""
+    from gpu_common import GpuRunner
+    states = None
+    if laser:
+        states = ["is_learning", "num_other_agents", "dist_to_goal", "heading_ego_frame", "pref_speed", "radius",
+                  "other_agents_states", "laserscan"]
+    cfg = make_config(N, evaluate=True, use_static_map=laser, states_in_obs=states)
+    c = to_cav_config(cfg, E, N, precision="f64", track_aux=False, obs_f32=obs_f32)
+    rows = random_scenario_bank(512, N, seed=77)
+    bank = HostBank(rows, kinds=kinds_array(512, N, policy))
+    hs = HostState(c)
+    orc = Oracle(c)
+    orc.reset(hs, bank)
+    r = GpuRunner(c)
+    r.cav.reset(r.bank(bank))
+    state_cols = [k for k in hs.arrays if k not in ("obs", "reward", "stats", "episode", "kinds", "num_active")]
+    f32 = common.Tol(2e-7, 1e-7)
+
+    def check(got):
+        common.compare_states(got, hs, N, 1e-9, 1e-9, cols=state_cols)
+        if obs_f32:
+            assert got.obs.dtype == np.float32
+            common.assert_close("obs", got.obs, hs.obs, 2e-7, 1e-7)
+            common.assert_close("reward", got.reward, hs.reward, 2e-7, 1e-7)
+        else:
+            common.compare_states(got, hs, N, 1e-9, 1e-9, cols=("obs", "reward"))
+    check(r.download())
+    done_seen = coll_seen = 0
+    for s in range(44 if not laser else 14):
+        heavy = s in (0, 1, 2) or s >= (41 if not laser else 12)
+        if heavy:
+            r.upload(hs)
+        orc.step(hs)
+        if heavy:
+            r.cav.step()
+            check(r.download())
+            done_seen += int(((hs.flags & abi.CAV_FLAG_DONE) != 0).sum())
+            coll_seen += int(((hs.flags & abi.CAV_FLAG_IN_COLLISION) != 0).sum())
+    assert laser or (done_seen > 0 and (policy == "RVO" or coll_seen > 0))  # the late steps saw finished agents
+    r.cav.close()
+
+
 @pytest.mark.parametrize("E,N,policy,prec", [(32768, 10, "noncoop", "f32"), (16384, 10, "RVO", "f64")])
 def test_full_size_properties(E, N, policy, prec):
     """BASELINE configs[1]/[2] sizes: size-independent properties of one step.

@@ -117,3 +117,30 @@ def test_vec_env_runs_on_device_generated_scenarios():
     st = env.episode_stats()
     assert st["episodes"] > 0
     env.close()
+
+
+def test_training_mode_banks_draw_random_initial_headings():
+    """EVALUATE_MODE False: the reference draws heading ~ U(-pi, pi) per agent (test_cases.py:558-559) instead of pointing
+    the agent at its goal; both bank sources of VecCollisionAvoidanceEnv follow (device: one more Philox draw per agent)."""
+    N, E = 6, 64
+    cfg = make_config(N, evaluate=False)
+    for src in ("host", "device"):
+        env = VecCollisionAvoidanceEnv(E, cfg, N, policies=["learning"] + ["RVO"] * (N - 1), scenario_source=src, seed=9,
+                                       num_scenarios=2048)
+        rows = env.bank.rows.cpu().numpy()
+        hd = rows[..., 6].ravel()
+        to_goal = np.arctan2(rows[..., 3] - rows[..., 1], rows[..., 2] - rows[..., 0]).ravel()
+        assert (hd >= -np.pi).all() and (hd < np.pi).all()
+        assert np.mean(np.abs(hd - to_goal) < 1e-9) < 0.01, src
+        grid = np.linspace(-np.pi, np.pi, 200)
+        ks = np.abs(np.searchsorted(np.sort(hd), grid) / hd.size - (grid + np.pi) / (2 * np.pi)).max()
+        assert ks < 0.02, (src, ks)
+        env.reset()
+        got = env.state.ht[..., 0].cpu().numpy()
+        sidx = np.arange(E) % 2048
+        assert np.array_equal(got, rows[sidx, :, 6])
+        env.close()
+    ev = VecCollisionAvoidanceEnv(E, make_config(N, evaluate=True), N, scenario_source="device", seed=9, num_scenarios=256)
+    r = ev.bank.rows.cpu().numpy()
+    np.testing.assert_allclose(r[..., 6], np.arctan2(r[..., 3] - r[..., 1], r[..., 2] - r[..., 0]), atol=1e-12)
+    ev.close()
