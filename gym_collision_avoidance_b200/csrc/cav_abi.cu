@@ -29,6 +29,10 @@ struct cav_handle_s {
     bool use_tpa;  // one-thread-per-agent kernels (small N) instead of the sub-warp-group kernels
     bool use_v2_policy;  // k_policy_move_v2 (cav_policy.cu, thread per agent, N <= 32) instead of the sub-warp-group kernel
     bool use_tpa_n;  // ... and, where instantiated, the compile-time-N pairwise+obs kernel (CAV_TPA_N=0 disables)
+    // cav_step in two halves (see step_split): a helper stream forked off / joined back into the caller's stream
+    cudaStream_t aux;
+    cudaEvent_t ev_fork, ev_join;
+    int split_env;  // first environment of the second half (0 = no split)
     int launches;
     char err[512];
 };
@@ -245,6 +249,43 @@ int cav_create(const cav_config_t *cfg, cav_handle_t *out) {
         delete h;
         return rc;
     }
+    // Two halves: policy + move is 1.5 waves of CTAs and pairwise + obs 1.8 at 16384 x 10, so each kernel ends with the
+    // GPU half empty for a quarter of its run time (profiles/r02e_ncu_f64_16384x10.txt: waves_per_multiprocessor).
+    // Environments are independent, so cav_step enqueues policy(A) -> pairwise(A) on the caller's stream and
+    // policy(B) -> pairwise(B) on a helper stream forked from it with an event and joined back with another: pairwise(A)
+    // fills the SMs that policy(B)'s tail leaves idle.  Caller-visible semantics are unchanged (everything is ordered
+    // after the caller's earlier work and before its later work; graph capture records the fork / join as edges).
+    // CAV_STEP_SPLIT=0 disables it.
+    h->split_env = 0;
+    h->aux = nullptr;
+    {
+        bool want = cfg->num_envs >= 4096 && h->use_v2_policy && h->use_tpa_n && !h->has_laser &&
+                    cfg->agent_sorting_method != CAV_SORT_TIME_TO_IMPACT;
+        if (const char *ev = getenv("CAV_STEP_SPLIT")) want = want && atoi(ev) != 0;
+        if (want) {
+            int pw_tile = 0;
+            const WallMap nomap{};
+            const cudaError_t q = (cfg->precision == CAV_F64)
+                ? (cfg->obs_f32 ? run_pairwise_obs_tpa_n<double, float>(h->bufs, h->pd, h->plan, nomap, nullptr, 0, h->sm_count, nullptr, 0, -1, &pw_tile)
+                                : run_pairwise_obs_tpa_n<double, double>(h->bufs, h->pd, h->plan, nomap, nullptr, 0, h->sm_count, nullptr, 0, -1, &pw_tile))
+                : run_pairwise_obs_tpa_n<float, float>(h->bufs, h->pf, h->plan, nomap, nullptr, 0, h->sm_count, nullptr, 0, -1, &pw_tile);
+            const int pm_tile = policy_move_v2_tile_envs(cfg->num_agents);
+            if (q == cudaSuccess && pw_tile > 0 && pm_tile > 0) {
+                int a = pw_tile, b = pm_tile;
+                while (b) {
+                    const int t = a % b;
+                    a = b;
+                    b = t;
+                }
+                const int unit = pw_tile / a * pm_tile;  // lcm: a boundary both kernels' tiles respect
+                const int split = (cfg->num_envs / 2) / unit * unit;
+                if (split > 0 && cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking) == cudaSuccess &&
+                    cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+                    cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) == cudaSuccess)
+                    h->split_env = split;
+            }
+        }
+    }
     *out = h;
     return CAV_OK;
 }
@@ -392,6 +433,35 @@ static int do_laser(cav_handle_t h, const uint8_t *mask, cudaStream_t st) {
     return CAV_OK;
 }
 
+// cav_step as two independent halves of the environments on two streams (see cav_create)
+static int step_split(cav_handle_t h, const float *ext, double dt, cudaStream_t st) {
+    const int E = h->cfg.num_envs, sp = h->split_env;
+    const WallMap wm = wall_map(h);
+    auto policy = [&](cudaStream_t s, int e0, int e1) {
+        return (h->cfg.precision == CAV_F64) ? run_policy_move_v2<double>(h->bufs, h->pd, ext, 3, dt, h->sm_count, s, e0, e1)
+                                             : run_policy_move_v2<float>(h->bufs, h->pf, ext, 3, dt, h->sm_count, s, e0, e1);
+    };
+    auto pairwise = [&](cudaStream_t s, int e0, int e1) {
+        return CAV_BY_PRECISION(
+            h, (run_pairwise_obs_tpa_n<float, float>(h->bufs, h->pf, h->plan, wm, nullptr, 0, h->sm_count, s, e0, e1, nullptr)),
+            (run_pairwise_obs_tpa_n<double, double>(h->bufs, h->pd, h->plan, wm, nullptr, 0, h->sm_count, s, e0, e1, nullptr)),
+            (run_pairwise_obs_tpa_n<double, float>(h->bufs, h->pd, h->plan, wm, nullptr, 0, h->sm_count, s, e0, e1, nullptr)));
+    };
+    CAV_CUDA(h, "step fork", cudaEventRecord(h->ev_fork, st));
+    h->launches--;
+    CAV_CUDA(h, "step fork", cudaStreamWaitEvent(h->aux, h->ev_fork, 0));
+    h->launches--;
+    CAV_CUDA(h, "policy_move_v2 (second half)", policy(h->aux, sp, E));
+    CAV_CUDA(h, "policy_move_v2 (first half)", policy(st, 0, sp));
+    CAV_CUDA(h, "pairwise_obs_tpa_n (second half)", pairwise(h->aux, sp, E));
+    CAV_CUDA(h, "pairwise_obs_tpa_n (first half)", pairwise(st, 0, sp));
+    CAV_CUDA(h, "step join", cudaEventRecord(h->ev_join, h->aux));
+    h->launches--;
+    CAV_CUDA(h, "step join", cudaStreamWaitEvent(st, h->ev_join, 0));
+    h->launches--;
+    return CAV_OK;
+}
+
 int cav_reset(cav_handle_t h, const uint8_t *env_mask, const cav_scenario_bank_t *bank, const int32_t *scenario_idx,
               int accumulate_stats, cav_stream_t stream) {
     CAV_CHECK_READY(h, "cav_reset");
@@ -432,6 +502,7 @@ int cav_step(cav_handle_t h, const float *ext_actions, double dt, cav_stream_t s
     cudaStream_t st = (cudaStream_t)stream;
     if (!(dt > 0.0)) dt = h->cfg.dt;
     h->launches = 0;
+    if (h->split_env > 0 && h->use_v2_policy && h->use_tpa_n && !debug_sync()) return step_split(h, ext_actions, dt, st);
     int rc = do_policy_move(h, ext_actions, 3, dt, st);
     if (rc) return rc;
     rc = do_pairwise_obs(h, nullptr, 0, st);
@@ -479,6 +550,11 @@ const char *cav_last_error(cav_handle_t h) { return valid(h) ? h->err : g_err; }
 int cav_destroy(cav_handle_t h) {
     if (!valid(h)) return fail(nullptr, CAV_ERR_BAD_HANDLE, "cav_destroy: bad handle");
     h->magic = 0;
+    if (h->aux) {
+        cudaStreamDestroy(h->aux);
+        if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+        if (h->ev_join) cudaEventDestroy(h->ev_join);
+    }
     delete h;
     return CAV_OK;
 }

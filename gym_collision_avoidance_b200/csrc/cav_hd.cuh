@@ -76,16 +76,31 @@ CAV_HDI double philox_u01(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, 
 }
 
 // Map.world_coordinates_to_map_indices (Map.py:28-29,36-37): floor(origin -/+ v/cell).  v*inv_cell replaces the division
-// unless the result is within 1e-9 of an integer, where the exact quotient decides -- so the cell is the reference's
-// for EVERY input (tests/test_geometry_native_cpu.py: random and adversarial values against NumPy's expression).
+// unless the result is within 1e-6 of an integer, where the exact quotient decides -- so the cell is the reference's
+// for EVERY input (|v*inv_cell - v/cell| <= 2 ulp ~ 1e-13 for map-sized values, far inside the guard band;
+// tests/test_geometry_native_cpu.py: random and adversarial values against NumPy's expression).  The floor is two adds
+// against 1.5 * 2^52 and one fix-up -- plain float64 pipe work instead of FRND / rint on the quarter-rate XU pipe (ncu,
+// round-1 form of this function: 25 % of k_laserscan's instructions).  Valid for |c| < 2^51.
+CAV_HDI double floor_small(double c) {
+#ifdef __CUDA_ARCH__
+    const double r = __dsub_rn(__dadd_rn(c, 6755399441055744.0), 6755399441055744.0);  // round to nearest integer
+#else
+    const volatile double t = c + 6755399441055744.0;
+    const double r = t - 6755399441055744.0;
+#endif
+    return r > c ? r - 1.0 : r;
+}
 CAV_HDI double cell_coord(double origin, double v, double cell, double inv_cell, bool negate) {
     const double a = v * inv_cell;
     double c = negate ? (origin - a) : (origin + a);
-    if (fabs(c - rint(c)) < 1e-9 * fmax(1.0, fabs(c))) {
+    double fl = floor_small(c);
+    const double fr = c - fl;
+    if (!(fr > 1e-6 && fr < 1.0 - 1e-6)) {  // close to a cell border (or not finite / huge): decide with the exact quotient
         const double q = v / cell;
         c = negate ? (origin - q) : (origin + q);
+        fl = floor(c);
     }
-    return floor(c);
+    return fl;
 }
 
 }  // namespace cav

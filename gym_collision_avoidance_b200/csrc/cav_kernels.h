@@ -27,14 +27,16 @@ size_t tpa_smem_bytes(int N, int precision_f64, const ObsPlan &plan, int K);
 // compile-time-N, register-resident specialisation (cav_tpa_n.cu); cudaErrorNotSupported = use the generic kernel
 template <typename T, typename OT>
 cudaError_t run_pairwise_obs_tpa_n(const cav_buffers_t &bufs, const KParams<T> &p, const ObsPlan &plan, const WallMap &wm,
-                                   const uint8_t *env_mask, int obs_only, int sm_count, cudaStream_t st);
+                                   const uint8_t *env_mask, int obs_only, int sm_count, cudaStream_t st, int env0 = 0,
+                                   int env1 = -1, int *tile_envs = nullptr);
 
 
 // thread-per-agent policy + move kernel (cav_policy.cu): every N in [2, 32], kd-tree order for N > 10;
 // cudaErrorNotSupported otherwise (N = 1 and N > 32: the sub-warp-group kernel above)
 template <typename T>
 cudaError_t run_policy_move_v2(const cav_buffers_t &bufs, const KParams<T> &p, const float *ext, int phases, double dt,
-                               int sm_count, cudaStream_t st);
+                               int sm_count, cudaStream_t st, int env0 = 0, int env1 = -1);
+int policy_move_v2_tile_envs(int N);  // environments per CTA tile (a launch's env0 must be a multiple of it)
 
 struct LaserParams {
     int E, N, B, P, obs_len, obs_off;

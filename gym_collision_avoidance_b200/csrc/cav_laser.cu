@@ -173,8 +173,9 @@ __global__ void __launch_bounds__(256) k_laserscan(LaserPtrs b, LaserParams lp, 
             }
             // ---- 3b. beams: the pass's (agent, beam) pairs flattened over the CTA, no barrier between agents ----
             const int ntask = (a_end - a0) * lp.B;
+            const int bshift = (lp.B & (lp.B - 1)) == 0 ? 31 - __clz(lp.B) : -1;  // 512 beams: shift instead of divide
             for (int task = tid; task < ntask; task += blockDim.x) {
-                const int q = task / lp.B, bi = task - q * lp.B;
+                const int q = bshift >= 0 ? (task >> bshift) : task / lp.B, bi = task - q * lp.B;
                 const int h = a0 + q;
                 const uint32_t cnt = s_cnt[h];
                 OT *o = g_obs + (base + h) * (size_t)lp.obs_len + lp.obs_off;
@@ -205,10 +206,17 @@ __global__ void __launch_bounds__(256) k_laserscan(LaserPtrs b, LaserParams lp, 
                     const double ang = ang0 + hd;  // :66
                     double sa, ca;
                     sincos(ang, &sa, &ca);
-                    int cum = 0;
-                    int k_lo = 0, k_hi = lp.nr - 1;
-                    if (!has_static) {
-                        double tmin = 1e300, tmax = -1e300;
+                    // Samples worth testing, as a bit mask over the (<= 64) range samples: with a static map every sample;
+                    // otherwise only those inside some candidate's inflated disc -- the ray / disc chord [t0, t1] widened
+                    // by one sample on each side.  Everything between two discs is free space by construction, so the
+                    // march jumps over it (round 1 marched ONE window from the first disc's entry to the last one's exit).
+                    unsigned long long smask;
+                    const bool masked = !has_static && lp.nr <= 64;
+                    if (!masked) {
+                        smask = ~0ull;
+                    } else {
+                        smask = 0ull;
+                        const double inv_res = 1.0 / lp.range_res;
                         while (inr != 0ull) {
                             const int c = __ffsll((long long)inr) - 1;
                             inr &= inr - 1ull;
@@ -220,22 +228,22 @@ __global__ void __launch_bounds__(256) k_laserscan(LaserPtrs b, LaserParams lp, 
                             const double t1 = tca + thc;
                             if (t1 < 0.0) continue;
                             const double t0 = tca - thc;
-                            tmin = fmin(tmin, t0);
-                            tmax = fmax(tmax, t1);
-                        }
-                        if (tmax < tmin) {
-                            k_lo = 1;
-                            k_hi = 0;  // the beam cannot hit anything
-                        } else {
-                            const double inv_res = 1.0 / lp.range_res;
-                            const double a = floor((tmin - lp.min_range) * inv_res) - 1.0;
-                            const double bnd = ceil((tmax - lp.min_range) * inv_res) + 1.0;
-                            k_lo = a > 0.0 ? (int)a : 0;
-                            k_hi = bnd < (double)(lp.nr - 1) ? (int)bnd : lp.nr - 1;
+                            const double a = floor((t0 - lp.min_range) * inv_res) - 1.0;
+                            const double bnd = ceil((t1 - lp.min_range) * inv_res) + 1.0;
+                            const int k0 = a > 0.0 ? (int)a : 0;
+                            const int k1 = bnd < (double)(lp.nr - 1) ? (int)bnd : lp.nr - 1;
+                            if (k1 >= k0) smask |= ((k1 - k0 >= 63) ? ~0ull : ((1ull << (k1 - k0 + 1)) - 1ull)) << k0;
                         }
                     }
+                    int first = -1;
+                    bool second = false;
+                    int k = 0;
 #pragma unroll 1
-                    for (int k = k_lo; k <= k_hi; ++k) {
+                    while (masked ? (smask != 0ull) : (k < lp.nr)) {
+                        if (masked) {
+                            k = __ffsll((long long)smask) - 1;
+                            smask &= smask - 1ull;
+                        }
                         const double rk = lp.min_range + (double)k * lp.range_res;  // np.arange (:39)
                         const double x = px + rk * ca, y = py + rk * sa;            // :70-72
                         const double fx = cell_coord(lp.origin0, y, lp.cell, lp.inv_cell, true);
@@ -249,12 +257,20 @@ __global__ void __launch_bounds__(256) k_laserscan(LaserPtrs b, LaserParams lp, 
                                 if (dc * dc + dr * dr < rr2) hit = 0;
                             }
                         }
-                        cum += hit;
-                        if (cum == 1) kstar = k;  // :78-82: the LAST index whose cumulative hit count is 1
-                        if (cum >= 2) break;
+                        // :78-82: the range is the LAST index whose cumulative hit count is 1 -- the sample just before the
+                        // second hit (skipped samples are misses and do not change the count), or the last sample of the beam
+                        if (hit) {
+                            if (first < 0) {
+                                first = k;
+                            } else {
+                                kstar = k - 1;
+                                second = true;
+                                break;
+                            }
+                        }
+                        if (!masked) ++k;
                     }
-                    // a single hit inside the window keeps cumsum == 1 up to the last range sample (:78-82)
-                    if (cum == 1) kstar = lp.nr - 1;
+                    if (first >= 0 && !second) kstar = lp.nr - 1;
                 }
                 const double rng = kstar >= 0 ? lp.min_range + (double)kstar * lp.range_res : lp.max_range;
                 if (cnt == 0u) {  // first measurement fills every row (:84-85)

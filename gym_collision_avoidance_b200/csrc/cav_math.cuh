@@ -134,8 +134,11 @@ CAV_HDI T pymod(T a, T b) {
 }
 
 // Dynamics.update_ego_frame (dynamics/Dynamics.py:24-41) + Agent.get_ref (agent.py:329-349).
+// vel_ego_frame (vex, vey) is only ever stored in the optional aux0 column: with want_vel_ego == false its sqrt + sin +
+// cos are skipped (vex = vey = 0), everything else is unchanged.
 template <typename T>
-CAV_HDI void update_ego(const R4<T> &pv, const R4<T> &goal, T heading, R4<T> &ego, T &vex, T &vey) {
+CAV_HDI void update_ego(const R4<T> &pv, const R4<T> &goal, T heading, R4<T> &ego, T &vex, T &vey,
+                        bool want_vel_ego = true) {
     const T gdx = goal.x - pv.x, gdy = goal.y - pv.y;
     const T dist = M<T>::sqrt_(gdx * gdx + gdy * gdy);
     T prx, pry;
@@ -148,9 +151,13 @@ CAV_HDI void update_ego(const R4<T> &pv, const R4<T> &goal, T heading, R4<T> &eg
     }
     const T ang = M<T>::atan2_(pry, prx);
     const T he = wrap<T>(heading - ang);
-    const T cur_speed = M<T>::sqrt_(pv.z * pv.z + pv.w * pv.w);
-    vex = cur_speed * M<T>::cos_(he);
-    vey = cur_speed * M<T>::sin_(he);
+    vex = (T)0;
+    vey = (T)0;
+    if (want_vel_ego) {
+        const T cur_speed = M<T>::sqrt_(pv.z * pv.z + pv.w * pv.w);
+        vex = cur_speed * M<T>::cos_(he);
+        vey = cur_speed * M<T>::sin_(he);
+    }
     ego.x = dist;
     ego.y = he;
     ego.z = prx;

@@ -101,7 +101,7 @@ CAV_HDI void tpa_move(const TpaBuffers &b, const KParams<T> &p, size_t gi, R4<T>
         }
         R4<T> ego;
         T vex, vey;
-        update_ego<T>(pv, gl, ht.x, ego, vex, vey);  // agent.py:227
+        update_ego<T>(pv, gl, ht.x, ego, vex, vey, b.aux0 != nullptr);  // agent.py:227
         if (b.aux0) st4(reinterpret_cast<R4<T> *>(b.aux0) + gi, R4<T>{speed_out, dhead_out, vex, vey});
         const int sn = b.step_num[gi];
         if (p.store_history && b.history && sn < p.history_len) {  // agent.py:257-260,275-289

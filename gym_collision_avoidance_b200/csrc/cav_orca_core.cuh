@@ -129,6 +129,9 @@ CAV_HDI bool lp1_flat(const Lines &lines, int lineNo, const Line &L, float radiu
     return true;
 }
 
+#ifndef CAV_LP2_JUMP
+#define CAV_LP2_JUMP 0  // 1: lanes re-converge on their k-th linearProgram1 call instead of on the line index (A/B switch)
+#endif
 // linearProgram2 (Agent.cpp:550-581) over lp1_flat; returns n on success, else the index of the failing line
 template <typename Lines>
 CAV_HDI int lp2_flat(const Lines &lines, int n, float radius, float ox, float oy, bool directionOpt, float &rx, float &ry) {
@@ -143,6 +146,11 @@ CAV_HDI int lp2_flat(const Lines &lines, int n, float radius, float ox, float oy
         rx = ox;
         ry = oy;
     }
+    // The reference walks the lines in order and runs linearProgram1 on every violated one (default below).  The alternative
+    // shape "skip to MY next violated line, then linearProgram1 on it" makes the lanes of a warp re-converge on their k-th
+    // linearProgram1 call instead of on the line index -- fewer calls per warp (~3 instead of ~8 of 9 at N = 10) but each as
+    // long as the largest index among the lanes: measured 77.5 vs 74.8 us at 16384 x 10 (profiles/r02f_ab.txt), so it stays off.
+#if !CAV_LP2_JUMP
 #pragma unroll 1
     for (int i = 0; i < n; ++i) {
         const Line li = lines.get(i);
@@ -156,6 +164,27 @@ CAV_HDI int lp2_flat(const Lines &lines, int n, float radius, float ox, float oy
         }
     }
     return n;
+#else
+    int i = 0;
+#pragma unroll 1
+    for (;;) {
+        Line li = Line{0.f, 0.f, 1.f, 0.f};
+#pragma unroll 1
+        for (; i < n; ++i) {
+            li = lines.get(i);
+            if (fdet(li.dx, li.dy, li.px - rx, li.py - ry) > 0.0f) break;
+        }
+        if (i >= n) break;
+        const float tx = rx, ty = ry;
+        if (!lp1_flat(lines, i, li, radius, ox, oy, directionOpt, rx, ry)) {
+            rx = tx;
+            ry = ty;
+            return i;
+        }
+        ++i;
+    }
+    return n;
+#endif
 }
 
 // linearProgram3 (Agent.cpp:583-630, numObstLines == 0); the projected lines go to `proj` (thread-private slots)

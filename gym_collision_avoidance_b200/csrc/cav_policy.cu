@@ -96,7 +96,7 @@ __device__ __forceinline__ R4<double> ld4_again<double>(const R4<double> *p) {
 template <typename T, int NT>
 __global__ void __launch_bounds__(32 * CAV_PM_WARPS, CAV_PM_MINB)
     k_policy_move_v2(TpaBuffers b, KParams<T> p, const float *__restrict__ ext, uint8_t *__restrict__ kd_order, int phases,
-                     T dt, int ntiles, PmLayout rl) {
+                     T dt, int tile0, int ntiles, PmLayout rl) {
     constexpr bool CT = NT > 0;
     constexpr PmLayout cl = pm_layout(CT ? NT : 32, false);
     const int N = CT ? NT : rl.N;
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(32 * CAV_PM_WARPS, CAV_PM_MINB)
     const int el = lane / N, a = lane - el * N;  // environment within the warp, agent within the environment
     const int eb = el * N;
 
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int tile = tile0 + blockIdx.x; tile < ntiles; tile += gridDim.x) {  // tiles [tile0, ntiles) of this launch
         const int ew0 = (tile * CAV_PM_WARPS + warp) * EPW;
         const int e = ew0 + el;
         const bool have = lane < LW && e < p.E;
@@ -255,12 +255,16 @@ __global__ void __launch_bounds__(32 * CAV_PM_WARPS, CAV_PM_MINB)
     }
 }
 
+// Environments [env0, env1) (env0 a multiple of policy_move_v2_tile_envs); env1 < 0 = all.
 template <typename T, int NT>
 static cudaError_t launch_v2(const cav_buffers_t &bufs, const KParams<T> &p, const float *ext, int phases, double dt,
-                             int sm_count, cudaStream_t st) {
+                             int sm_count, cudaStream_t st, int env0, int env1) {
     const PmLayout L = pm_layout(p.N, NT == 0);
     const int epb = CAV_PM_WARPS * L.EPW;
-    const int ntiles = (p.E + epb - 1) / epb;
+    if (env1 < 0 || env1 > p.E) env1 = p.E;
+    const int tile0 = env0 / epb;
+    const int ntiles = (env1 + epb - 1) / epb;  // one past the last tile of this launch
+    if (ntiles <= tile0) return cudaSuccess;
     const size_t smem = (size_t)CAV_PM_WARPS * L.warp_bytes;
     auto kern = k_policy_move_v2<T, NT>;
     if (smem > 48 * 1024) {
@@ -268,18 +272,20 @@ static cudaError_t launch_v2(const cav_buffers_t &bufs, const KParams<T> &p, con
         if (e != cudaSuccess) return e;
     }
     const int cap = sm_count * 32;
-    const int grid = ntiles < cap ? ntiles : cap;
-    kern<<<grid, 32 * CAV_PM_WARPS, smem, st>>>(make_tpa(bufs), p, ext, bufs.kd_order, phases, (T)dt, ntiles, L);
+    const int grid = (ntiles - tile0) < cap ? (ntiles - tile0) : cap;
+    kern<<<grid, 32 * CAV_PM_WARPS, smem, st>>>(make_tpa(bufs), p, ext, bufs.kd_order, phases, (T)dt, tile0, ntiles, L);
     return cudaGetLastError();
 }
 
 // every N in [2, 32]; cudaErrorNotSupported otherwise (N = 1 and N > 32 take the sub-warp-group kernel)
+int policy_move_v2_tile_envs(int N) { return CAV_PM_WARPS * pm_layout(N, N > 10).EPW; }
+
 template <typename T>
 cudaError_t run_policy_move_v2(const cav_buffers_t &bufs, const KParams<T> &p, const float *ext, int phases, double dt,
-                               int sm_count, cudaStream_t st) {
+                               int sm_count, cudaStream_t st, int env0, int env1) {
     switch (p.N) {
 #define CAV_CASE(NN) \
-    case NN: return launch_v2<T, NN>(bufs, p, ext, phases, dt, sm_count, st);
+    case NN: return launch_v2<T, NN>(bufs, p, ext, phases, dt, sm_count, st, env0, env1);
         CAV_CASE(2)
         CAV_CASE(3)
         CAV_CASE(4)
@@ -292,13 +298,13 @@ cudaError_t run_policy_move_v2(const cav_buffers_t &bufs, const KParams<T> &p, c
 #undef CAV_CASE
         default: break;
     }
-    if (p.N > 10 && p.N <= 32) return launch_v2<T, 0>(bufs, p, ext, phases, dt, sm_count, st);
+    if (p.N > 10 && p.N <= 32) return launch_v2<T, 0>(bufs, p, ext, phases, dt, sm_count, st, env0, env1);
     return cudaErrorNotSupported;
 }
 
 template cudaError_t run_policy_move_v2<float>(const cav_buffers_t &, const KParams<float> &, const float *, int, double,
-                                               int, cudaStream_t);
+                                               int, cudaStream_t, int, int);
 template cudaError_t run_policy_move_v2<double>(const cav_buffers_t &, const KParams<double> &, const float *, int, double,
-                                                int, cudaStream_t);
+                                                int, cudaStream_t, int, int);
 
 }  // namespace cav

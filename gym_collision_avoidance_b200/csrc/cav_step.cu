@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(512) k_policy_move(DevBuffers b, KParams<T> p,
                     }
                     R4<T> ego;
                     T vex, vey;
-                    update_ego<T>(pv, gl, ht.x, ego, vex, vey);  // agent.py:227
+                    update_ego<T>(pv, gl, ht.x, ego, vex, vey, b.aux0 != nullptr);  // agent.py:227
                     if (b.aux0) st4(reinterpret_cast<R4<T> *>(b.aux0) + gi, R4<T>{speed_out, dhead_out, vex, vey});
                     const int sn = b.step_num[gi];
                     if (p.store_history && b.history && sn < p.history_len) {  // agent.py:257-260,275-289

@@ -90,7 +90,7 @@ template <typename T, int NT, typename OT>
 __global__ void __launch_bounds__(32 * TpaNShape<T, NT, OT>::WARPS, (TpaNBounds<T>::MINB * 4) / TpaNShape<T, NT, OT>::WARPS)
     k_pairwise_obs_tpa_n(TpaBuffers b, KParams<T> p, WallMap wm,
                                                               const uint8_t *__restrict__ env_mask, int obs_only,
-                                                              int ntiles) {
+                                                              int tile0, int ntiles) {
     using S = TpaNShape<T, NT, OT>;
     constexpr int NO = S::NO, EPW = S::EPW, LW = S::LW, CL = S::CL, WS = S::WS, RA = S::RA;
     constexpr int KSHIFT = KeyCodec<T>::PB + 6;
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(32 * TpaNShape<T, NT, OT>::WARPS, (TpaNBounds<
     const int el = lane / NT, h = lane - el * NT;  // env within the warp, agent within the env
     const int eb = el * NT;
 
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int tile = tile0 + blockIdx.x; tile < ntiles; tile += gridDim.x) {  // tiles [tile0, ntiles) of this launch
         const int ew0 = (tile * S::WARPS + warp) * EPW;  // first environment of this warp
         const int e = ew0 + el;
         const bool have = lane < LW && e < p.E;
@@ -409,27 +409,36 @@ static bool standard_layout(const ObsPlan &plan, const KParams<float> *, int N, 
 
 template <typename T, int NT, typename OT>
 static cudaError_t launch_n(const cav_buffers_t &bufs, const KParams<T> &p, const WallMap &wm, const uint8_t *env_mask,
-                            int obs_only, int sm_count, cudaStream_t st) {
+                            int obs_only, int sm_count, cudaStream_t st, int env0, int env1, int *tile_envs) {
     using S = TpaNShape<T, NT, OT>;
-    const int ntiles = (p.E + S::EPB - 1) / S::EPB;
+    if (tile_envs) {  // query only: environments per tile of this instantiation
+        *tile_envs = S::EPB;
+        return cudaSuccess;
+    }
+    if (env1 < 0 || env1 > p.E) env1 = p.E;
+    const int tile0 = env0 / S::EPB;
+    const int ntiles = (env1 + S::EPB - 1) / S::EPB;
+    if (ntiles <= tile0) return cudaSuccess;
     const size_t smem = S::WARP_BYTES * S::WARPS;
     if (smem > 48 * 1024) {  // per device, so not cached in a process-wide flag (no current shape needs it: <= 38.4 KB)
         cudaError_t e = cudaFuncSetAttribute(k_pairwise_obs_tpa_n<T, NT, OT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    const int grid = ntiles < sm_count * 16 ? ntiles : sm_count * 16;
-    k_pairwise_obs_tpa_n<T, NT, OT><<<grid, 32 * S::WARPS, smem, st>>>(make_tpa(bufs), p, wm, env_mask, obs_only, ntiles);
+    const int grid = (ntiles - tile0) < sm_count * 16 ? (ntiles - tile0) : sm_count * 16;
+    k_pairwise_obs_tpa_n<T, NT, OT><<<grid, 32 * S::WARPS, smem, st>>>(make_tpa(bufs), p, wm, env_mask, obs_only, tile0, ntiles);
     return cudaGetLastError();
 }
 
 // Returns cudaErrorNotSupported when no specialisation applies (the caller then runs the generic kernel).
+// env range [env0, env1) (env0 a multiple of the tile; env1 < 0 = all); tile_envs != nullptr only queries the tile size
 template <typename T, typename OT>
 cudaError_t run_pairwise_obs_tpa_n(const cav_buffers_t &bufs, const KParams<T> &p, const ObsPlan &plan, const WallMap &wm,
-                                   const uint8_t *env_mask, int obs_only, int sm_count, cudaStream_t st) {
+                                   const uint8_t *env_mask, int obs_only, int sm_count, cudaStream_t st, int env0, int env1,
+                                   int *tile_envs) {
     if (!standard_layout(plan, nullptr, p.N, p.K, p.obs_len, p.sorting)) return cudaErrorNotSupported;
     switch (p.N) {
 #define CAV_CASE(NN) \
-    case NN: return launch_n<T, NN, OT>(bufs, p, wm, env_mask, obs_only, sm_count, st);
+    case NN: return launch_n<T, NN, OT>(bufs, p, wm, env_mask, obs_only, sm_count, st, env0, env1, tile_envs);
         CAV_CASE(2)
         CAV_CASE(3)
         CAV_CASE(4)
@@ -444,10 +453,10 @@ cudaError_t run_pairwise_obs_tpa_n(const cav_buffers_t &bufs, const KParams<T> &
 }
 
 template cudaError_t run_pairwise_obs_tpa_n<float, float>(const cav_buffers_t &, const KParams<float> &, const ObsPlan &,
-                                                          const WallMap &, const uint8_t *, int, int, cudaStream_t);
+                                                          const WallMap &, const uint8_t *, int, int, cudaStream_t, int, int, int *);
 template cudaError_t run_pairwise_obs_tpa_n<double, double>(const cav_buffers_t &, const KParams<double> &, const ObsPlan &,
-                                                            const WallMap &, const uint8_t *, int, int, cudaStream_t);
+                                                            const WallMap &, const uint8_t *, int, int, cudaStream_t, int, int, int *);
 template cudaError_t run_pairwise_obs_tpa_n<double, float>(const cav_buffers_t &, const KParams<double> &, const ObsPlan &,
-                                                           const WallMap &, const uint8_t *, int, int, cudaStream_t);
+                                                           const WallMap &, const uint8_t *, int, int, cudaStream_t, int, int, int *);
 
 }  // namespace cav

@@ -16,8 +16,11 @@
  *     cav_last_error(h) returns a human-readable message for the last failure on that handle.
  *   - all device pointers are BORROWED (e.g. torch tensor.data_ptr()); the library never frees them.
  *     Vector columns (pv / goal / ht / ego / aux*) and obs must be 16-byte aligned.
- *   - all work is enqueued on the caller's CUDA stream; no implicit synchronisation, no host allocation and
- *     no host<->device copy on the step path, so a step can be captured into a CUDA graph.
+ *   - all work is ordered on the caller's CUDA stream; no implicit synchronisation, no host allocation and
+ *     no host<->device copy on the step path, so a step can be captured into a CUDA graph.  (cav_step may run half of the
+ *     environments on a library-owned helper stream that is forked from the caller's stream with an event and joined back
+ *     into it before cav_step returns to the stream's next operation: invisible to the caller, graph capture records it
+ *     as a fork / join; CAV_STEP_SPLIT=0 in the environment disables it.)
  *   - a handle is bound to the CUDA device that was current at cav_create; use it from one thread at a time.
  *     Multi-GPU = one handle per device / rank (environments are independent; no collective per step).
  *   - `real` below means float when cfg.precision == CAV_F32 and double when CAV_F64.  CAV_F64 reproduces the
