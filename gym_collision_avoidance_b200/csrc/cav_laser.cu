@@ -53,6 +53,10 @@ __global__ void __launch_bounds__(256) k_laserscan(LaserPtrs b, LaserParams lp, 
     // per agent of the pass: the other agents its beams can reach, compacted in agent order, [APC][N]
     LaserCand *s_cand = reinterpret_cast<LaserCand *>(s_ncand + CAV_MAX_AGENTS);
     short2 *s_brange = reinterpret_cast<short2 *>(s_cand + (size_t)APC * lp.N);  // beams [lo, hi] per candidate
+    // per agent of the pass: which beams have ANY candidate in range (bit per beam) -- three quarters of the beams of a
+    // 20-agent scene have none and skip the candidate walk altogether
+    const int bwords = (lp.B + 31) >> 5;
+    uint32_t *s_bany = reinterpret_cast<uint32_t *>(s_brange + (size_t)APC * lp.N);  // [APC][bwords]
 
     const int tid = threadIdx.x;
     const int N = lp.N;
@@ -117,6 +121,8 @@ __global__ void __launch_bounds__(256) k_laserscan(LaserPtrs b, LaserParams lp, 
             // then looks at a candidate's float64 geometry only if its index is in range.
             if (!has_static) {
                 const float inv_step = lp.ang_step > 0.0 ? (float)(1.0 / lp.ang_step) : 0.f;
+                for (int k = tid; k < (a_end - a0) * bwords; k += blockDim.x) s_bany[k] = 0u;
+                __syncthreads();
                 for (int q = warp; q < a_end - a0; q += nwarps) {
                     const int h = a0 + q;
                     const double px = s_px[h], py = s_py[h];
@@ -164,6 +170,10 @@ __global__ void __launch_bounds__(256) k_laserscan(LaserPtrs b, LaserParams lp, 
                             const int pos = q * N + nc + __popc(m & ((1u << lane) - 1u));
                             s_cand[pos] = LaserCand{ox, oy, dd, R * R};
                             s_brange[pos] = make_short2((short)blo, (short)bhi);
+                            for (int w = blo >> 5; w <= (bhi >> 5); ++w) {  // mark beams [blo, bhi]
+                                const int lo = max(blo, w << 5) & 31, hi = min(bhi, (w << 5) + 31) & 31;
+                                atomicOr(&s_bany[q * bwords + w], (hi == 31 ? ~0u : ((2u << hi) - 1u)) & ~((1u << lo) - 1u));
+                            }
                         }
                         nc += __popc(m);
                     }
@@ -192,8 +202,9 @@ __global__ void __launch_bounds__(256) k_laserscan(LaserPtrs b, LaserParams lp, 
                 const short2 *brange = s_brange + q * N;
                 // candidates whose beam range holds this beam, as a bit mask over the compacted list (<= 63 entries)
                 unsigned long long inr = 0ull;
+                const bool any = has_static ? false : ((s_bany[q * bwords + (bi >> 5)] >> (bi & 31)) & 1u) != 0u;
 #pragma unroll 1
-                for (int c = 0; c < ncand; ++c) {
+                for (int c = 0; any && c < ncand; ++c) {
                     const short2 br = brange[c];
                     if (bi >= br.x && bi <= br.y) inr |= 1ull << c;
                 }
@@ -305,7 +316,7 @@ cudaError_t run_laserscan(const cav_buffers_t &bufs, const LaserParams &lp, cons
     p.static_map_bits = bufs.static_map_bits;
     const int APC = lp.N < 32 ? lp.N : 32;  // agents per pass: candidate records [APC][N] x 36 B <= 72 KB
     const size_t smem = (((size_t)lp.rows * lp.wpr * 4 + 15) & ~(size_t)15) + CAV_MAX_AGENTS * (4 * 8 + 5 * 4) +
-                        (size_t)APC * lp.N * (sizeof(LaserCand) + sizeof(short2)) + 64;
+                        (size_t)APC * lp.N * (sizeof(LaserCand) + sizeof(short2)) + (size_t)APC * ((lp.B + 31) / 32) * 4 + 64;
     auto kern = k_laserscan<T, OT>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
