@@ -4,10 +4,12 @@ N=${1:-8}; TAG=${2:-r02}
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
 timeout 300 $TR bench.py --gpus $N --steps 20 --warmup 5 --no-cpu-baseline 2>gpurun_out/${TAG}_bench_${N}gpu.err | tail -1 > gpurun_out/${TAG}_bench_${N}gpu.json
+if [ -n "$CAV_MULTI_FULL" ]; then
 timeout 300 $TR bench.py --gpus $N --steps 20 --warmup 5 --no-cpu-baseline --no-numa 2>/dev/null | tail -1 > gpurun_out/${TAG}_bench_${N}gpu_nonuma.json
+fi
 if [ "$N" = "8" ]; then
   timeout 300 $TR bench.py --gpus $N --steps 20 --warmup 5 --no-cpu-baseline --envs 1024 --agents 20 --laser --history 0 2>/dev/null | tail -1 > gpurun_out/${TAG}_bench_c4_${N}gpu.json
-  timeout 400 $TR tools/sweep.py --agents 2,8,32 --envs 4096,32768 --steps 8 2>/dev/null | grep '^{' > gpurun_out/${TAG}_sweep_${N}gpu.jsonl
+  [ -n "$CAV_MULTI_FULL" ] && timeout 400 $TR tools/sweep.py --agents 2,8,32 --envs 4096,32768 --steps 8 2>/dev/null | grep '^{' > gpurun_out/${TAG}_sweep_${N}gpu.jsonl
 fi
 python - <<PY
 import json
