@@ -109,7 +109,7 @@ class CavScenarioGen(ctypes.Structure):
 EXPORTED_SYMBOLS = [
     "cav_abi_version", "cav_create", "cav_real_bytes", "cav_workspace_bytes", "cav_bind", "cav_reset", "cav_step",
     "cav_k_policy", "cav_k_dynamics", "cav_k_pairwise_obs", "cav_k_laserscan", "cav_k_observe",
-    "cav_generate_scenarios", "cav_last_launch_count",
+    "cav_generate_scenarios", "cav_last_launch_count", "cav_env_schedule",
     "cav_last_error", "cav_destroy",
 ]
 
@@ -162,6 +162,8 @@ def load_library(path=None):
     L.cav_generate_scenarios.restype = ctypes.c_int
     L.cav_generate_scenarios.argtypes = [h, ctypes.POINTER(CavScenarioGen), _vp, _vp, ctypes.c_int32, _vp]
     L.cav_last_launch_count.argtypes = [h]
+    L.cav_env_schedule.restype = ctypes.c_int
+    L.cav_env_schedule.argtypes = [h, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     L.cav_last_error.restype = ctypes.c_char_p
     L.cav_last_error.argtypes = [h]
     L.cav_destroy.restype = ctypes.c_int

@@ -29,10 +29,15 @@ struct cav_handle_s {
     bool use_tpa;  // one-thread-per-agent kernels (small N) instead of the sub-warp-group kernels
     bool use_v2_policy;  // k_policy_move_v2 (cav_policy.cu, thread per agent, N <= 32) instead of the sub-warp-group kernel
     bool use_tpa_n;  // ... and, where instantiated, the compile-time-N pairwise+obs kernel (CAV_TPA_N=0 disables)
-    // cav_step in two halves (see step_split): a helper stream forked off / joined back into the caller's stream
-    cudaStream_t aux;
-    cudaEvent_t ev_fork, ev_join;
-    int split_env;  // first environment of the second half (0 = no split)
+    // cav_step in 2..4 env ranges (see step_split): helper streams forked off / joined back into the caller's stream
+    cudaStream_t aux[3];
+    cudaEvent_t ev_fork, ev_join[3];
+    int split_parts;   // number of env ranges (0 = no split)
+    int split_at[5];   // range k = [split_at[k], split_at[k + 1])
+    // environment scheduling of k_policy_move_v2 (cav_policy.cu, EnvSchedule): the only device memory the library owns
+    EnvSchedule sched;
+    cudaStream_t sort_stream;
+    cudaEvent_t ev_policy[4], ev_sorted;
     int launches;
     char err[512];
 };
@@ -151,6 +156,18 @@ extern "C" {
 
 int cav_abi_version(void) { return CAV_ABI_VERSION; }
 
+// the environment ranges the schedule is sorted in: cav_step's launch ranges (one range without the split)
+static void sched_ranges(cav_handle_t h, int *at, int *n) {
+    if (h->split_parts > 1) {
+        *n = h->split_parts;
+        for (int k = 0; k <= h->split_parts; ++k) at[k] = h->split_at[k];
+    } else {
+        *n = 1;
+        at[0] = 0;
+        at[1] = h->cfg.num_envs;
+    }
+}
+
 int cav_create(const cav_config_t *cfg, cav_handle_t *out) {
     if (!cfg || !out) return fail(nullptr, CAV_ERR_NULL_POINTER, "cav_create: null argument");
     *out = nullptr;
@@ -255,13 +272,17 @@ int cav_create(const cav_config_t *cfg, cav_handle_t *out) {
     // policy(B) -> pairwise(B) on a helper stream forked from it with an event and joined back with another: pairwise(A)
     // fills the SMs that policy(B)'s tail leaves idle.  Caller-visible semantics are unchanged (everything is ordered
     // after the caller's earlier work and before its later work; graph capture records the fork / join as edges).
-    // CAV_STEP_SPLIT=0 disables it.
-    h->split_env = 0;
-    h->aux = nullptr;
+    // CAV_STEP_SPLIT=0 disables it, 2..4 picks the number of ranges (default 2).
+    h->split_parts = 0;
+    for (int k = 0; k < 3; ++k) h->aux[k] = nullptr, h->ev_join[k] = nullptr;
+    h->ev_fork = nullptr;
     {
         bool want = cfg->num_envs >= 4096 && h->use_v2_policy && h->use_tpa_n && !h->has_laser &&
                     cfg->agent_sorting_method != CAV_SORT_TIME_TO_IMPACT;
-        if (const char *ev = getenv("CAV_STEP_SPLIT")) want = want && atoi(ev) != 0;
+        int parts = 2;
+        if (const char *ev = getenv("CAV_STEP_SPLIT")) parts = atoi(ev);
+        if (parts > 4) parts = 4;
+        want = want && parts >= 2;
         if (want) {
             int pw_tile = 0;
             const WallMap nomap{};
@@ -278,11 +299,53 @@ int cav_create(const cav_config_t *cfg, cav_handle_t *out) {
                     b = t;
                 }
                 const int unit = pw_tile / a * pm_tile;  // lcm: a boundary both kernels' tiles respect
-                const int split = (cfg->num_envs / 2) / unit * unit;
-                if (split > 0 && cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking) == cudaSuccess &&
-                    cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
-                    cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) == cudaSuccess)
-                    h->split_env = split;
+                bool ok = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+                h->split_at[0] = 0;
+                for (int k = 1; k < parts && ok; ++k) {
+                    h->split_at[k] = (int)((long long)cfg->num_envs * k / parts) / unit * unit;
+                    ok = h->split_at[k] > h->split_at[k - 1] &&
+                         cudaStreamCreateWithFlags(&h->aux[k - 1], cudaStreamNonBlocking) == cudaSuccess &&
+                         cudaEventCreateWithFlags(&h->ev_join[k - 1], cudaEventDisableTiming) == cudaSuccess;
+                }
+                h->split_at[parts] = cfg->num_envs;
+                if (ok) h->split_parts = parts;
+            }
+        }
+    }
+    // Environment schedule (see cav_policy.cu): 6 bytes per environment of library-owned scratch, identity order to start
+    // with.  CAV_ENV_ORDER=0 disables it (the kernels then process environment q at position q).
+    h->sort_stream = nullptr;
+    h->ev_sorted = nullptr;
+    for (int k = 0; k < 4; ++k) h->ev_policy[k] = nullptr;
+    {
+        bool want = h->use_v2_policy && cfg->num_envs >= 2048;
+        if (const char *ev = getenv("CAV_ENV_ORDER")) want = want && atoi(ev) != 0;
+        if (want) {
+            int *order = nullptr;
+            unsigned short *cost = nullptr;
+            const size_t E = (size_t)cfg->num_envs;
+            bool ok = cudaMalloc(&order, E * sizeof(int)) == cudaSuccess && cudaMalloc(&cost, E * sizeof(unsigned short)) == cudaSuccess &&
+                      cudaMemset(cost, 0, E * sizeof(unsigned short)) == cudaSuccess;
+            if (ok) {
+                h->sched.order = order;
+                h->sched.cost = cost;
+                // the same ranges cav_step launches: order[range] must always be a permutation OF THAT RANGE, or one
+                // range's policy kernel would move environments the other range's pairwise kernel is reading
+                int at[5], nr;
+                sched_ranges(h, at, &nr);
+                ok = run_env_order(h->sched, at, nr, nullptr) == cudaSuccess && cudaStreamSynchronize(nullptr) == cudaSuccess;
+            }
+            if (ok && h->split_parts > 1) {
+                ok = cudaStreamCreateWithFlags(&h->sort_stream, cudaStreamNonBlocking) == cudaSuccess &&
+                     cudaEventCreateWithFlags(&h->ev_sorted, cudaEventDisableTiming) == cudaSuccess;
+                for (int k = 0; k < h->split_parts && ok; ++k)
+                    ok = cudaEventCreateWithFlags(&h->ev_policy[k], cudaEventDisableTiming) == cudaSuccess;
+            }
+            if (!ok) {
+                cudaGetLastError();
+                if (order) cudaFree(order);
+                if (cost) cudaFree(cost);
+                h->sched = EnvSchedule{};
             }
         }
     }
@@ -293,8 +356,19 @@ int cav_create(const cav_config_t *cfg, cav_handle_t *out) {
 size_t cav_real_bytes(cav_handle_t h) { return valid(h) ? (h->cfg.precision == CAV_F64 ? 8 : 4) : 0; }
 
 size_t cav_workspace_bytes(cav_handle_t h) {
-    (void)h;
-    return 0;
+    return (valid(h) && h->sched.order) ? (size_t)h->cfg.num_envs * (sizeof(int) + sizeof(unsigned short)) : 0;
+}
+
+int cav_env_schedule(cav_handle_t h, int32_t *order, uint16_t *cost, cav_stream_t stream) {
+    if (!valid(h)) return fail(nullptr, CAV_ERR_BAD_HANDLE, "cav_env_schedule: bad handle");
+    if (!h->sched.order) return fail(h, CAV_ERR_BAD_CONFIG, "cav_env_schedule: no environment schedule on this handle");
+    const size_t E = (size_t)h->cfg.num_envs;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t ce = cudaSuccess;
+    if (order) ce = cudaMemcpyAsync(order, h->sched.order, E * sizeof(int32_t), cudaMemcpyDeviceToDevice, st);
+    if (ce == cudaSuccess && cost) ce = cudaMemcpyAsync(cost, h->sched.cost, E * sizeof(uint16_t), cudaMemcpyDeviceToDevice, st);
+    if (ce != cudaSuccess) return fail(h, CAV_ERR_CUDA, "cav_env_schedule: %s", cudaGetErrorString(ce));
+    return CAV_OK;
 }
 
 int cav_bind(cav_handle_t h, const cav_buffers_t *bufs) {
@@ -360,8 +434,8 @@ static int do_policy_move(cav_handle_t h, const float *ext, int phases, double d
     if (h->use_v2_policy) {
         const cudaError_t ce = debug_after(
             "policy_move_v2", (h->cfg.precision == CAV_F64)
-                                  ? run_policy_move_v2<double>(h->bufs, h->pd, ext, phases, dt, h->sm_count, st)
-                                  : run_policy_move_v2<float>(h->bufs, h->pf, ext, phases, dt, h->sm_count, st));
+                                  ? run_policy_move_v2<double>(h->bufs, h->pd, ext, phases, dt, h->sm_count, st, 0, -1, h->sched)
+                                  : run_policy_move_v2<float>(h->bufs, h->pf, ext, phases, dt, h->sm_count, st, 0, -1, h->sched));
         if (ce == cudaSuccess) {
             h->launches++;
             return CAV_OK;
@@ -435,11 +509,11 @@ static int do_laser(cav_handle_t h, const uint8_t *mask, cudaStream_t st) {
 
 // cav_step as two independent halves of the environments on two streams (see cav_create)
 static int step_split(cav_handle_t h, const float *ext, double dt, cudaStream_t st) {
-    const int E = h->cfg.num_envs, sp = h->split_env;
+    const int P = h->split_parts;
     const WallMap wm = wall_map(h);
     auto policy = [&](cudaStream_t s, int e0, int e1) {
-        return (h->cfg.precision == CAV_F64) ? run_policy_move_v2<double>(h->bufs, h->pd, ext, 3, dt, h->sm_count, s, e0, e1)
-                                             : run_policy_move_v2<float>(h->bufs, h->pf, ext, 3, dt, h->sm_count, s, e0, e1);
+        return (h->cfg.precision == CAV_F64) ? run_policy_move_v2<double>(h->bufs, h->pd, ext, 3, dt, h->sm_count, s, e0, e1, h->sched)
+                                             : run_policy_move_v2<float>(h->bufs, h->pf, ext, 3, dt, h->sm_count, s, e0, e1, h->sched);
     };
     auto pairwise = [&](cudaStream_t s, int e0, int e1) {
         return CAV_BY_PRECISION(
@@ -447,18 +521,37 @@ static int step_split(cav_handle_t h, const float *ext, double dt, cudaStream_t 
             (run_pairwise_obs_tpa_n<double, double>(h->bufs, h->pd, h->plan, wm, nullptr, 0, h->sm_count, s, e0, e1, nullptr)),
             (run_pairwise_obs_tpa_n<double, float>(h->bufs, h->pd, h->plan, wm, nullptr, 0, h->sm_count, s, e0, e1, nullptr)));
     };
+    // range 0 runs on the caller's stream, range k > 0 on helper stream k - 1
+    auto stream_of = [&](int k) { return k == 0 ? st : h->aux[k - 1]; };
     CAV_CUDA(h, "step fork", cudaEventRecord(h->ev_fork, st));
     h->launches--;
-    CAV_CUDA(h, "step fork", cudaStreamWaitEvent(h->aux, h->ev_fork, 0));
-    h->launches--;
-    CAV_CUDA(h, "policy_move_v2 (second half)", policy(h->aux, sp, E));
-    CAV_CUDA(h, "policy_move_v2 (first half)", policy(st, 0, sp));
-    CAV_CUDA(h, "pairwise_obs_tpa_n (second half)", pairwise(h->aux, sp, E));
-    CAV_CUDA(h, "pairwise_obs_tpa_n (first half)", pairwise(st, 0, sp));
-    CAV_CUDA(h, "step join", cudaEventRecord(h->ev_join, h->aux));
-    h->launches--;
-    CAV_CUDA(h, "step join", cudaStreamWaitEvent(st, h->ev_join, 0));
-    h->launches--;
+    for (int k = 1; k < P; ++k) {
+        CAV_CUDA(h, "step fork", cudaStreamWaitEvent(h->aux[k - 1], h->ev_fork, 0));
+        h->launches--;
+    }
+    for (int k = P - 1; k >= 0; --k) CAV_CUDA(h, "policy_move_v2 (env range)", policy(stream_of(k), h->split_at[k], h->split_at[k + 1]));
+    if (h->sched.order) {  // next step's schedule, beside the pairwise kernels
+        for (int k = 0; k < P; ++k) {
+            CAV_CUDA(h, "env order fork", cudaEventRecord(h->ev_policy[k], stream_of(k)));
+            h->launches--;
+            CAV_CUDA(h, "env order fork", cudaStreamWaitEvent(h->sort_stream, h->ev_policy[k], 0));
+            h->launches--;
+        }
+        CAV_CUDA(h, "env_order", run_env_order(h->sched, h->split_at, P, h->sort_stream));
+        CAV_CUDA(h, "env order join", cudaEventRecord(h->ev_sorted, h->sort_stream));
+        h->launches--;
+    }
+    for (int k = P - 1; k >= 0; --k) CAV_CUDA(h, "pairwise_obs_tpa_n (env range)", pairwise(stream_of(k), h->split_at[k], h->split_at[k + 1]));
+    if (h->sched.order) {
+        CAV_CUDA(h, "env order join", cudaStreamWaitEvent(st, h->ev_sorted, 0));
+        h->launches--;
+    }
+    for (int k = 1; k < P; ++k) {
+        CAV_CUDA(h, "step join", cudaEventRecord(h->ev_join[k - 1], h->aux[k - 1]));
+        h->launches--;
+        CAV_CUDA(h, "step join", cudaStreamWaitEvent(st, h->ev_join[k - 1], 0));
+        h->launches--;
+    }
     return CAV_OK;
 }
 
@@ -502,9 +595,14 @@ int cav_step(cav_handle_t h, const float *ext_actions, double dt, cav_stream_t s
     cudaStream_t st = (cudaStream_t)stream;
     if (!(dt > 0.0)) dt = h->cfg.dt;
     h->launches = 0;
-    if (h->split_env > 0 && h->use_v2_policy && h->use_tpa_n && !debug_sync()) return step_split(h, ext_actions, dt, st);
+    if (h->split_parts > 1 && h->use_v2_policy && h->use_tpa_n && !debug_sync()) return step_split(h, ext_actions, dt, st);
     int rc = do_policy_move(h, ext_actions, 3, dt, st);
     if (rc) return rc;
+    if (h->sched.order && h->use_v2_policy) {
+        int at[5], nr;
+        sched_ranges(h, at, &nr);
+        CAV_CUDA(h, "env_order", run_env_order(h->sched, at, nr, st));
+    }
     rc = do_pairwise_obs(h, nullptr, 0, st);
     if (rc) return rc;
     if (h->has_laser) rc = do_laser(h, nullptr, st);
@@ -550,11 +648,17 @@ const char *cav_last_error(cav_handle_t h) { return valid(h) ? h->err : g_err; }
 int cav_destroy(cav_handle_t h) {
     if (!valid(h)) return fail(nullptr, CAV_ERR_BAD_HANDLE, "cav_destroy: bad handle");
     h->magic = 0;
-    if (h->aux) {
-        cudaStreamDestroy(h->aux);
-        if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-        if (h->ev_join) cudaEventDestroy(h->ev_join);
+    for (int k = 0; k < 3; ++k) {
+        if (h->aux[k]) cudaStreamDestroy(h->aux[k]);
+        if (h->ev_join[k]) cudaEventDestroy(h->ev_join[k]);
     }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->sort_stream) cudaStreamDestroy(h->sort_stream);
+    if (h->ev_sorted) cudaEventDestroy(h->ev_sorted);
+    for (int k = 0; k < 4; ++k)
+        if (h->ev_policy[k]) cudaEventDestroy(h->ev_policy[k]);
+    if (h->sched.order) cudaFree(const_cast<int *>(h->sched.order));
+    if (h->sched.cost) cudaFree(h->sched.cost);
     delete h;
     return CAV_OK;
 }

@@ -31,12 +31,21 @@ cudaError_t run_pairwise_obs_tpa_n(const cav_buffers_t &bufs, const KParams<T> &
                                    int env1 = -1, int *tile_envs = nullptr);
 
 
+// Scheduling order of the environments inside k_policy_move_v2 (library-owned scratch, see cav_policy.cu): position q of
+// a launch's range processes environment order[q]; cost[e] is what environment e's linear programs cost last step.
+struct EnvSchedule {
+    const int *order = nullptr;
+    unsigned short *cost = nullptr;
+};
+
 // thread-per-agent policy + move kernel (cav_policy.cu): every N in [2, 32], kd-tree order for N > 10;
 // cudaErrorNotSupported otherwise (N = 1 and N > 32: the sub-warp-group kernel above)
 template <typename T>
 cudaError_t run_policy_move_v2(const cav_buffers_t &bufs, const KParams<T> &p, const float *ext, int phases, double dt,
-                               int sm_count, cudaStream_t st, int env0 = 0, int env1 = -1);
+                               int sm_count, cudaStream_t st, int env0 = 0, int env1 = -1, EnvSchedule sched = EnvSchedule{});
 int policy_move_v2_tile_envs(int N);  // environments per CTA tile (a launch's env0 must be a multiple of it)
+// order[lo, hi) := the environments lo .. hi - 1 by decreasing cost, for each of the nranges ranges [at[k], at[k + 1])
+cudaError_t run_env_order(const EnvSchedule &sched, const int *at, int nranges, cudaStream_t st);
 
 struct LaserParams {
     int E, N, B, P, obs_len, obs_off;

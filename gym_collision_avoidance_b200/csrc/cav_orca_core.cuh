@@ -133,8 +133,11 @@ CAV_HDI bool lp1_flat(const Lines &lines, int lineNo, const Line &L, float radiu
 #define CAV_LP2_JUMP 0  // 1: lanes re-converge on their k-th linearProgram1 call instead of on the line index (A/B switch)
 #endif
 // linearProgram2 (Agent.cpp:550-581) over lp1_flat; returns n on success, else the index of the failing line
+// `work` (optional): accumulates a cost estimate of this call -- (4 + line index) per linearProgram1 run -- that
+// k_policy_move_v2 turns into the environment's scheduling key (cav_policy.cu); it has no part in the result.
 template <typename Lines>
-CAV_HDI int lp2_flat(const Lines &lines, int n, float radius, float ox, float oy, bool directionOpt, float &rx, float &ry) {
+CAV_HDI int lp2_flat(const Lines &lines, int n, float radius, float ox, float oy, bool directionOpt, float &rx, float &ry,
+                     int *work = nullptr) {
     if (directionOpt) {
         rx = ox * radius;
         ry = oy * radius;
@@ -156,6 +159,7 @@ CAV_HDI int lp2_flat(const Lines &lines, int n, float radius, float ox, float oy
         const Line li = lines.get(i);
         if (fdet(li.dx, li.dy, li.px - rx, li.py - ry) > 0.0f) {
             const float tx = rx, ty = ry;
+            if (work) *work += 4 + i;
             if (!lp1_flat(lines, i, li, radius, ox, oy, directionOpt, rx, ry)) {
                 rx = tx;
                 ry = ty;

@@ -23,6 +23,14 @@
 //     persistent agent permutation (`kd_order`) is re-partitioned by ONE lane per environment (cav_kdtree.cuh,
 //     operation for operation KdTree.cpp:47-111) while the other lanes wait at a __syncwarp, then every lane inserts
 //     its neighbours in the tree's visiting order.
+//   * environment scheduling (EnvSchedule): a warp's cost is that of its costliest lane at every line index, so a warp of
+//     UNLIKE environments pays for all of them, and the kernel ends when its longest warp does.  Measured with 16
+//     scenarios x 1024 copies at 16384 x 10 (profiles/r02i_grouping.txt): scenarios interleaved over the environments
+//     64.9 us, like next to like 52.0 us, like next to like AND costliest first 48.5 us.  So every step each lane counts
+//     (4 + line index) per linearProgram1 it runs (+64 for a linearProgram3), the environment's sum goes to cost[e],
+//     k_env_order sorts each launch range by decreasing cost (one CTA per range: 1024-bucket counting sort in shared
+//     memory), and position q of the next step's launch processes environment order[q].  Environments are independent:
+//     the order changes which warp computes an environment, never what it computes.
 // NT > 0: compile-time agent count (2..10: sorting network in registers, no kd-tree needed: single leaf).
 // NT == 0: run-time agent count 11..32 (insertion sort through shared memory in kd-tree order).
 #include "cav_orca_core.cuh"
@@ -96,7 +104,7 @@ __device__ __forceinline__ R4<double> ld4_again<double>(const R4<double> *p) {
 template <typename T, int NT>
 __global__ void __launch_bounds__(32 * CAV_PM_WARPS, CAV_PM_MINB)
     k_policy_move_v2(TpaBuffers b, KParams<T> p, const float *__restrict__ ext, uint8_t *__restrict__ kd_order, int phases,
-                     T dt, int tile0, int ntiles, PmLayout rl) {
+                     T dt, int tile0, int ntiles, PmLayout rl, EnvSchedule sched) {
     constexpr bool CT = NT > 0;
     constexpr PmLayout cl = pm_layout(CT ? NT : 32, false);
     const int N = CT ? NT : rl.N;
@@ -122,10 +130,11 @@ __global__ void __launch_bounds__(32 * CAV_PM_WARPS, CAV_PM_MINB)
     const int eb = el * N;
 
     for (int tile = tile0 + blockIdx.x; tile < ntiles; tile += gridDim.x) {  // tiles [tile0, ntiles) of this launch
-        const int ew0 = (tile * CAV_PM_WARPS + warp) * EPW;
-        const int e = ew0 + el;
-        const bool have = lane < LW && e < p.E;
-        const size_t gi = (size_t)ew0 * N + lane;
+        const int q = (tile * CAV_PM_WARPS + warp) * EPW + el;  // position in the schedule
+        const bool have = lane < LW && q < p.E;
+        const int e = (have && sched.order) ? sched.order[q] : q;
+        const size_t gi = (size_t)e * N + a;
+        int work = 0;
         uint32_t f = 0, kind = 0;
         int n = 0;
         float prefx = 0.f, prefy = 0.f, maxSpeed = 0.f;
@@ -202,8 +211,9 @@ __global__ void __launch_bounds__(32 * CAV_PM_WARPS, CAV_PM_MINB)
         }
         float nvx = 0.f, nvy = 0.f;
         if (rvo) {
-            const int lp_fail = lp2_flat(SmemLines{s_lines + lane, LW}, nl, maxSpeed, prefx, prefy, false, nvx, nvy);
+            const int lp_fail = lp2_flat(SmemLines{s_lines + lane, LW}, nl, maxSpeed, prefx, prefy, false, nvx, nvy, &work);
             if (lp_fail < nl) {  // infeasible: linearProgram3 (Agent.cpp:419-421)
+                work += 64;
                 Line projbuf[CT ? (NT > 2 ? NT - 1 : 2) : 31];
                 lp3_flat(SmemLines{s_lines + lane, LW}, nl, lp_fail, maxSpeed, LocalLines{projbuf}, nvx, nvy);
             }
@@ -252,13 +262,71 @@ __global__ void __launch_bounds__(32 * CAV_PM_WARPS, CAV_PM_MINB)
             tpa_move<T>(b, p, gi, pv, gl, ht, f, kind, act, live, dt);
         }
         __syncwarp();
+        if (sched.cost && (phases & 1)) {  // the environment's scheduling key for the next step
+            const unsigned env_bits = lane < LW ? ((N >= 32 ? 0xffffffffu : ((1u << N) - 1u)) << eb) : (1u << lane);
+            const int total = __reduce_add_sync(env_bits, work);
+            if (have && a == 0) sched.cost[e] = (unsigned short)(total < 1023 ? total : 1023);
+        }
     }
+}
+
+// order[lo, hi) := environments lo .. hi - 1 by decreasing cost (ties in any order); one CTA per range
+#define CAV_ORDER_BUCKETS 1024
+__global__ void __launch_bounds__(1024) k_env_order(const unsigned short *__restrict__ cost, int *__restrict__ order, int4 at0,
+                                                    int at4) {
+    __shared__ int s_cnt[CAV_ORDER_BUCKETS];
+    __shared__ int s_warp[32];
+    const int at[5] = {at0.x, at0.y, at0.z, at0.w, at4};
+    const int lo = at[blockIdx.x], hi = at[blockIdx.x + 1];
+    const int tid = threadIdx.x;
+    s_cnt[tid] = 0;
+    __syncthreads();
+    for (int e = lo + tid; e < hi; e += 1024) {
+        const int c = cost[e];
+        atomicAdd(&s_cnt[CAV_ORDER_BUCKETS - 1 - (c < CAV_ORDER_BUCKETS - 1 ? c : CAV_ORDER_BUCKETS - 1)], 1);
+    }
+    __syncthreads();
+    // exclusive prefix sum over the buckets (bucket 0 = highest cost)
+    const int v = s_cnt[tid];
+    int inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, d);
+        if ((tid & 31) >= d) inc += t;
+    }
+    if ((tid & 31) == 31) s_warp[tid >> 5] = inc;
+    __syncthreads();
+    if (tid < 32) {
+        int w = s_warp[tid];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, w, d);
+            if (tid >= d) w += t;
+        }
+        s_warp[tid] = w;
+    }
+    __syncthreads();
+    s_cnt[tid] = inc - v + ((tid >> 5) ? s_warp[(tid >> 5) - 1] : 0);
+    __syncthreads();
+    for (int e = lo + tid; e < hi; e += 1024) {
+        const int c = cost[e];
+        const int slot = atomicAdd(&s_cnt[CAV_ORDER_BUCKETS - 1 - (c < CAV_ORDER_BUCKETS - 1 ? c : CAV_ORDER_BUCKETS - 1)], 1);
+        order[lo + slot] = e;
+    }
+}
+
+cudaError_t run_env_order(const EnvSchedule &sched, const int *at, int nranges, cudaStream_t st) {
+    if (!sched.order || !sched.cost || nranges < 1 || nranges > 4) return cudaErrorInvalidValue;
+    int a[5];
+    for (int k = 0; k < 5; ++k) a[k] = at[k < nranges ? k : nranges];
+    k_env_order<<<nranges, 1024, 0, st>>>(sched.cost, const_cast<int *>(sched.order), make_int4(a[0], a[1], a[2], a[3]), a[4]);
+    return cudaGetLastError();
 }
 
 // Environments [env0, env1) (env0 a multiple of policy_move_v2_tile_envs); env1 < 0 = all.
 template <typename T, int NT>
 static cudaError_t launch_v2(const cav_buffers_t &bufs, const KParams<T> &p, const float *ext, int phases, double dt,
-                             int sm_count, cudaStream_t st, int env0, int env1) {
+                             int sm_count, cudaStream_t st, int env0, int env1, const EnvSchedule &sched) {
     const PmLayout L = pm_layout(p.N, NT == 0);
     const int epb = CAV_PM_WARPS * L.EPW;
     if (env1 < 0 || env1 > p.E) env1 = p.E;
@@ -273,7 +341,7 @@ static cudaError_t launch_v2(const cav_buffers_t &bufs, const KParams<T> &p, con
     }
     const int cap = sm_count * 32;
     const int grid = (ntiles - tile0) < cap ? (ntiles - tile0) : cap;
-    kern<<<grid, 32 * CAV_PM_WARPS, smem, st>>>(make_tpa(bufs), p, ext, bufs.kd_order, phases, (T)dt, tile0, ntiles, L);
+    kern<<<grid, 32 * CAV_PM_WARPS, smem, st>>>(make_tpa(bufs), p, ext, bufs.kd_order, phases, (T)dt, tile0, ntiles, L, sched);
     return cudaGetLastError();
 }
 
@@ -282,10 +350,10 @@ int policy_move_v2_tile_envs(int N) { return CAV_PM_WARPS * pm_layout(N, N > 10)
 
 template <typename T>
 cudaError_t run_policy_move_v2(const cav_buffers_t &bufs, const KParams<T> &p, const float *ext, int phases, double dt,
-                               int sm_count, cudaStream_t st, int env0, int env1) {
+                               int sm_count, cudaStream_t st, int env0, int env1, EnvSchedule sched) {
     switch (p.N) {
 #define CAV_CASE(NN) \
-    case NN: return launch_v2<T, NN>(bufs, p, ext, phases, dt, sm_count, st, env0, env1);
+    case NN: return launch_v2<T, NN>(bufs, p, ext, phases, dt, sm_count, st, env0, env1, sched);
         CAV_CASE(2)
         CAV_CASE(3)
         CAV_CASE(4)
@@ -298,13 +366,13 @@ cudaError_t run_policy_move_v2(const cav_buffers_t &bufs, const KParams<T> &p, c
 #undef CAV_CASE
         default: break;
     }
-    if (p.N > 10 && p.N <= 32) return launch_v2<T, 0>(bufs, p, ext, phases, dt, sm_count, st, env0, env1);
+    if (p.N > 10 && p.N <= 32) return launch_v2<T, 0>(bufs, p, ext, phases, dt, sm_count, st, env0, env1, sched);
     return cudaErrorNotSupported;
 }
 
 template cudaError_t run_policy_move_v2<float>(const cav_buffers_t &, const KParams<float> &, const float *, int, double,
-                                               int, cudaStream_t, int, int);
+                                               int, cudaStream_t, int, int, EnvSchedule);
 template cudaError_t run_policy_move_v2<double>(const cav_buffers_t &, const KParams<double> &, const float *, int, double,
-                                                int, cudaStream_t, int, int);
+                                                int, cudaStream_t, int, int, EnvSchedule);
 
 }  // namespace cav

@@ -61,7 +61,8 @@ typedef enum {
     CAV_POLICY_NONCOOP = 1,  /* NonCooperativePolicy.py:21 */
     CAV_POLICY_STATIC = 2,   /* StaticPolicy.py:21-22 (goal := pos) */
     CAV_POLICY_EXTERNAL = 3, /* ExternalPolicy.py:14-16 (passthrough of the caller's action) */
-    CAV_POLICY_LEARNING = 4  /* LearningPolicy.py:30-32 (scaled external action, is_still_learning) */
+    CAV_POLICY_LEARNING = 4, /* LearningPolicy.py:30-32 (scaled external action, is_still_learning) */
+    CAV_POLICY_GA3C = 5      /* GA3CCADRLPolicy.py:49-84: LSTM network on the agent's own observation (cav_bind_ga3c) */
 } cav_policy_t;
 
 /* Dynamics plugin ids (reference envs/test_cases.py:93-96 dynamics_dict; envs/dynamics/*.py). */
@@ -256,10 +257,18 @@ int cav_create(const cav_config_t *cfg, cav_handle_t *out);
 /* Bytes of `real` for this handle (4 or 8). */
 size_t cav_real_bytes(cav_handle_t h);
 
-/* Device scratch the library needs beyond cav_buffers_t: none -- every kernel works out of registers and its own shared
- * memory, so this returns 0 for every configuration.  (SURVEY.md §8b lists the entry point; it stays so that a caller
- * written against that list links, and so that a later kernel that does need scratch can ask for it.) */
+/* Device scratch the library holds beyond cav_buffers_t (SURVEY.md §8b lists the entry point): the kernels work out of
+ * registers and their own shared memory; the one exception is the environment schedule of the policy + move kernel --
+ * 6 bytes per environment (an int32 order and a uint16 cost), allocated by cav_create with cudaMalloc on the current
+ * device when num_envs >= 2048 and freed by cav_destroy (CAV_ENV_ORDER=0 in the environment disables it).  Returns
+ * those bytes, 0 when there are none. */
 size_t cav_workspace_bytes(cav_handle_t h);
+
+/* Diagnostics: copies the environment schedule into caller-owned DEVICE buffers on `stream` (either may be NULL):
+ * order[q] = environment processed at position q of the policy + move kernel (int32 [num_envs]), cost[e] = scheduling key
+ * environment e earned in its last step (uint16 [num_envs]).  Returns CAV_ERR_BAD_CONFIG when the schedule is disabled.
+ * The schedule only decides WHICH warp computes an environment -- results do not depend on it. */
+int cav_env_schedule(cav_handle_t h, int32_t *order, uint16_t *cost, cav_stream_t stream);
 
 /* Attaches caller-owned device columns (replaces the per-Agent Python attribute storage, agent.py:59-138). */
 int cav_bind(cav_handle_t h, const cav_buffers_t *bufs);
@@ -314,6 +323,43 @@ typedef struct cav_scenario_gen {
 } cav_scenario_gen_t;
 int cav_generate_scenarios(cav_handle_t h, const cav_scenario_gen_t *gen, double *rows, int32_t *case_kind,
                            int32_t num_scenarios, cav_stream_t stream);
+
+/* ---- GA3C-CADRL policy network (reference policies/GA3CCADRLPolicy.py:49-84, policies/GA3C_CADRL/network.py:37-74) ------
+ * The reference restores a TF1 meta-graph + checkpoint and calls sess.run('Softmax:0', {X: vec_obs}).  The graph (read
+ * from network_01900000.meta; identical in the three shipped checkpoints) is:
+ *   X [rows, 138] = [num_other_agents, dist_to_goal, heading_ego_frame, pref_speed, radius, 19 x 7 other-agent states]
+ *   Xn = (X - avg) / std                                       (Const, Const_1: sub, div)
+ *   LSTMCell(64, forget_bias 1) over Xn[:, 5:] as 19 steps of 7, sequence_length = int32(X[:, 0]), zero initial state:
+ *       [i j f o] = [x_t, h] @ Wl + bl;  c = sigmoid(f + 1) * c + sigmoid(i) * tanh(j);  h = sigmoid(o) * tanh(c)
+ *   a1 = relu([Xn[:, 1:5], h] @ W1 + b1); a2 = relu(a1 @ W2 + b2); a3 = relu(a2 @ W3 + b3); p = softmax(a3 @ Wo + bo)
+ * and the policy takes actions[argmax p] of the 11-entry table (network.py:7-16), speed scaled by the observed pref_speed.
+ * All float32.  The weights travel as ONE float32 blob in device memory (host memory for the oracle), sections in this
+ * order, each in TF's row-major [in][out] layout except the LSTM kernel, whose 256 columns are regrouped per hidden unit:
+ *   avg[138] std[138] Wl[71][64][4 = i,j,f,o] bl[64][4] W1[68][256] b1[256] W2[256][256] b2[256] W3[256][256] b3[256]
+ *   Wo[256][11] bo[11] pad[1]                                     = CAV_GA3C_BLOB_FLOATS floats
+ * (gym_collision_avoidance_b200/envs/policies/GA3C_CADRL/network.py reads the reference's checkpoint files into it). */
+#define CAV_GA3C_X_LEN 138
+#define CAV_GA3C_MAX_OTHERS 19
+#define CAV_GA3C_HIDDEN 64
+#define CAV_GA3C_FC 256
+#define CAV_GA3C_ACTIONS 11
+#define CAV_GA3C_BLOB_FLOATS 170784
+
+/* Attaches the network to a handle: agents whose policy id is CAV_POLICY_GA3C then get their action from it inside
+ * cav_step / cav_k_policy.  X is gathered from the agent's packed observation of the previous step (what the reference
+ * passes to find_next_action, env.py:313-323): the states of Config.STATES_IN_OBS in order without is_learning,
+ * cropped / zero-padded to 138 (network.py:24-35 crop_x).  `blob` is borrowed device memory (float32, 16-byte aligned). */
+int cav_bind_ga3c(cav_handle_t h, const float *blob);
+
+/* Phase entry point: the network for every live CAV_POLICY_GA3C agent -> bufs.actions ([pref_speed * a0, a1] as float32,
+ * GA3CCADRLPolicy.py:80-84); cav_step and cav_k_policy run it themselves when a network is bound.  probs (nullable):
+ * float32 [E*N*11] device, receives the softmax of the agents it ran for (other rows untouched). */
+int cav_k_ga3c(cav_handle_t h, float *probs, cav_stream_t stream);
+
+/* The network alone on a batch (replaces NetworkVPCore.predict_p, network.py:37-41): X float32 [rows][138] device ->
+ * probs float32 [rows][11] (nullable) and action_index int32 [rows] (nullable, argmax: first maximum). */
+int cav_ga3c_forward(const float *blob, const float *X, int32_t rows, float *probs, int32_t *action_index,
+                     cav_stream_t stream);
 
 /* Number of kernels the last cav_step / cav_reset call on this handle enqueued (for launch accounting). */
 int cav_last_launch_count(cav_handle_t h);

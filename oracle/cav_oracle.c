@@ -493,6 +493,132 @@ static int cavo_world_to_cell(const cavo_map_t *m, double px, double py, int *gx
 #define R_COS cosf
 #define R_ATAN2 atan2f
 #define R_SQRT sqrtf
+/* ------------------------------------------------------------------------------------------------------------
+ * GA3C-CADRL network forward pass (policies/GA3CCADRLPolicy.py:49-84 -> policies/GA3C_CADRL/network.py:37-41
+ * sess.run('Softmax:0')).  TensorFlow is not in this image, so the restatement follows the reference's own GRAPH
+ * (network_01900000.meta, node for node: sub / div / strided_slice* / Reshape / transpose / dynamic_rnn LSTMCell while
+ * loop with sequence_length Select / layer1_input concat / layer1 / layer2 / fullyconnected1 / logits_p / Softmax) and
+ * is pinned against oracle/tf1_graph.py, a numpy interpreter that EXECUTES that graph's nodes with the checkpoint's
+ * variables (tests/test_ga3c_cpu.py, tests/golden/ga3c_iros18.npz).  float32 throughout, sums in ascending k.
+ * Weight blob layout: include/cavoid.h (CAV_GA3C_*).
+ * ---------------------------------------------------------------------------------------------------------- */
+static const float *g_ga3c_blob = NULL;
+void cavo_set_ga3c(const float *blob) { g_ga3c_blob = blob; }
+
+static float ga3c_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+void cavo_ga3c_forward(const float *blob, const float *X, int rows, float *probs, int32_t *action_index) {
+    enum { XL = CAV_GA3C_X_LEN, T = CAV_GA3C_MAX_OTHERS, H = CAV_GA3C_HIDDEN, F = CAV_GA3C_FC, A = CAV_GA3C_ACTIONS };
+    const float *avg = blob, *std_ = avg + XL, *wl = std_ + XL, *bl = wl + (7 + H) * H * 4, *w1 = bl + H * 4,
+                *b1 = w1 + (4 + H) * F, *w2 = b1 + F, *b2 = w2 + F * F, *w3 = b2 + F, *b3 = w3 + F * F, *wo = b3 + F,
+                *bo = wo + F * A;
+    for (int r = 0; r < rows; ++r) {
+        const float *x = X + (size_t)r * XL;
+        float xn[XL];
+        for (int k = 0; k < XL; ++k) xn[k] = (x[k] - avg[k]) / std_[k]; /* sub, div */
+        const int len = (int)x[0];                                       /* ToInt32(X[:, 0]) */
+        float c[H], h[H];
+        memset(c, 0, sizeof(c));
+        memset(h, 0, sizeof(h));
+        for (int t = 0; t < T; ++t) {       /* rnn/while: time < 19 */
+            if (t >= len) continue;         /* Select(time >= sequence_length, old state, new state) */
+            const float *xt = xn + 5 + 7 * t;
+            float cn[H], hn[H];
+            for (int u = 0; u < H; ++u) {
+                float g[4];
+                for (int q = 0; q < 4; ++q) {
+                    float acc = 0.0f;
+                    for (int k = 0; k < 7; ++k) acc += xt[k] * wl[(k * H + u) * 4 + q];
+                    for (int k = 0; k < H; ++k) acc += h[k] * wl[((7 + k) * H + u) * 4 + q];
+                    g[q] = acc + bl[u * 4 + q]; /* BiasAdd */
+                }
+                cn[u] = ga3c_sigmoid(g[2] + 1.0f) * c[u] + ga3c_sigmoid(g[0]) * tanhf(g[1]);
+                hn[u] = ga3c_sigmoid(g[3]) * tanhf(cn[u]);
+            }
+            memcpy(c, cn, sizeof(c));
+            memcpy(h, hn, sizeof(h));
+        }
+        float in1[4 + H], a1[F], a2[F], a3[F], logit[A];
+        for (int k = 0; k < 4; ++k) in1[k] = xn[1 + k]; /* layer1_input = concat(Xn[:, 1:5], h) */
+        for (int k = 0; k < H; ++k) in1[4 + k] = h[k];
+        for (int j = 0; j < F; ++j) {
+            float acc = 0.0f;
+            for (int k = 0; k < 4 + H; ++k) acc += in1[k] * w1[k * F + j];
+            acc += b1[j];
+            a1[j] = acc > 0.0f ? acc : 0.0f;
+        }
+        for (int j = 0; j < F; ++j) {
+            float acc = 0.0f;
+            for (int k = 0; k < F; ++k) acc += a1[k] * w2[k * F + j];
+            acc += b2[j];
+            a2[j] = acc > 0.0f ? acc : 0.0f;
+        }
+        for (int j = 0; j < F; ++j) {
+            float acc = 0.0f;
+            for (int k = 0; k < F; ++k) acc += a2[k] * w3[k * F + j];
+            acc += b3[j];
+            a3[j] = acc > 0.0f ? acc : 0.0f;
+        }
+        float mx = -INFINITY;
+        int best = 0;
+        for (int j = 0; j < A; ++j) {
+            float acc = 0.0f;
+            for (int k = 0; k < F; ++k) acc += a3[k] * wo[k * A + j];
+            logit[j] = acc + bo[j];
+            if (logit[j] > mx) {
+                mx = logit[j];
+                best = j; /* np.argmax: first maximum (softmax is monotone) */
+            }
+        }
+        if (probs) {
+            float e[A], sum = 0.0f;
+            for (int j = 0; j < A; ++j) {
+                e[j] = expf(logit[j] - mx);
+                sum += e[j];
+            }
+            for (int j = 0; j < A; ++j) probs[(size_t)r * A + j] = e[j] / sum;
+        }
+        if (action_index) action_index[r] = best;
+    }
+}
+
+/* the flattened observation the policy hands the network (GA3CCADRLPolicy.py:68-75): Config.STATES_IN_OBS in order
+ * without is_learning, cut / zero-padded to 138 (network.py:24-35).  src[k] = float index in the packed row, -1 = 0. */
+void cavo_ga3c_gather(const cav_config_t *cfg, int16_t *src) {
+    int order[CAV_OBS_NUM_STATES], n = 0;
+    for (int s = 0; s < CAV_OBS_NUM_STATES; ++s)
+        if (cfg->obs_offset[s] >= 0) order[n++] = s;
+    for (int i = 1; i < n; ++i) /* by offset = STATES_IN_OBS order */
+        for (int j = i; j > 0 && cfg->obs_offset[order[j]] < cfg->obs_offset[order[j - 1]]; --j) {
+            const int t = order[j];
+            order[j] = order[j - 1];
+            order[j - 1] = t;
+        }
+    int k = 0;
+    for (int i = 0; i < n && k < CAV_GA3C_X_LEN; ++i) {
+        const int s = order[i];
+        const int beg = cfg->obs_offset[s], end = (i + 1 < n) ? cfg->obs_offset[order[i + 1]] : cfg->obs_len;
+        if (s == CAV_OBS_IS_LEARNING) continue; /* Config.STATES_NOT_USED_IN_POLICY */
+        for (int o = beg; o < end && k < CAV_GA3C_X_LEN; ++o) src[k++] = (int16_t)o;
+    }
+    for (; k < CAV_GA3C_X_LEN; ++k) src[k] = -1;
+}
+
+/* speed fraction / heading change of action j (network.py:7-16) */
+static void ga3c_action(int j, double *speed, double *dheading) {
+    const double pi6 = 3.14159265358979323846 / 6, pi12 = 3.14159265358979323846 / 12;
+    if (j < 5) {
+        *speed = 1.0;
+        *dheading = -pi6 + j * pi12;
+    } else if (j < 8) {
+        *speed = 0.5;
+        *dheading = -pi6 + (j - 5) * pi6;
+    } else {
+        *speed = 0.0;
+        *dheading = -pi6 + (j - 8) * pi6;
+    }
+}
+
 #define R_FABS fabsf
 #define R_FMOD fmodf
 #define R_RINT rintf

@@ -124,6 +124,20 @@ static void SFX(policy_env)(const cav_config_t *cfg, const cav_buffers_t *b, con
             goal[i].y = pv[i].y;
             a0 = 0;
             a1 = 0;
+        } else if (pol == CAV_POLICY_GA3C) { /* GA3CCADRLPolicy.py:49-84 on the agent's observation of the last step */
+            if (!g_ga3c_blob) continue;
+            int16_t src[CAV_GA3C_X_LEN];
+            cavo_ga3c_gather(cfg, src);
+            const REAL *orow = (const REAL *)b->obs + ((size_t)e * N + i) * cfg->obs_len;
+            float X[CAV_GA3C_X_LEN];
+            for (int k = 0; k < CAV_GA3C_X_LEN; ++k) X[k] = src[k] >= 0 ? (float)orow[src[k]] : 0.0f; /* float32 feed */
+            int32_t best = 0;
+            cavo_ga3c_forward(g_ga3c_blob, X, 1, NULL, &best);
+            double sp, dh;
+            ga3c_action(best, &sp, &dh);
+            /* obs['pref_speed'] is a float32 entry of the observation dict (config.py:93-170 dtype) */
+            a0 = (REAL)((double)(float)orow[cfg->obs_offset[CAV_OBS_PREF_SPEED]] * sp);
+            a1 = (REAL)dh;
         } else if (pol == CAV_POLICY_RVO) { /* RVOPolicy.py:50-122 */
             const REAL gx = goal[i].x - pv[i].x, gy = goal[i].y - pv[i].y;      /* :66 */
             const REAL nrm = R_SQRT(gx * gx + gy * gy);                         /* np.linalg.norm */

@@ -409,3 +409,41 @@ def test_compile_time_n_kernels_forced_on_and_off(N, prec, monkeypatch):
             else:
                 for a, b in zip(first, trace):
                     common.compare_states(b, a, N, 0.0, 0.0)
+
+
+@pytest.mark.parametrize("E,N", [(4800, 10), (2304, 10), (2100, 16), (4224, 4)])
+def test_environment_schedule_changes_nothing_but_the_order(E, N, monkeypatch):
+    """k_policy_move_v2 processes the environments in order of decreasing cost of their previous step (cav_policy.cu,
+    EnvSchedule): the order must be a permutation of every launch range sorted by the recorded cost, and 40 free-running
+    steps with auto-reset must be bit-identical to the same run with the schedule off (E >= 4096: split step with the
+    ordering kernel on its own stream; below: single-range step).  A third of the environments run a dense scenario."""
+    from gpu_common import GpuRunner
+    c = to_cav_config(make_config(N, evaluate=True), E, N, precision="f64", track_aux=True, obs_f32=True)
+    rows = np.concatenate([random_scenario_bank(2, N, seed=7 + N), random_scenario_bank(1, N, seed=9, side_length=2.0 + 0.35 * N ** 0.5)])
+    bank = HostBank(rows, kinds=kinds_array(3, N, "RVO"))
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("CAV_ENV_ORDER", mode)
+        r = GpuRunner(c)
+        db = r.bank(bank)
+        r.cav.reset(db)
+        for s in range(40):
+            r.cav.step()
+            if mode == "1" and s in (3, 17):
+                sch = r.cav.env_schedule()
+                assert sch is not None
+                order, cost = (t.cpu().numpy() for t in sch)
+                assert np.array_equal(np.sort(order), np.arange(E)), "the schedule must be a permutation"
+                # the order was sorted on the cost of THIS step (the ordering kernel runs after policy + move)
+                parts = 2 if E >= 4096 else 1
+                # range boundaries are internal; check sortedness on maximal runs instead: cost along the order may rise
+                # at most parts - 1 times
+                rises = int(np.sum(np.diff(cost[order].astype(np.int64)) > 0))
+                assert rises <= parts - 1, (rises, parts)
+                assert cost.max() > cost.min(), "dense and sparse scenarios must earn different costs"
+            r.cav.reset(db, env_mask=r.cav.state.game_over, accumulate_stats=True)
+        if mode == "0":
+            assert r.cav.env_schedule() is None
+        out[mode] = r.download()
+        r.cav.close()
+    common.compare_states(out["1"], out["0"], N, 0.0, 0.0)
