@@ -7,6 +7,7 @@ import ctypes
 import os
 
 CAV_ABI_VERSION = 2
+CAV_GA3C_BLOB_FLOATS = 170784
 
 # cav_status_t
 CAV_OK = 0
@@ -15,7 +16,7 @@ STATUS_NAMES = {0: "CAV_OK", -1: "CAV_ERR_BAD_CONFIG", -2: "CAV_ERR_NULL_POINTER
 
 CAV_F32, CAV_F64 = 0, 1
 
-CAV_POLICY_RVO, CAV_POLICY_NONCOOP, CAV_POLICY_STATIC, CAV_POLICY_EXTERNAL, CAV_POLICY_LEARNING = range(5)
+CAV_POLICY_RVO, CAV_POLICY_NONCOOP, CAV_POLICY_STATIC, CAV_POLICY_EXTERNAL, CAV_POLICY_LEARNING, CAV_POLICY_GA3C = range(6)
 CAV_DYN_UNICYCLE, CAV_DYN_UNICYCLE_MAX_TURN_RATE, CAV_DYN_EXTERNAL = range(3)
 
 
@@ -109,7 +110,8 @@ class CavScenarioGen(ctypes.Structure):
 EXPORTED_SYMBOLS = [
     "cav_abi_version", "cav_create", "cav_real_bytes", "cav_workspace_bytes", "cav_bind", "cav_reset", "cav_step",
     "cav_k_policy", "cav_k_dynamics", "cav_k_pairwise_obs", "cav_k_laserscan", "cav_k_observe",
-    "cav_generate_scenarios", "cav_last_launch_count", "cav_env_schedule",
+    "cav_generate_scenarios", "cav_last_launch_count", "cav_env_schedule", "cav_bind_ga3c", "cav_k_ga3c",
+    "cav_ga3c_forward",
     "cav_last_error", "cav_destroy",
 ]
 
@@ -162,6 +164,13 @@ def load_library(path=None):
     L.cav_generate_scenarios.restype = ctypes.c_int
     L.cav_generate_scenarios.argtypes = [h, ctypes.POINTER(CavScenarioGen), _vp, _vp, ctypes.c_int32, _vp]
     L.cav_last_launch_count.argtypes = [h]
+    L.cav_bind_ga3c.restype = ctypes.c_int
+    L.cav_bind_ga3c.argtypes = [h, ctypes.c_void_p]
+    L.cav_k_ga3c.restype = ctypes.c_int
+    L.cav_k_ga3c.argtypes = [h, ctypes.c_void_p, ctypes.c_void_p]
+    L.cav_ga3c_forward.restype = ctypes.c_int
+    L.cav_ga3c_forward.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
+                                   ctypes.c_void_p]
     L.cav_env_schedule.restype = ctypes.c_int
     L.cav_env_schedule.argtypes = [h, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     L.cav_last_error.restype = ctypes.c_char_p

@@ -15,7 +15,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 ROOT = os.path.dirname(PKG)
 OUT = os.path.join(CSRC, "libcavoid_sm100a.so")
-SOURCES = ["cav_step.cu", "cav_tpa.cu", "cav_tpa_n.cu", "cav_policy.cu", "cav_laser.cu", "cav_reset.cu", "cav_scenario.cu", "cav_abi.cu"]
+SOURCES = ["cav_step.cu", "cav_tpa.cu", "cav_tpa_n.cu", "cav_policy.cu", "cav_ga3c.cu", "cav_laser.cu", "cav_reset.cu", "cav_scenario.cu", "cav_abi.cu"]
 HEADERS = ["cav_common.cuh", "cav_orca.cuh", "cav_tpa_common.cuh", "cav_sortnet.cuh", "cav_scenario_gen.cuh", "cav_hd.cuh", "cav_keys.cuh", "cav_tti.cuh", "cav_math.cuh", "cav_move.cuh", "cav_orca_core.cuh", "cav_kdtree.cuh", "cav_kernels.h", os.path.join(ROOT, "include", "cavoid.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",

@@ -35,6 +35,7 @@ struct cav_handle_s {
     int split_parts;   // number of env ranges (0 = no split)
     int split_at[5];   // range k = [split_at[k], split_at[k + 1])
     // environment scheduling of k_policy_move_v2 (cav_policy.cu, EnvSchedule): the only device memory the library owns
+    const float *ga3c_blob;  // GA3C-CADRL weights (cav_bind_ga3c), borrowed
     EnvSchedule sched;
     cudaStream_t sort_stream;
     cudaEvent_t ev_policy[4], ev_sorted;
@@ -273,6 +274,7 @@ int cav_create(const cav_config_t *cfg, cav_handle_t *out) {
     // fills the SMs that policy(B)'s tail leaves idle.  Caller-visible semantics are unchanged (everything is ordered
     // after the caller's earlier work and before its later work; graph capture records the fork / join as edges).
     // CAV_STEP_SPLIT=0 disables it, 2..4 picks the number of ranges (default 2).
+    h->ga3c_blob = nullptr;
     h->split_parts = 0;
     for (int k = 0; k < 3; ++k) h->aux[k] = nullptr, h->ev_join[k] = nullptr;
     h->ev_fork = nullptr;
@@ -430,7 +432,17 @@ static cudaError_t debug_after(const char *name, cudaError_t ce) {
         (h)->launches++;                                                                       \
     } while (0)
 
+// the network for the CAV_POLICY_GA3C agents -> bufs.actions, ahead of the kernels that consume the actions
+static int do_ga3c(cav_handle_t h, float *probs, cudaStream_t st) {
+    CAV_CUDA(h, "ga3c_policy", run_ga3c_policy(h->bufs, h->cfg, h->ga3c_blob, probs, st));
+    return CAV_OK;
+}
+
 static int do_policy_move(cav_handle_t h, const float *ext, int phases, double dt, cudaStream_t st) {
+    if (h->ga3c_blob && (phases & 1)) {
+        const int rc = do_ga3c(h, nullptr, st);
+        if (rc) return rc;
+    }
     if (h->use_v2_policy) {
         const cudaError_t ce = debug_after(
             "policy_move_v2", (h->cfg.precision == CAV_F64)
@@ -523,6 +535,10 @@ static int step_split(cav_handle_t h, const float *ext, double dt, cudaStream_t 
     };
     // range 0 runs on the caller's stream, range k > 0 on helper stream k - 1
     auto stream_of = [&](int k) { return k == 0 ? st : h->aux[k - 1]; };
+    if (h->ga3c_blob) {
+        const int rc = do_ga3c(h, nullptr, st);
+        if (rc) return rc;
+    }
     CAV_CUDA(h, "step fork", cudaEventRecord(h->ev_fork, st));
     h->launches--;
     for (int k = 1; k < P; ++k) {
@@ -639,6 +655,39 @@ int cav_k_observe(cav_handle_t h, const uint8_t *env_mask, cav_stream_t stream) 
     if (rc) return rc;
     if (h->has_laser) rc = do_laser(h, env_mask, (cudaStream_t)stream);
     return rc;
+}
+
+int cav_bind_ga3c(cav_handle_t h, const float *blob) {
+    if (!valid(h)) return fail(nullptr, CAV_ERR_BAD_HANDLE, "cav_bind_ga3c: bad handle");
+    if (!blob) {
+        h->ga3c_blob = nullptr;  // detach
+        return CAV_OK;
+    }
+    if ((reinterpret_cast<uintptr_t>(blob) & 15u) != 0) return fail(h, CAV_ERR_MISALIGNED, "cav_bind_ga3c: blob must be 16-byte aligned");
+    const cav_config_t &c = h->cfg;
+    // GA3CCADRLPolicy.find_next_action reads obs['pref_speed'] and feeds the flattened observation: the network's first five
+    // inputs must be the scalars it was trained on
+    if (c.obs_offset[CAV_OBS_PREF_SPEED] < 0 || c.obs_offset[CAV_OBS_NUM_OTHER_AGENTS] < 0)
+        return fail(h, CAV_ERR_BAD_CONFIG, "cav_bind_ga3c: STATES_IN_OBS must hold num_other_agents and pref_speed");
+    h->ga3c_blob = blob;
+    return CAV_OK;
+}
+
+int cav_k_ga3c(cav_handle_t h, float *probs, cav_stream_t stream) {
+    CAV_CHECK_READY(h, "cav_k_ga3c");
+    if (!h->ga3c_blob) return fail(h, CAV_ERR_NOT_BOUND, "cav_k_ga3c: no network bound (cav_bind_ga3c)");
+    h->launches = 0;
+    return do_ga3c(h, probs, (cudaStream_t)stream);
+}
+
+int cav_ga3c_forward(const float *blob, const float *X, int32_t rows, float *probs, int32_t *action_index,
+                     cav_stream_t stream) {
+    if (!blob || (!X && rows > 0)) return fail(nullptr, CAV_ERR_NULL_POINTER, "cav_ga3c_forward: blob / X is NULL");
+    if (rows < 0) return fail(nullptr, CAV_ERR_BAD_CONFIG, "cav_ga3c_forward: rows < 0");
+    if ((reinterpret_cast<uintptr_t>(blob) & 15u) != 0) return fail(nullptr, CAV_ERR_MISALIGNED, "cav_ga3c_forward: blob must be 16-byte aligned");
+    const cudaError_t ce = run_ga3c_forward(blob, X, rows, probs, action_index, (cudaStream_t)stream);
+    if (ce != cudaSuccess) return fail(nullptr, CAV_ERR_CUDA, "cav_ga3c_forward: %s", cudaGetErrorString(ce));
+    return CAV_OK;
 }
 
 int cav_last_launch_count(cav_handle_t h) { return valid(h) ? h->launches : 0; }

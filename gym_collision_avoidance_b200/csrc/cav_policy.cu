@@ -247,6 +247,10 @@ __global__ void __launch_bounds__(32 * CAV_PM_WARPS, CAV_PM_MINB)
                 const float2 x = ext ? reinterpret_cast<const float2 *>(ext)[gi] : make_float2(0.f, 0.f);
                 a0 = (T)x.x;
                 a1 = (T)x.y;
+            } else if (pol == CAV_POLICY_GA3C) {  // GA3CCADRLPolicy.py:80-84: k_ga3c (cav_ga3c.cu) wrote it this step
+                const float2 x = reinterpret_cast<const float2 *>(b.actions)[gi];
+                a0 = (T)x.x;
+                a1 = (T)x.y;
             } else {  // CAV_POLICY_LEARNING, LearningPolicy.py:30-32
                 const float2 x = ext ? reinterpret_cast<const float2 *>(ext)[gi] : make_float2(0.f, 0.f);
                 a1 = p.max_heading_change * ((T)2. * (T)x.y - (T)1.);

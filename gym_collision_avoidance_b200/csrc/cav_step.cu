@@ -233,6 +233,10 @@ __global__ void __launch_bounds__(512) k_policy_move(DevBuffers b, KParams<T> p,
                     const float2 x = ext ? reinterpret_cast<const float2 *>(ext)[base + li] : make_float2(0.f, 0.f);
                     a0 = (T)x.x;
                     a1 = (T)x.y;
+                } else if (pol == CAV_POLICY_GA3C) {  // GA3CCADRLPolicy.py:80-84: k_ga3c (cav_ga3c.cu) wrote it this step
+                    const float2 x = reinterpret_cast<const float2 *>(b.actions)[base + li];
+                    a0 = (T)x.x;
+                    a1 = (T)x.y;
                 } else {  // CAV_POLICY_LEARNING, LearningPolicy.py:30-32
                     const float2 x = ext ? reinterpret_cast<const float2 *>(ext)[base + li] : make_float2(0.f, 0.f);
                     a1 = p.max_heading_change * ((T)2. * (T)x.y - (T)1.);

@@ -153,6 +153,28 @@ class Cavoid(object):
                                      int(accumulate_stats), self._stream(stream)), "cav_reset")
         self.launches += self.L.cav_last_launch_count(self._h)
 
+    def bind_ga3c(self, blob):
+        """Attach the GA3C-CADRL network (cav_bind_ga3c): ``blob`` is the float32 weight blob (numpy array or CUDA tensor,
+        ``envs/policies/GA3C_CADRL/network.py: load_blob``); None detaches.  The tensor is kept alive by this object."""
+        if blob is None:
+            self._ga3c_blob = None
+            self._check(self.L.cav_bind_ga3c(self._h, None), "cav_bind_ga3c")
+            return
+        if not isinstance(blob, torch.Tensor):
+            import numpy as np
+            blob = torch.from_numpy(np.ascontiguousarray(blob, dtype=np.float32))
+        blob = blob.to(device=self.device, dtype=torch.float32).contiguous()
+        if blob.numel() != abi.CAV_GA3C_BLOB_FLOATS:
+            raise abi.CavoidError("GA3C-CADRL weight blob must hold %d floats" % abi.CAV_GA3C_BLOB_FLOATS)
+        self._ga3c_blob = blob
+        self._check(self.L.cav_bind_ga3c(self._h, blob.data_ptr()), "cav_bind_ga3c")
+
+    def k_ga3c(self, probs=None, stream=None):
+        """The network for every live CAV_POLICY_GA3C agent -> state.actions; ``probs`` (optional float32 [E*N*11] CUDA
+        tensor) receives the softmax rows of those agents."""
+        self._check(self.L.cav_k_ga3c(self._h, _ptr(probs), self._stream(stream)), "cav_k_ga3c")
+        self.launches += self.L.cav_last_launch_count(self._h)
+
     def env_schedule(self, stream=None):
         """(order, cost) of the policy + move kernel's environment schedule (cav_env_schedule) as int32 tensors, or None
         when the handle has no schedule (fewer than 2048 environments, CAV_ENV_ORDER=0, sub-warp-group policy kernel)."""

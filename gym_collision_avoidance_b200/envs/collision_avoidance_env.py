@@ -199,6 +199,7 @@ class CollisionAvoidanceEnv(object):
         hs = HostState(self._c)
         n = len(self.agents)
         hs.num_active[0] = n
+        ga3c = None
         for i, a in enumerate(self.agents):
             hs.pv[0, i] = [a.pos_global_frame[0], a.pos_global_frame[1], a.vel_global_frame[0], a.vel_global_frame[1]]
             hs.goal[0, i] = [a.goal_global_frame[0], a.goal_global_frame[1], a.radius, a.pref_speed]
@@ -214,10 +215,18 @@ class CollisionAvoidanceEnv(object):
             hs.flags[0, i] = f
             hs.step_num[0, i] = a.step_num
             hs.kinds[0, i] = abi.make_kind(_kernel_id(a.policy, "policy"), _kernel_id(a.dynamics_model, "dynamics"))
+            if hs.kinds[0, i] & 0xff == abi.CAV_POLICY_GA3C:
+                ga3c = a.policy
             hs.aux0[0, i] = [a.speed_global_frame, a.delta_heading_global_frame, a.vel_ego_frame[0], a.vel_ego_frame[1]]
             hs.past_actions[0, i] = a.past_actions.reshape(-1)
             hs.past_vel[0, i] = a.past_global_velocities.reshape(-1)
             hs.actions[0, i] = a.past_actions[0]
+        if ga3c is not None and full:
+            # one network per environment (the reference loads one TF session per GA3CCADRLPolicy object; agents that were
+            # initialised from different checkpoints cannot share a device network)
+            if ga3c.weight_blob is None:
+                raise abi.CavoidError("GA3CCADRLPolicy: call agent.policy.initialize_network() before env.set_agents / reset")
+            self._cav.bind_ga3c(ga3c.weight_blob)
         self._cav.state.load_host(hs, cols=None if full else self._AGENT_COLS)
 
     def _download(self):

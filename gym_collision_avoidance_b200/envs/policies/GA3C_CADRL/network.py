@@ -29,29 +29,55 @@ class Actions(object):
 
 
 def _check_graph(nodes):
-    """The meta-graph must be the network cavoid.h documents; anything else is rejected instead of mis-evaluated."""
+    """The meta-graph must be the network cavoid.h documents; anything else is rejected instead of mis-evaluated.  Node
+    names differ between TF versions (the IROS18 graph says ``rnn/while/rnn/lstm_cell/lstm_cell/...``, the 2019 ones
+    ``rnn/while/lstm_cell/...``), so nodes are found by op and wiring."""
     def need(cond, what):
         if not cond:
             raise abi.CavoidError("GA3C-CADRL meta-graph: unexpected %s" % what)
+
+    def ins(name):
+        return [i for i in nodes[name]["inputs"] if not i.startswith("^")]
+
+    def const(name):
+        return nodes[name]["attrs"]["value"]
     need(nodes.get("X", {}).get("op") == "Placeholder" and nodes["X"]["attrs"]["shape"] == ("shape", [-1, X_LEN]), "X shape")
-    need("Softmax" in nodes and nodes["Softmax"]["inputs"] == ["logits_p/BiasAdd"], "output head")
-    need(nodes["sub"]["inputs"] == ["X", "Const"] and nodes["div"]["inputs"] == ["sub", "Const_1"], "input normalisation")
-    need(list(nodes["Reshape/shape"]["attrs"]["value"]) == [-1, MAX_OTHERS, 7], "sequence reshape")
-    need(list(nodes["strided_slice_1/stack"]["attrs"]["value"]) == [0, 1] and
-         list(nodes["strided_slice_1/stack_1"]["attrs"]["value"]) == [0, 5], "host-state slice")
-    need(list(nodes["strided_slice_2/stack"]["attrs"]["value"]) == [0, 5], "other-agent slice")
-    need(nodes["ToInt32"]["inputs"] == ["strided_slice"] and nodes["sequence_length"]["inputs"] == ["ToInt32"], "sequence length")
-    cell = "rnn/while/rnn/lstm_cell/lstm_cell/"
-    need(float(nodes[cell + "add/y"]["attrs"]["value"]) == 1.0, "LSTM forget bias")
-    need(nodes[cell + "split"]["attrs"]["num_split"] == 4, "LSTM gate split")
-    need(nodes[cell + "Sigmoid_1"]["inputs"] == [cell + "split"] and nodes[cell + "Tanh"]["inputs"] == [cell + "split:1"] and
-         nodes[cell + "add"]["inputs"][0] == cell + "split:2" and nodes[cell + "Sigmoid_2"]["inputs"] == [cell + "split:3"],
+    need("Softmax" in nodes and ins("Softmax") == ["logits_p/BiasAdd"], "output head")
+    need(ins("sub") == ["X", "Const"] and nodes["sub"]["op"] == "Sub" and ins("div") == ["sub", "Const_1"] and
+         nodes["div"]["op"] == "RealDiv", "input normalisation")
+    need(list(const("Reshape/shape")) == [-1, MAX_OTHERS, 7] and ins("Reshape")[0] == "strided_slice_2", "sequence reshape")
+    need(ins("strided_slice")[0] == "X" and list(const("strided_slice/stack")) == [0, 0] and
+         list(const("strided_slice/stack_1")) == [0, 1], "sequence-length slice")
+    need(ins("strided_slice_1")[0] == "div" and list(const("strided_slice_1/stack")) == [0, 1] and
+         list(const("strided_slice_1/stack_1")) == [0, 5], "host-state slice")
+    need(ins("strided_slice_2")[0] == "div" and list(const("strided_slice_2/stack")) == [0, 5], "other-agent slice")
+    casts = [n for n, nd in nodes.items() if nd["op"] == "Cast" and ins(n) == ["strided_slice"]]
+    need(len(casts) == 1 and nodes[casts[0]]["attrs"]["DstT"] == ("type", 3), "sequence length cast")
+    splits = [n for n, nd in nodes.items() if nd["op"] == "Split" and "gradients" not in n and "lstm_cell" in n]
+    need(len(splits) == 1 and nodes[splits[0]]["attrs"]["num_split"] == 4, "LSTM gate split")
+    cell = splits[0][:-len("split")]
+    need(float(const(cell + "add/y")) == 1.0, "LSTM forget bias")
+    need(ins(cell + "Sigmoid_1") == [cell + "split"] and ins(cell + "Tanh") == [cell + "split:1"] and
+         ins(cell + "add")[0] == cell + "split:2" and ins(cell + "Sigmoid_2") == [cell + "split:3"],
          "LSTM gate order (i, j, f, o)")
-    need(nodes["layer1_input"]["inputs"][:2] == ["strided_slice_1", "rnn/while/Exit_3"], "layer1 input")
-    for a, b in (("layer1", "layer1_input"), ("layer2", "layer1/Relu"), ("fullyconnected1", "Flatten/Reshape"),
-                 ("logits_p", "fullyconnected1/Relu")):
-        need(nodes[a + "/MatMul"]["inputs"][0] == b, a + " input")
-    need(nodes["Flatten/Reshape"]["inputs"][0] == "layer2/Relu", "flatten input")
+    need(ins(cell + "add_1") == [cell + "mul", cell + "mul_1"] and ins(cell + "mul")[0] == cell + "Sigmoid" and
+         ins(cell + "mul_1") == [cell + "Sigmoid_1", cell + "Tanh"] and
+         ins(cell + "mul_2") == [cell + "Sigmoid_2", cell + "Tanh_1"] and ins(cell + "Tanh_1") == [cell + "add_1"], "LSTM cell update")
+    l1 = ins("layer1_input")
+    need(nodes["layer1_input"]["op"] == "ConcatV2" and l1[0] == "strided_slice_1" and nodes[l1[1]]["op"] == "Exit", "layer1 input")
+    # the Exit must carry h (the state concatenated with the input inside the cell), not c
+    sw = ins(l1[1])[0]
+    merge = ins(sw)[0]
+    ident = [n for n, nd in nodes.items() if nd["op"] == "Identity" and ins(n) == [sw + ":1"]]
+    concat = [n for n, nd in nodes.items() if nd["op"] == "ConcatV2" and n.startswith(cell) and len(ins(n)) == 3]
+    need(len(ident) == 1 and any(ident[0] == ins(c)[1] for c in concat) and nodes[merge]["op"] == "Merge", "recurrent state wiring")
+    need(ins("layer1/MatMul")[0] == "layer1_input" and ins("layer2/MatMul")[0] == "layer1/Relu" and
+         ins("logits_p/MatMul")[0] == "fullyconnected1/Relu", "dense stack")
+    flat = ins("fullyconnected1/MatMul")[0]
+    need(nodes[flat]["op"] == "Reshape" and ins(flat)[0] == "layer2/Relu", "flatten input")
+    for name in ("layer1", "layer2", "fullyconnected1"):
+        need(nodes[name + "/Relu"]["op"] == "Relu" and ins(name + "/Relu") == [name + "/BiasAdd"] and
+             ins(name + "/BiasAdd")[0] == name + "/MatMul", name + " activation")
 
 
 def pack_blob(variables, avg, std):

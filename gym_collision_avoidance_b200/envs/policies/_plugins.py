@@ -87,3 +87,51 @@ class RVOPolicy(InternalPolicy):
         self.max_delta_heading = np.pi / 6
         self.has_fixed_speed = False
         self.heading_noise = False
+
+
+class GA3CCADRLPolicy(InternalPolicy):
+    """Reference ``policies/GA3CCADRLPolicy.py:10-84``: the pre-trained GA3C-CADRL LSTM network (Everett et al., IROS 2018)
+    picks one of 11 discrete ``[speed, heading change]`` actions from the agent's own observation.  Here the network runs
+    on the GPU inside the step (``cav_ga3c.cu``); ``initialize_network`` reads the reference's TF1 checkpoint files
+    without TensorFlow (``GA3C_CADRL/network.py``) and the environment binds the weights when it is built.
+
+    The checkpoints are the reference's data and are not redistributed with this package: ``checkpt_dir`` is an absolute
+    directory, or a name below ``$GA3C_CADRL_CHECKPOINTS`` (default: the reference's own
+    ``envs/policies/GA3C_CADRL/checkpoints`` if ``gym_collision_avoidance`` is importable)."""
+    kernel_id = abi.CAV_POLICY_GA3C
+
+    def __init__(self):
+        InternalPolicy.__init__(self, str="GA3C_CADRL")
+        from .GA3C_CADRL import network
+        self.possible_actions = network.Actions()
+        self.device = "cuda:0"
+        self.nn = network.NetworkVP_rnn(self.device, "network", self.possible_actions.num_actions)
+
+    @staticmethod
+    def _checkpoint_root():
+        import os
+        root = os.environ.get("GA3C_CADRL_CHECKPOINTS")
+        if root:
+            return root
+        try:
+            import importlib.util
+            spec = importlib.util.find_spec("gym_collision_avoidance")
+            if spec and spec.submodule_search_locations:
+                return os.path.join(list(spec.submodule_search_locations)[0], "envs", "policies", "GA3C_CADRL", "checkpoints")
+        except (ImportError, ValueError):
+            pass
+        raise abi.CavoidError("GA3C-CADRL checkpoints: set GA3C_CADRL_CHECKPOINTS or pass an absolute checkpt_dir")
+
+    def initialize_network(self, **kwargs):
+        """Same keywords as the reference (GA3CCADRLPolicy.py:24-47): ``checkpt_name`` (default ``network_01900000``),
+        ``checkpt_dir`` (absolute, or relative to the checkpoint root; default ``IROS18``)."""
+        import os
+        name = kwargs.get("checkpt_name", "network_01900000")
+        d = kwargs.get("checkpt_dir", "IROS18")
+        if not os.path.isabs(d):
+            d = os.path.join(self._checkpoint_root(), d)
+        self.nn.simple_load(os.path.join(d, name))
+
+    @property
+    def weight_blob(self):
+        return self.nn.blob

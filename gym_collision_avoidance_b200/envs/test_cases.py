@@ -10,6 +10,7 @@ from .dynamics.ExternalDynamics import ExternalDynamics
 from .dynamics.UnicycleDynamics import UnicycleDynamics
 from .dynamics.UnicycleDynamicsMaxTurnRate import UnicycleDynamicsMaxTurnRate
 from .policies.ExternalPolicy import ExternalPolicy
+from .policies.GA3CCADRLPolicy import GA3CCADRLPolicy
 from .policies.LearningPolicy import LearningPolicy
 from .policies.NonCooperativePolicy import NonCooperativePolicy
 from .policies.RVOPolicy import RVOPolicy
@@ -19,7 +20,7 @@ from .sensors.LaserScanSensor import LaserScanSensor
 from .sensors.OtherAgentsStatesSensor import OtherAgentsStatesSensor
 
 policy_dict = {"RVO": RVOPolicy, "noncoop": NonCooperativePolicy, "external": ExternalPolicy,
-               "learning": LearningPolicy, "static": StaticPolicy}
+               "learning": LearningPolicy, "static": StaticPolicy, "GA3C_CADRL": GA3CCADRLPolicy}
 sensor_dict = {"other_agents_states": OtherAgentsStatesSensor, "laserscan": LaserScanSensor}
 dynamics_dict = {"unicycle": UnicycleDynamics, "external": ExternalDynamics,
                  "unicycle_max_turn_rate": UnicycleDynamicsMaxTurnRate}

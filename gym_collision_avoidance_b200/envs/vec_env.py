@@ -17,7 +17,8 @@ from . import config as _config
 from .scenarios import random_scenario_bank
 
 POLICY_IDS = {"RVO": abi.CAV_POLICY_RVO, "noncoop": abi.CAV_POLICY_NONCOOP, "static": abi.CAV_POLICY_STATIC,
-              "external": abi.CAV_POLICY_EXTERNAL, "learning": abi.CAV_POLICY_LEARNING}
+              "external": abi.CAV_POLICY_EXTERNAL, "learning": abi.CAV_POLICY_LEARNING,
+              "GA3C_CADRL": abi.CAV_POLICY_GA3C}
 DYNAMICS_IDS = {"unicycle": abi.CAV_DYN_UNICYCLE, "unicycle_max_turn_rate": abi.CAV_DYN_UNICYCLE_MAX_TURN_RATE,
                 "external": abi.CAV_DYN_EXTERNAL}
 
@@ -48,7 +49,7 @@ class VecCollisionAvoidanceEnv(object):
     def __init__(self, num_envs, config=None, num_agents=None, device="cuda:0", precision="f64", scenario_bank=None,
                  bank_kinds=None, bank_num_active=None, policies="RVO", dynamics="unicycle", auto_reset=True,
                  use_cuda_graph=True, history_len=0, track_aux=False, seed=0, num_scenarios=None,
-                 scenario_source="host", obs_f32=False, host_lookahead=None):
+                 scenario_source="host", obs_f32=False, host_lookahead=None, ga3c=None):
         if config is None:
             config = _config.make_config(num_agents or 10, evaluate=True)
         self.config = config
@@ -94,6 +95,15 @@ class VecCollisionAvoidanceEnv(object):
         self.ext_actions = torch.zeros((self.num_envs, self.num_agents, 2), dtype=torch.float32, device=self.device)
         self.agent_dones = torch.zeros_like(st.done)  # which_agents_done of the step (kept across auto-reset)
         kinds_np = np.asarray(bank_kinds, dtype=np.uint32) & 0xff
+        # GA3C-CADRL agents ("GA3C_CADRL"): `ga3c` is the weight blob (float32 array / tensor) or the prefix of a TF1
+        # checkpoint of the reference (".../IROS18/network_01900000"), read without TensorFlow
+        if ga3c is not None:
+            if isinstance(ga3c, str):
+                from .policies.GA3C_CADRL import network as _ga3c_network
+                ga3c = _ga3c_network.load_blob(ga3c)
+            self.cav.bind_ga3c(ga3c)
+        elif (kinds_np == abi.CAV_POLICY_GA3C).any():
+            raise abi.CavoidError("GA3C_CADRL agents need the network: pass ga3c=<checkpoint prefix or weight blob>")
         self.has_external_agents = bool(np.isin(kinds_np, [abi.CAV_POLICY_EXTERNAL, abi.CAV_POLICY_LEARNING]).any())
         # ---- host-buffer API (step_host): pinned mirrors, a copy stream, optional one-step lookahead ----
         # The host API hands observations / rewards out as float32.  With float32 columns (precision f32 or obs_f32) the

@@ -467,39 +467,13 @@ static int cavo_world_to_cell(const cavo_map_t *m, double px, double py, int *gx
     return 1;
 }
 
-#define REAL double
-#define SFX(n) n##_f64
-#define R_SIN sin
-#define R_COS cos
-#define R_ATAN2 atan2
-#define R_SQRT sqrt
-#define R_FABS fabs
-#define R_FMOD fmod
-#define R_RINT rint
-#include "cav_oracle_impl.h"
-#undef REAL
-#undef SFX
-#undef R_SIN
-#undef R_COS
-#undef R_ATAN2
-#undef R_SQRT
-#undef R_FABS
-#undef R_FMOD
-#undef R_RINT
-
-#define REAL float
-#define SFX(n) n##_f32
-#define R_SIN sinf
-#define R_COS cosf
-#define R_ATAN2 atan2f
-#define R_SQRT sqrtf
 /* ------------------------------------------------------------------------------------------------------------
  * GA3C-CADRL network forward pass (policies/GA3CCADRLPolicy.py:49-84 -> policies/GA3C_CADRL/network.py:37-41
  * sess.run('Softmax:0')).  TensorFlow is not in this image, so the restatement follows the reference's own GRAPH
  * (network_01900000.meta, node for node: sub / div / strided_slice* / Reshape / transpose / dynamic_rnn LSTMCell while
  * loop with sequence_length Select / layer1_input concat / layer1 / layer2 / fullyconnected1 / logits_p / Softmax) and
  * is pinned against oracle/tf1_graph.py, a numpy interpreter that EXECUTES that graph's nodes with the checkpoint's
- * variables (tests/test_ga3c_cpu.py, tests/golden/ga3c_iros18.npz).  float32 throughout, sums in ascending k.
+ * variables (tests/test_ga3c_cpu.py, tests/golden/ga3c/ga3c_iros18.npz).  float32 throughout, sums in ascending k.
  * Weight blob layout: include/cavoid.h (CAV_GA3C_*).
  * ---------------------------------------------------------------------------------------------------------- */
 static const float *g_ga3c_blob = NULL;
@@ -619,6 +593,32 @@ static void ga3c_action(int j, double *speed, double *dheading) {
     }
 }
 
+#define REAL double
+#define SFX(n) n##_f64
+#define R_SIN sin
+#define R_COS cos
+#define R_ATAN2 atan2
+#define R_SQRT sqrt
+#define R_FABS fabs
+#define R_FMOD fmod
+#define R_RINT rint
+#include "cav_oracle_impl.h"
+#undef REAL
+#undef SFX
+#undef R_SIN
+#undef R_COS
+#undef R_ATAN2
+#undef R_SQRT
+#undef R_FABS
+#undef R_FMOD
+#undef R_RINT
+
+#define REAL float
+#define SFX(n) n##_f32
+#define R_SIN sinf
+#define R_COS cosf
+#define R_ATAN2 atan2f
+#define R_SQRT sqrtf
 #define R_FABS fabsf
 #define R_FMOD fmodf
 #define R_RINT rintf

@@ -49,12 +49,49 @@ def lib():
                                       ctypes.c_int, fp, fp, vp, ctypes.POINTER(ctypes.c_int)]
         L.cavo_kd_build.argtypes = [vp, vp, vp, ctypes.c_int]
         L.cavo_kd_build.restype = None
+        L.cavo_ga3c_forward.argtypes = [vp, vp, ctypes.c_int, vp, vp]
+        L.cavo_ga3c_forward.restype = None
+        L.cavo_set_ga3c.argtypes = [vp]
+        L.cavo_set_ga3c.restype = None
+        L.cavo_ga3c_gather.argtypes = [cfgp, vp]
+        L.cavo_ga3c_gather.restype = None
         _LIB = L
     return _LIB
 
 
 def _ptr(a):
     return None if a is None else a.ctypes.data
+
+
+_GA3C_BLOB = None  # keeps the array behind cavo_set_ga3c's pointer alive
+
+
+def set_ga3c(blob):
+    """Weights for CAV_POLICY_GA3C agents in Oracle.policy / Oracle.step (float32 blob, include/cavoid.h layout)."""
+    global _GA3C_BLOB
+    import numpy as np
+    _GA3C_BLOB = None if blob is None else np.ascontiguousarray(blob, dtype=np.float32)
+    lib().cavo_set_ga3c(_ptr(_GA3C_BLOB))
+
+
+def ga3c_forward(blob, X):
+    """(softmax [rows, 11] float32, argmax [rows] int32) of the C restatement of the GA3C-CADRL network."""
+    import numpy as np
+    blob = np.ascontiguousarray(blob, dtype=np.float32)
+    X = np.ascontiguousarray(X, dtype=np.float32)
+    assert X.ndim == 2 and X.shape[1] == 138
+    probs = np.zeros((X.shape[0], 11), np.float32)
+    act = np.zeros(X.shape[0], np.int32)
+    lib().cavo_ga3c_forward(_ptr(blob), _ptr(X), X.shape[0], _ptr(probs), _ptr(act))
+    return probs, act
+
+
+def ga3c_gather(c):
+    """int16 [138]: packed-observation index feeding each network input (-1 = zero padding)."""
+    import numpy as np
+    src = np.zeros(138, np.int16)
+    lib().cavo_ga3c_gather(ctypes.byref(c), _ptr(src))
+    return src
 
 
 class Oracle(object):
