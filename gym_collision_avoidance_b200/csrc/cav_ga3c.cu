@@ -1,7 +1,7 @@
 // cav_ga3c.cu -- GA3C-CADRL policy network on the device (reference policies/GA3CCADRLPolicy.py:49-84 ->
 // policies/GA3C_CADRL/network.py:37-41 `sess.run(Softmax:0, {X: vec_obs})`; the graph is spelled out in include/cavoid.h).
 //
-// One CTA = 64 agents (rows) x 256 threads, float32 on the CUDA cores: the reference computes in float32 and the policy
+// One CTA = 64 agents (rows) x 256 threads (CAV_GA3C_ROWS), float32 on the CUDA cores: the reference computes in float32 and the policy
 // takes an ARGMAX, so the arithmetic stays IEEE float32 (TF32 / BF16 tensor-core inputs would move ~1e-3 of the softmax
 // and flip near-ties).  Every layer is a [64 rows] x [K] x [256 columns] product with the same register tile: thread
 // (cg = tid & 63, rg = tid >> 6) owns rows rg*16 .. +15 and
@@ -20,11 +20,15 @@
 #include "cavoid.h"
 #include "cav_kernels.h"
 
+#ifndef CAV_GA3C_ROWS
+#define CAV_GA3C_ROWS 64  // agents per CTA: 64 (256 threads, 149 KB shared) or 128 (512 threads, 225 KB, 128 registers)
+#endif
+
 namespace cav {
 
 namespace ga {
 constexpr int XL = CAV_GA3C_X_LEN, T = CAV_GA3C_MAX_OTHERS, H = CAV_GA3C_HIDDEN, F = CAV_GA3C_FC, A = CAV_GA3C_ACTIONS;
-constexpr int R = 64, NT = 256;
+constexpr int R = CAV_GA3C_ROWS, NT = 4 * R;  // 16 rows x 64 column groups per 64 threads
 constexpr int OFF_AVG = 0, OFF_STD = XL, OFF_WL = 2 * XL, OFF_BL = OFF_WL + (7 + H) * H * 4, OFF_W1 = OFF_BL + H * 4,
               OFF_B1 = OFF_W1 + (4 + H) * F, OFF_W2 = OFF_B1 + F, OFF_B2 = OFF_W2 + F * F, OFF_W3 = OFF_B2 + F,
               OFF_B3 = OFF_W3 + F * F, OFF_WO = OFF_B3 + F, OFF_BO = OFF_WO + F * A;
@@ -45,7 +49,19 @@ struct Ga3cEnvIn {  // MODE 1: rows are the agents of a bound handle
     short src[ga::XL];
 };
 
+#ifndef CAV_GA3C_FAST_MATH
+#define CAV_GA3C_FAST_MATH 0  // 1: MUFU-based exp / reciprocal in the gates (a few ulp, like Eigen's vectorised ones in TF)
+#endif
+#if CAV_GA3C_FAST_MATH
+__device__ __forceinline__ float ga_sigmoid(float x) { return __frcp_rn(1.0f + __expf(-x)); }
+__device__ __forceinline__ float ga_tanh(float x) {
+    const float t = __expf(-2.0f * fabsf(x));
+    return copysignf((1.0f - t) * __frcp_rn(1.0f + t), x);
+}
+#else
 __device__ __forceinline__ float ga_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float ga_tanh(float x) { return tanhf(x); }
+#endif
 
 __device__ __forceinline__ void ga_copy_to_smem(float *dst, const float *__restrict__ src, int floats, int tid) {
     const float4 *s4 = reinterpret_cast<const float4 *>(src);
@@ -114,7 +130,7 @@ __global__ void __launch_bounds__(ga::NT, 1)
     for (int i = tid; i < R * H / 4; i += NT) reinterpret_cast<float4 *>(sH)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
     for (int i = tid; i < R * XL; i += NT) {
-        const int r = i & (R - 1), k = i >> 6;
+        const int r = i & (R - 1), k = i / R;
         const int row = row0 + r;
         float x = 0.0f;
         if (sActive[r]) {
@@ -176,8 +192,8 @@ __global__ void __launch_bounds__(ga::NT, 1)
             float h;
             if (t < sLen[row]) {
                 const float gi = acc[r][0] + bl.x, gj = acc[r][1] + bl.y, gf = acc[r][2] + bl.z, go = acc[r][3] + bl.w;
-                c[r] = ga_sigmoid(gf + 1.0f) * c[r] + ga_sigmoid(gi) * tanhf(gj);
-                h = ga_sigmoid(go) * tanhf(c[r]);
+                c[r] = ga_sigmoid(gf + 1.0f) * c[r] + ga_sigmoid(gi) * ga_tanh(gj);
+                h = ga_sigmoid(go) * ga_tanh(c[r]);
             } else {
                 h = hc[row * H + cg];  // Select(time >= sequence_length, old, new)
             }

@@ -677,7 +677,14 @@ static void widen_end(widen_t *w) {
     free(w->rew);
 }
 
-int cavo_policy(const cav_config_t *cfg, const cav_buffers_t *b, const float *ext) { return DISPATCH(policy, cfg, b, ext); }
+int cavo_policy(const cav_config_t *cfg, const cav_buffers_t *b, const float *ext) {
+    if (!g_ga3c_blob) return DISPATCH(policy, cfg, b, ext);
+    widen_t w; /* GA3C-CADRL agents read their observation row */
+    widen_begin(&cfg, &b, &w);
+    const int rc = DISPATCH(policy, cfg, b, ext);
+    widen_end(&w);
+    return rc;
+}
 int cavo_dynamics(const cav_config_t *cfg, const cav_buffers_t *b, double dt) { return DISPATCH(dynamics, cfg, b, dt); }
 int cavo_pairwise_obs(const cav_config_t *cfg, const cav_buffers_t *b) {
     widen_t w;

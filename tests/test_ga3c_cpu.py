@@ -165,14 +165,14 @@ def test_observation_gather(N):
     assert list(src) == want
 
 
-@pytest.mark.parametrize("prec", ["f64", "f32"])
-def test_oracle_step_with_ga3c_agents(golden, prec):
+@pytest.mark.parametrize("prec,obs_f32", [("f64", False), ("f64", True), ("f32", False)])
+def test_oracle_step_with_ga3c_agents(golden, prec, obs_f32):
     """Two GA3C-CADRL agents swapping places (the reference's example pairs this policy with itself): both reach their goals,
     nobody collides; and in a mixed environment the RVO agents are untouched by the network being present."""
     cav_oracle.set_ga3c(golden["blob"])
     try:
         N = 2
-        c = to_cav_config(make_config(N, evaluate=True), 1, N, precision=prec, track_aux=True)
+        c = to_cav_config(make_config(N, evaluate=True), 1, N, precision=prec, track_aux=True, obs_f32=obs_f32)
         rows = np.array([[[-3.0, 0.0, 3.0, 0.0, 1.0, 0.5, 0.0], [3.0, 0.0, -3.0, 0.0, 1.0, 0.5, np.pi]]])
         bank = HostBank(rows, kinds=kinds_array(1, N, "GA3C_CADRL"))
         hs = HostState(c)
