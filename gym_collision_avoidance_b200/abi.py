@@ -11,6 +11,7 @@ CAV_GA3C_BLOB_FLOATS = 170784
 
 # cav_status_t
 CAV_OK = 0
+CAV_ERR_BAD_CONFIG = -1
 STATUS_NAMES = {0: "CAV_OK", -1: "CAV_ERR_BAD_CONFIG", -2: "CAV_ERR_NULL_POINTER", -3: "CAV_ERR_MISALIGNED",
                 -4: "CAV_ERR_NOT_BOUND", -5: "CAV_ERR_CUDA", -6: "CAV_ERR_BAD_HANDLE", -7: "CAV_ERR_UNSUPPORTED"}
 

@@ -36,6 +36,7 @@ struct cav_handle_s {
     int split_at[5];   // range k = [split_at[k], split_at[k + 1])
     // environment scheduling of k_policy_move_v2 (cav_policy.cu, EnvSchedule): the only device memory the library owns
     const float *ga3c_blob;  // GA3C-CADRL weights (cav_bind_ga3c), borrowed
+    int32_t *ga3c_list;      // scratch of k_ga3c_compact: E*N + 1 ints, owned (allocated by cav_bind_ga3c)
     EnvSchedule sched;
     cudaStream_t sort_stream;
     cudaEvent_t ev_policy[4], ev_sorted;
@@ -275,6 +276,7 @@ int cav_create(const cav_config_t *cfg, cav_handle_t *out) {
     // after the caller's earlier work and before its later work; graph capture records the fork / join as edges).
     // CAV_STEP_SPLIT=0 disables it, 2..4 picks the number of ranges (default 2).
     h->ga3c_blob = nullptr;
+    h->ga3c_list = nullptr;
     h->split_parts = 0;
     for (int k = 0; k < 3; ++k) h->aux[k] = nullptr, h->ev_join[k] = nullptr;
     h->ev_fork = nullptr;
@@ -358,7 +360,10 @@ int cav_create(const cav_config_t *cfg, cav_handle_t *out) {
 size_t cav_real_bytes(cav_handle_t h) { return valid(h) ? (h->cfg.precision == CAV_F64 ? 8 : 4) : 0; }
 
 size_t cav_workspace_bytes(cav_handle_t h) {
-    return (valid(h) && h->sched.order) ? (size_t)h->cfg.num_envs * (sizeof(int) + sizeof(unsigned short)) : 0;
+    if (!valid(h)) return 0;
+    size_t b = h->sched.order ? (size_t)h->cfg.num_envs * (sizeof(int) + sizeof(unsigned short)) : 0;
+    if (h->ga3c_list) b += ((size_t)h->cfg.num_envs * h->cfg.num_agents + 1) * sizeof(int32_t);
+    return b;
 }
 
 int cav_env_schedule(cav_handle_t h, int32_t *order, uint16_t *cost, cav_stream_t stream) {
@@ -434,7 +439,7 @@ static cudaError_t debug_after(const char *name, cudaError_t ce) {
 
 // the network for the CAV_POLICY_GA3C agents -> bufs.actions, ahead of the kernels that consume the actions
 static int do_ga3c(cav_handle_t h, float *probs, cudaStream_t st) {
-    CAV_CUDA(h, "ga3c_policy", run_ga3c_policy(h->bufs, h->cfg, h->ga3c_blob, probs, st));
+    CAV_CUDA(h, "ga3c_policy", run_ga3c_policy(h->bufs, h->cfg, h->ga3c_blob, probs, h->ga3c_list, st));
     return CAV_OK;
 }
 
@@ -669,6 +674,13 @@ int cav_bind_ga3c(cav_handle_t h, const float *blob) {
     // inputs must be the scalars it was trained on
     if (c.obs_offset[CAV_OBS_PREF_SPEED] < 0 || c.obs_offset[CAV_OBS_NUM_OTHER_AGENTS] < 0)
         return fail(h, CAV_ERR_BAD_CONFIG, "cav_bind_ga3c: STATES_IN_OBS must hold num_other_agents and pref_speed");
+    if (!h->ga3c_list) {
+        const size_t n = (size_t)c.num_envs * c.num_agents + 1;
+        if (cudaMalloc(&h->ga3c_list, n * sizeof(int32_t)) != cudaSuccess) {
+            h->ga3c_list = nullptr;
+            return fail(h, CAV_ERR_CUDA, "cav_bind_ga3c: cudaMalloc of the agent list failed: %s", cudaGetErrorString(cudaGetLastError()));
+        }
+    }
     h->ga3c_blob = blob;
     return CAV_OK;
 }
@@ -706,6 +718,7 @@ int cav_destroy(cav_handle_t h) {
     if (h->ev_sorted) cudaEventDestroy(h->ev_sorted);
     for (int k = 0; k < 4; ++k)
         if (h->ev_policy[k]) cudaEventDestroy(h->ev_policy[k]);
+    if (h->ga3c_list) cudaFree(h->ga3c_list);
     if (h->sched.order) cudaFree(const_cast<int *>(h->sched.order));
     if (h->sched.cost) cudaFree(h->sched.cost);
     delete h;

@@ -1,7 +1,7 @@
 // cav_ga3c.cu -- GA3C-CADRL policy network on the device (reference policies/GA3CCADRLPolicy.py:49-84 ->
 // policies/GA3C_CADRL/network.py:37-41 `sess.run(Softmax:0, {X: vec_obs})`; the graph is spelled out in include/cavoid.h).
 //
-// One CTA = 64 agents (rows) x 256 threads (CAV_GA3C_ROWS), float32 on the CUDA cores: the reference computes in float32 and the policy
+// One CTA = 128 agents (rows) x 512 threads (CAV_GA3C_ROWS; 64 x 256 measured 18 % slower), float32 on the CUDA cores: the reference computes in float32 and the policy
 // takes an ARGMAX, so the arithmetic stays IEEE float32 (TF32 / BF16 tensor-core inputs would move ~1e-3 of the softmax
 // and flip near-ties).  Every layer is a [64 rows] x [K] x [256 columns] product with the same register tile: thread
 // (cg = tid & 63, rg = tid >> 6) owns rows rg*16 .. +15 and
@@ -12,6 +12,8 @@
 //                 activations [row][k] in shared memory, overwritten in place behind a barrier.
 // 64 FMAs per 5 LDS.128 in the inner loops (explicit fmaf: the library is built with -fmad=false for the ORCA solve).  Weights stream from the (L2-resident, 683 KB) blob into shared memory one
 // section at a time: LSTM kernel 71 KB, W1 68 KB, then 64-row slabs of the two 256 x 256 layers.
+// Inside the environment a first tiny kernel (k_ga3c_compact) lists the live agents whose policy is GA3C-CADRL, so that CTAs
+// are full whatever the policy mix and the share of finished agents (rows are independent; their order is immaterial).
 // Sequence handling as dynamic_rnn's: step t updates (c, h) of a row only while t < int(X[row][0]); the loop stops at the
 // CTA's longest sequence (the remaining steps would copy state through unchanged).
 #include <cuda_runtime.h>
@@ -21,7 +23,8 @@
 #include "cav_kernels.h"
 
 #ifndef CAV_GA3C_ROWS
-#define CAV_GA3C_ROWS 64  // agents per CTA: 64 (256 threads, 149 KB shared) or 128 (512 threads, 225 KB, 128 registers)
+#define CAV_GA3C_ROWS 128  // agents per CTA: 128 (512 threads, 225 KB shared, 128 registers: 2.77 ms at 163840 agents) or 64
+                           // (256 threads, 149 KB, 152 registers: 3.36 ms) -- profiles/r02m_ga3c_variants.txt
 #endif
 
 namespace cav {
@@ -42,10 +45,9 @@ constexpr size_t SMEM_BYTES = (size_t)(SW_FLOATS + SX_FLOATS) * 4 + R * 4 + R * 
 
 struct Ga3cEnvIn {  // MODE 1: rows are the agents of a bound handle
     const void *obs;
-    const uint32_t *flags, *kinds;
-    const int32_t *num_active;
+    const int32_t *list;   // compacted indices of the live GA3C agents (k_ga3c_compact), list[max_rows] = their count
     float *actions;
-    int obs_len, N, pref_off;
+    int obs_len, pref_off;
     short src[ga::XL];
 };
 
@@ -101,29 +103,19 @@ __global__ void __launch_bounds__(ga::NT, 1)
     float *sAct = sXo;                    // [R][F], aliases sXo / sXh / sH once the LSTM is done
     int *sLen = reinterpret_cast<int *>(sW + SW_FLOATS + SX_FLOATS);
     float *sLogit = reinterpret_cast<float *>(sLen + R);  // [R][12]
-    int *sActive = reinterpret_cast<int *>(sLogit + R * 12);
+    int *sRow = reinterpret_cast<int *>(sLogit + R * 12);  // global row (agent) index of each tile row, -1 = none
 
     const int tid = threadIdx.x;
     const int row0 = blockIdx.x * R;
     const int cg = tid & 63, rg = tid >> 6, rbase = rg * 16;
 
-    // ---- which rows run (MODE 1: live agents whose policy is GA3C) ----
-    int any = 1;
+    // ---- which rows run (MODE 1: the compacted list of live agents whose policy is GA3C) ----
     if (MODE == 1) {
-        int act = 0;
-        if (tid < R) {
-            const int gi = row0 + tid;
-            if (gi < rows) {
-                const int e = gi / env.N, a = gi - e * env.N;
-                const int n = env.num_active ? env.num_active[e] : env.N;
-                act = a < n && CAV_KIND_POLICY(env.kinds[gi]) == CAV_POLICY_GA3C && !(env.flags[gi] & CAV_FLAG_DONE);
-            }
-            sActive[tid] = act;
-        }
-        any = __syncthreads_or(act);
-        if (!any) return;
+        const int count = env.list[rows];
+        if (row0 >= count) return;
+        if (tid < R) sRow[tid] = row0 + tid < count ? env.list[row0 + tid] : -1;
     } else if (tid < R) {
-        sActive[tid] = row0 + tid < rows;
+        sRow[tid] = row0 + tid < rows ? row0 + tid : -1;
     }
     // ---- inputs: (X - avg) / std, sequence length, zero initial h ----
     for (int i = tid; i < R * XO_STRIDE / 4; i += NT) reinterpret_cast<float4 *>(sXo)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -131,9 +123,9 @@ __global__ void __launch_bounds__(ga::NT, 1)
     __syncthreads();
     for (int i = tid; i < R * XL; i += NT) {
         const int r = i & (R - 1), k = i / R;
-        const int row = row0 + r;
+        const int row = sRow[r];
         float x = 0.0f;
-        if (sActive[r]) {
+        if (row >= 0) {
             if (MODE == 0) {
                 x = X[(size_t)row * XL + k];
             } else {
@@ -143,7 +135,7 @@ __global__ void __launch_bounds__(ga::NT, 1)
         }
         const float xn = (x - __ldg(blob + OFF_AVG + k)) / __ldg(blob + OFF_STD + k);
         if (k == 0) {
-            int len = sActive[r] ? (int)x : 0;  // ToInt32(X[:, 0])
+            int len = row >= 0 ? (int)x : 0;  // ToInt32(X[:, 0])
             sLen[r] = len < 0 ? 0 : (len > T ? T : len);
         } else if (k < 5) {
             sXh[r * 4 + (k - 1)] = xn;
@@ -258,8 +250,8 @@ __global__ void __launch_bounds__(ga::NT, 1)
         for (int r = 0; r < 16; ++r) sLogit[(rbase + r) * 12 + cg] = lo[r] + b;
     }
     __syncthreads();
-    if (tid < R && sActive[tid]) {
-        const int row = row0 + tid;
+    if (tid < R && sRow[tid] >= 0) {
+        const int row = sRow[tid];
         const float *lg = sLogit + tid * 12;
         float mx = lg[0];
         int best = 0;
@@ -298,6 +290,26 @@ __global__ void __launch_bounds__(ga::NT, 1)
             reinterpret_cast<float2 *>(env.actions)[row] = make_float2((float)((double)ps * sp), (float)dh);
         }
     }
+}
+
+// indices of the live agents whose policy is GA3C-CADRL, in any order; list[rows] counts them (zeroed by the caller)
+__global__ void __launch_bounds__(256) k_ga3c_compact(const uint32_t *__restrict__ flags, const uint32_t *__restrict__ kinds,
+                                                      const int32_t *__restrict__ num_active, int N, int rows,
+                                                      int32_t *__restrict__ list) {
+    const int gi = blockIdx.x * blockDim.x + threadIdx.x;
+    bool act = false;
+    if (gi < rows) {
+        const int e = gi / N, a = gi - e * N;
+        const int n = num_active ? num_active[e] : N;
+        act = a < n && CAV_KIND_POLICY(kinds[gi]) == CAV_POLICY_GA3C && !(flags[gi] & CAV_FLAG_DONE);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, act);
+    if (!m) return;
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(list + rows, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (act) list[base + __popc(m & ((1u << lane) - 1u))] = gi;
 }
 
 template <int MODE, typename OT>
@@ -339,15 +351,18 @@ void ga3c_gather_table(const cav_config_t &cfg, short *src) {
 }
 
 cudaError_t run_ga3c_policy(const cav_buffers_t &bufs, const cav_config_t &cfg, const float *blob, float *probs,
-                            cudaStream_t st) {
+                            int32_t *list, cudaStream_t st) {
+    const int nrows = cfg.num_envs * cfg.num_agents;
+    cudaError_t ce = cudaMemsetAsync(list + nrows, 0, sizeof(int32_t), st);
+    if (ce != cudaSuccess) return ce;
+    k_ga3c_compact<<<(nrows + 255) / 256, 256, 0, st>>>(bufs.flags, bufs.kinds, bufs.num_active, cfg.num_agents, nrows, list);
+    ce = cudaGetLastError();
+    if (ce != cudaSuccess) return ce;
     Ga3cEnvIn env{};
     env.obs = bufs.obs;
-    env.flags = bufs.flags;
-    env.kinds = bufs.kinds;
-    env.num_active = bufs.num_active;
+    env.list = list;
     env.actions = bufs.actions;
     env.obs_len = cfg.obs_len;
-    env.N = cfg.num_agents;
     env.pref_off = cfg.obs_offset[CAV_OBS_PREF_SPEED];
     ga3c_gather_table(cfg, env.src);
     const int rows = cfg.num_envs * cfg.num_agents;

@@ -49,7 +49,8 @@ cudaError_t run_env_order(const EnvSchedule &sched, const int *at, int nranges, 
 
 // GA3C-CADRL policy network (cav_ga3c.cu): on a batch X [rows][138], and for the CAV_POLICY_GA3C agents of bound buffers
 cudaError_t run_ga3c_forward(const float *blob, const float *X, int rows, float *probs, int32_t *action_index, cudaStream_t st);
-cudaError_t run_ga3c_policy(const cav_buffers_t &bufs, const cav_config_t &cfg, const float *blob, float *probs, cudaStream_t st);
+cudaError_t run_ga3c_policy(const cav_buffers_t &bufs, const cav_config_t &cfg, const float *blob, float *probs,
+                            int32_t *list /* scratch: num_envs * num_agents + 1 ints */, cudaStream_t st);
 
 struct LaserParams {
     int E, N, B, P, obs_len, obs_off;

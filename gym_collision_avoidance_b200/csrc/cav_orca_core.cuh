@@ -129,6 +129,9 @@ CAV_HDI bool lp1_flat(const Lines &lines, int lineNo, const Line &L, float radiu
     return true;
 }
 
+#ifndef CAV_SCHED_KEY
+#define CAV_SCHED_KEY 0  // scheduling key of k_policy_move_v2: 0 = summed cost, 1 = union of the violated line indices (A/B)
+#endif
 #ifndef CAV_LP2_JUMP
 #define CAV_LP2_JUMP 0  // 1: lanes re-converge on their k-th linearProgram1 call instead of on the line index (A/B switch)
 #endif
@@ -159,7 +162,11 @@ CAV_HDI int lp2_flat(const Lines &lines, int n, float radius, float ox, float oy
         const Line li = lines.get(i);
         if (fdet(li.dx, li.dy, li.px - rx, li.py - ry) > 0.0f) {
             const float tx = rx, ty = ry;
+#if CAV_SCHED_KEY == 1
+            if (work) *work |= 1 << i;
+#else
             if (work) *work += 4 + i;
+#endif
             if (!lp1_flat(lines, i, li, radius, ox, oy, directionOpt, rx, ry)) {
                 rx = tx;
                 ry = ty;

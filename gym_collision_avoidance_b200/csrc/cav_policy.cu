@@ -213,7 +213,11 @@ __global__ void __launch_bounds__(32 * CAV_PM_WARPS, CAV_PM_MINB)
         if (rvo) {
             const int lp_fail = lp2_flat(SmemLines{s_lines + lane, LW}, nl, maxSpeed, prefx, prefy, false, nvx, nvy, &work);
             if (lp_fail < nl) {  // infeasible: linearProgram3 (Agent.cpp:419-421)
+#if CAV_SCHED_KEY == 1
+                work |= 1 << 30;
+#else
                 work += 64;
+#endif
                 Line projbuf[CT ? (NT > 2 ? NT - 1 : 2) : 31];
                 lp3_flat(SmemLines{s_lines + lane, LW}, nl, lp_fail, maxSpeed, LocalLines{projbuf}, nvx, nvy);
             }
@@ -268,7 +272,15 @@ __global__ void __launch_bounds__(32 * CAV_PM_WARPS, CAV_PM_MINB)
         __syncwarp();
         if (sched.cost && (phases & 1)) {  // the environment's scheduling key for the next step
             const unsigned env_bits = lane < LW ? ((N >= 32 ? 0xffffffffu : ((1u << N) - 1u)) << eb) : (1u << lane);
+#if CAV_SCHED_KEY == 1
+            // union over the environment's agents of the line indices that ran linearProgram1 (what a warp of such
+            // environments executes), the highest nine indices as the key, linearProgram3 on top
+            const unsigned uni = __reduce_or_sync(env_bits, (unsigned)work);
+            const int sh = NO > 9 ? NO - 9 : 0;
+            const int total = (int)((uni & 0x3fffffffu) >> sh & 511u) | ((uni >> 30) ? 512 : 0);
+#else
             const int total = __reduce_add_sync(env_bits, work);
+#endif
             if (have && a == 0) sched.cost[e] = (unsigned short)(total < 1023 ? total : 1023);
         }
     }

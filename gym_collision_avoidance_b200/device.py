@@ -178,13 +178,13 @@ class Cavoid(object):
     def env_schedule(self, stream=None):
         """(order, cost) of the policy + move kernel's environment schedule (cav_env_schedule) as int32 tensors, or None
         when the handle has no schedule (fewer than 2048 environments, CAV_ENV_ORDER=0, sub-warp-group policy kernel)."""
-        if self.L.cav_workspace_bytes(self._h) == 0:
-            return None
         E = self.c.num_envs
         order = torch.empty(E, dtype=torch.int32, device=self.device)
         cost = torch.empty(E, dtype=torch.int16, device=self.device)
-        self._check(self.L.cav_env_schedule(self._h, order.data_ptr(), cost.data_ptr(), self._stream(stream)),
-                    "cav_env_schedule")
+        rc = self.L.cav_env_schedule(self._h, order.data_ptr(), cost.data_ptr(), self._stream(stream))
+        if rc == abi.CAV_ERR_BAD_CONFIG:  # no schedule on this handle
+            return None
+        self._check(rc, "cav_env_schedule")
         return order, cost.to(torch.int32) & 0xFFFF
 
     def generate_scenarios(self, bank, seed, side_length=None, speed_bnds=(0.5, 2.0), radius_bnds=(0.2, 0.8),

@@ -260,8 +260,9 @@ size_t cav_real_bytes(cav_handle_t h);
 /* Device scratch the library holds beyond cav_buffers_t (SURVEY.md §8b lists the entry point): the kernels work out of
  * registers and their own shared memory; the one exception is the environment schedule of the policy + move kernel --
  * 6 bytes per environment (an int32 order and a uint16 cost), allocated by cav_create with cudaMalloc on the current
- * device when num_envs >= 2048 and freed by cav_destroy (CAV_ENV_ORDER=0 in the environment disables it).  Returns
- * those bytes, 0 when there are none. */
+ * device when num_envs >= 2048 and freed by cav_destroy (CAV_ENV_ORDER=0 in the environment disables it) -- and, once
+ * cav_bind_ga3c has been called, the list of live GA3C-CADRL agents (4 bytes per agent slot).  Returns those bytes, 0 when
+ * there are none. */
 size_t cav_workspace_bytes(cav_handle_t h);
 
 /* Diagnostics: copies the environment schedule into caller-owned DEVICE buffers on `stream` (either may be NULL):

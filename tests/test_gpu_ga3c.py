@@ -185,18 +185,25 @@ def test_vec_env_with_ga3c_policy(golden):
 
 def test_facade_with_ga3c_policy(golden):
     """The reference's example: CollisionAvoidanceEnv with GA3CCADRLPolicy agents (weights set from the fixture instead of
-    initialize_network, whose checkpoint files are not on the GPU box)."""
-    from gym_collision_avoidance_b200.envs import test_cases as tc
-    from gym_collision_avoidance_b200.envs.collision_avoidance_env import CollisionAvoidanceEnv
-    env = CollisionAvoidanceEnv()
-    agents = tc.get_testcase_two_agents(policies=("GA3C_CADRL", "GA3C_CADRL"))
-    for a in agents:
-        a.policy.nn.set_blob(golden["blob"])
-    env.set_agents(agents)
-    env.reset()
-    done = False
-    for _ in range(200):
-        _, _, done, _, _ = env.step({})
-        if done:
-            break
-    assert done and all(a.is_at_goal for a in env.agents) and not any(a.in_collision for a in env.agents)
+    initialize_network, whose checkpoint files are not on the GPU box), evaluation config (game over = all agents done)."""
+    import gym_collision_avoidance_b200.envs as envs_pkg
+    old = envs_pkg.Config
+    envs_pkg.set_config(make_config(2, evaluate=True))
+    try:
+        from gym_collision_avoidance_b200.envs import test_cases as tc
+        from gym_collision_avoidance_b200.envs.collision_avoidance_env import CollisionAvoidanceEnv
+        env = CollisionAvoidanceEnv()
+        agents = tc.get_testcase_two_agents(policies=("GA3C_CADRL", "GA3C_CADRL"))
+        for a in agents:
+            a.policy.nn.set_blob(golden["blob"])
+        env.set_agents(agents)
+        env.reset()
+        done, steps = False, 0
+        for steps in range(200):
+            _, _, done, _, _ = env.step({})
+            if done:
+                break
+        assert done and 40 < steps < 150
+        assert all(a.is_at_goal for a in env.agents) and not any(a.in_collision for a in env.agents)
+    finally:
+        envs_pkg.set_config(old)

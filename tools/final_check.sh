@@ -26,6 +26,12 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:"k_p
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:"k_laserscan" \
     --launch-skip 6 --launch-count 3 -f -o gpurun_out/${TAG}_laser \
     python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-graph --envs 1024 --agents 20 --laser --history 0 > gpurun_out/${TAG}_laser.log 2>&1
+# GA3C-CADRL agents: device-timed step + the network kernel alone (fp32 FLOP rate), and its ncu capture
+: > gpurun_out/${TAG}_ga3c_bench.jsonl
+for args in "" "--mix" "--envs 4096 --agents 4"; do timeout 200 python tools/bench_ga3c.py $args 2>/dev/null | tail -1 >> gpurun_out/${TAG}_ga3c_bench.jsonl; done
+cat gpurun_out/${TAG}_ga3c_bench.jsonl
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:"k_ga3c" --launch-skip 8 --launch-count 1 -f -o gpurun_out/${TAG}_ga3c \
+    python tools/bench_ga3c.py --steps 4 > gpurun_out/${TAG}_ga3c.log 2>&1
 python - <<PY
 import json
 for n in ("bench_f64_driver","bench_reference_arm","bench_f64","bench_f64_steady","bench_f64_obsf64","bench_f64_nolookahead","bench_f32"):
