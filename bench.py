@@ -432,8 +432,17 @@ def run_ours(a):
         env.step_host(h_act)
     torch.cuda.synchronize()
     e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    e2e_rank = torch.zeros(world, dtype=torch.float64, device=dev)
+    e2e_rank[rank] = e2e_t[0]
+    numa_all = [numa]
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(e2e_rank, op=dist.ReduceOp.SUM)
+        try:
+            numa_all = [None] * world
+            dist.all_gather_object(numa_all, numa)
+        except Exception:  # diagnostics only
+            numa_all = [numa]
     e2e_val = world * a.envs * a.agents * e2e_steps / float(e2e_t.item())
 
     totals, per_rank = env.gather_episode_stats()  # the only collective (NCCL all-gather), not on the step path
@@ -451,10 +460,11 @@ def run_ours(a):
             "live_agent_steps_per_s": live_steps / (dev_ms * 1e-3),
             "per_rank_ms_per_step": [x / a.steps for x in per_rank_ms],
             "wall_ms_per_step_incl_flush": t_wall / a.steps * 1e3,
-            "clocks": clocks, "numa_binding": numa,
+            "clocks": clocks, "numa_binding": numa, "numa_binding_per_rank": numa_all,
             "e2e": {"value": e2e_val, "unit": "agent-steps/s", "h2d_bytes_per_step": world * env.h2d_bytes_per_step,
                     "d2h_bytes_per_step": world * env.d2h_bytes_per_step, "bytes_scope": "whole job (all ranks)",
                     "steps": e2e_steps, "ms_per_step": float(e2e_t.item()) / e2e_steps * 1e3,
+                    "per_rank_ms_per_step": [float(x) / e2e_steps * 1e3 for x in e2e_rank.tolist()],
                     "lookahead": bool(env.host_lookahead),
                     "note": "every call uploads the [E,N,2] action array from pinned memory and downloads the float32 obs / "
                             "reward / done arrays; with lookahead (no external-policy agent reads the actions) the next "
