@@ -30,7 +30,7 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:"k_l
 : > gpurun_out/${TAG}_ga3c_bench.jsonl
 for args in "" "--mix" "--envs 4096 --agents 4"; do timeout 200 python tools/bench_ga3c.py $args 2>/dev/null | tail -1 >> gpurun_out/${TAG}_ga3c_bench.jsonl; done
 cat gpurun_out/${TAG}_ga3c_bench.jsonl
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:"k_ga3c" --launch-skip 8 --launch-count 1 -f -o gpurun_out/${TAG}_ga3c \
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:"^k_ga3c$" --launch-skip 8 --launch-count 1 -f -o gpurun_out/${TAG}_ga3c \
     python tools/bench_ga3c.py --steps 4 > gpurun_out/${TAG}_ga3c.log 2>&1
 python - <<PY
 import json
