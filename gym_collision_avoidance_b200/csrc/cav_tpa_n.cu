@@ -38,6 +38,12 @@ namespace cav {
 // parked in a per-warp shared-memory table [slot][lane] and fetched by neighbour index after the sort (1) -- 2 x (N-1)
 // fewer live registers and half the selects per compare-exchange for float64 state.
 #ifndef CAV_TPA_N_DC_SMEM
+// centre distances of an agent to its neighbours: 0 = registers, 1 = shared memory, one private column of NO values per
+// lane (default), 2 = shared memory, ONE value per unordered pair of the environment (the distance is symmetric bit for
+// bit: (-rx)*(-rx) == rx*rx), each lane computing half of its pairs -- half the IEEE float64 square roots and 1.2 KB less
+// shared memory per warp, i.e. a tenth CTA per SM.  Measured (profiles/r02r_ab.txt, parity suite green on it): the
+// kernel alone 28.3 vs 27.9 us at 16384 x 10, the step 0.0969 vs 0.0984 ms, but 4096 x 10 and 32768 x 10 noncoop ~8 %
+// WORSE (an extra __syncwarp and scattered 8-byte reads in front of the sort): stays off.
 #define CAV_TPA_N_DC_SMEM 1
 #endif
 template <typename T>
@@ -79,7 +85,9 @@ struct TpaNShape {
     // float32, single pass, staging stride == packed row length: the slice is a flat image of the HBM block
     static constexpr bool FLAT4 = sizeof(OT) == 4 && P == 1 && WS == CL;
     static constexpr size_t r16(size_t x) { return (x + 15) & ~(size_t)15; }
-    static constexpr size_t DC_BYTES = CAV_TPA_N_DC_SMEM ? r16(sizeof(T) * (NO > 0 ? NO : 1) * 32) : 0;
+    static constexpr int NP = NT * (NT - 1) / 2;  // unordered pairs of one environment
+    static constexpr size_t DC_BYTES = CAV_TPA_N_DC_SMEM == 2 ? r16(sizeof(T) * (NP > 0 ? NP : 1) * EPW)
+                                       : (CAV_TPA_N_DC_SMEM ? r16(sizeof(T) * (NO > 0 ? NO : 1) * 32) : 0);
     static constexpr size_t WARP_BYTES =
         r16(sizeof(R4<T>) * LW) + r16(sizeof(T) * LW) + r16(sizeof(OT) * (LW * WS + 4)) + DC_BYTES;
 };
@@ -105,8 +113,17 @@ __global__ void __launch_bounds__(32 * TpaNShape<T, NT, OT>::WARPS, (TpaNBounds<
     sp += a16(sizeof(T) * LW);
     OT *const stage0 = reinterpret_cast<OT *>(sp);  // [LW][WS] (+ up to 3 values of phase shift, see FLAT4)
     sp += a16(sizeof(OT) * (LW * WS + 4));
-    T *const s_dc = reinterpret_cast<T *>(sp);  // [NO][32] centre distances (CAV_TPA_N_DC_SMEM)
+    T *const s_dc = reinterpret_cast<T *>(sp);  // centre distances (CAV_TPA_N_DC_SMEM): [NO][32], or [EPW][NP] per pair
+#if CAV_TPA_N_DC_SMEM == 2
+    const int dc_env = (lane / NT) * S::NP;
+    // pair (a < b) of one environment -> a * NT - a * (a + 1) / 2 + (b - a - 1)
+    auto dc_of = [&](int o, int hh) -> T {
+        const int a = o < hh ? o : hh, bb = o < hh ? hh : o;
+        return s_dc[dc_env + a * NT - ((a * (a + 1)) >> 1) + (bb - a - 1)];
+    };
+#else
     auto dc_of = [&](int o, int hh) -> T { return s_dc[(o - (o > hh ? 1 : 0)) * 32 + lane]; };
+#endif
     const R4<T> *g_pv = reinterpret_cast<const R4<T> *>(b.pv);
     const R4<T> *g_goal = reinterpret_cast<const R4<T> *>(b.goal);
     const R4<T> *g_ego = reinterpret_cast<const R4<T> *>(b.ego);
@@ -144,6 +161,25 @@ __global__ void __launch_bounds__(32 * TpaNShape<T, NT, OT>::WARPS, (TpaNBounds<
         __syncwarp();
 
         const bool active = have && h < n;
+#if CAV_TPA_N_DC_SMEM == 2
+        // every unordered pair once: lane h takes the partners h + 1 .. h + (NT - 1) / 2 (mod NT), and for even NT the
+        // opposite agent h + NT / 2 in the lower half of the lanes only
+        if (active) {
+#pragma unroll
+            for (int k = 1; k <= NT / 2; ++k) {
+                if (2 * k == NT && h >= NT / 2) continue;
+                int o = h + k;
+                if (o >= NT) o -= NT;
+                if (o < n) {
+                    const R4<T> pvo = s_pv[eb + o];
+                    const T rx = pvo.x - pvh.x, ry = pvo.y - pvh.y;
+                    const int a = o < h ? o : h, bb = o < h ? h : o;
+                    s_dc[dc_env + a * NT - ((a * (a + 1)) >> 1) + (bb - a - 1)] = M<T>::sqrt_(rx * rx + ry * ry);
+                }
+            }
+        }
+        __syncwarp();
+#endif
         const T prx = egh.z, pry = egh.w;
         const T orx = -pry, ory = prx;  // ref_orth, agent.py:347
         unsigned long long key[NO > 0 ? NO : 1];
@@ -167,7 +203,11 @@ __global__ void __launch_bounds__(32 * TpaNShape<T, NT, OT>::WARPS, (TpaNBounds<
                     const R4<T> pvo = s_pv[eb + o];
                     const T ro = s_rad[eb + o];
                     const T rx = pvo.x - pvh.x, ry = pvo.y - pvh.y;
+#if CAV_TPA_N_DC_SMEM == 2
+                    const T dc = dc_of(o, h);  // util.l2norm == util.vec2_l2_norm, computed once per pair above
+#else
                     const T dc = M<T>::sqrt_(rx * rx + ry * ry);  // util.l2norm == util.vec2_l2_norm
+#endif
                     const T cr = glh.z + ro;                       // env.py:481
                     md = min_keep(md, dc - cr);                    // :482-487
                     coll = coll || (dc <= cr);                     // :490
@@ -175,9 +215,9 @@ __global__ void __launch_bounds__(32 * TpaNShape<T, NT, OT>::WARPS, (TpaNBounds<
                         const T d2o = dc - glh.z - ro;             // :87
                         const T po = (rx * orx + ry * ory) + (T)0;
                         key[j] = make_key<T>(M<T>::rint_(d2o * (T)100), po, o, false);
-#if CAV_TPA_N_DC_SMEM
+#if CAV_TPA_N_DC_SMEM == 1
                         s_dc[j * 32 + lane] = dc;
-#else
+#elif !CAV_TPA_N_DC_SMEM
                         dcv[j] = dc;
 #endif
                         ++nc;
