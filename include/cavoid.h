@@ -15,12 +15,17 @@
  *   - every function returns 0 (CAV_OK) or a negative cav_status_t; nothing throws across the ABI;
  *     cav_last_error(h) returns a human-readable message for the last failure on that handle.
  *   - all device pointers are BORROWED (e.g. torch tensor.data_ptr()); the library never frees them.
- *     Vector columns (pv / goal / ht / ego / aux*) and obs must be 16-byte aligned.
+ *     Vector columns (pv / goal / ht / ego / aux*) and obs must be 16-byte aligned.  The library itself allocates
+ *     two small scratch arrays with cudaMalloc (cav_workspace_bytes): the environment schedule of the policy + move
+ *     kernel at cav_create and the live-agent list of the GA3C-CADRL network at cav_bind_ga3c; cav_destroy frees them.
  *   - all work is ordered on the caller's CUDA stream; no implicit synchronisation, no host allocation and
- *     no host<->device copy on the step path, so a step can be captured into a CUDA graph.  (cav_step may run half of the
- *     environments on a library-owned helper stream that is forked from the caller's stream with an event and joined back
- *     into it before cav_step returns to the stream's next operation: invisible to the caller, graph capture records it
- *     as a fork / join; CAV_STEP_SPLIT=0 in the environment disables it.)
+ *     no host<->device copy on the step path, so a step can be captured into a CUDA graph.  (cav_step may run ranges of
+ *     the environments and the environment-ordering kernel on library-owned helper streams that are forked from the
+ *     caller's stream with an event and joined back into it before cav_step returns to the stream's next operation:
+ *     invisible to the caller, graph capture records it as forks / joins; CAV_STEP_SPLIT=0 in the environment disables
+ *     the ranges.)
+ *   - agents whose policy id is CAV_POLICY_GA3C need a network (cav_bind_ga3c) before the first cav_step; without one
+ *     they keep their previous action (the host classes refuse to build such an environment).
  *   - a handle is bound to the CUDA device that was current at cav_create; use it from one thread at a time.
  *     Multi-GPU = one handle per device / rank (environments are independent; no collective per step).
  *   - `real` below means float when cfg.precision == CAV_F32 and double when CAV_F64.  CAV_F64 reproduces the

@@ -99,3 +99,19 @@ def test_config_defaults_match_reference_semantics():
     with pytest.raises(abi.CavoidError):
         m.STATES_IN_OBS = ["dist_to_goal", "other_agents_states_encoded"]
         cfgmod.obs_layout(m)
+
+
+def test_ga3c_entry_points_validate_arguments_without_gpu(libpath):
+    """Argument errors of the GA3C-CADRL entry points are reported before any CUDA call: NULL blob / X, negative row count,
+    misaligned blob, bad handles."""
+    L = abi.load_library()
+    buf = ctypes.create_string_buffer(64)
+    a16 = (ctypes.addressof(buf) + 15) & ~15
+    assert L.cav_ga3c_forward(None, None, 4, None, None, None) == -2      # CAV_ERR_NULL_POINTER
+    assert b"NULL" in L.cav_last_error(None)
+    assert L.cav_ga3c_forward(a16, None, 4, None, None, None) == -2
+    assert L.cav_ga3c_forward(a16, a16, -1, None, None, None) == -1       # CAV_ERR_BAD_CONFIG
+    assert L.cav_ga3c_forward(a16 + 4, a16, 1, None, None, None) == -3    # CAV_ERR_MISALIGNED
+    assert L.cav_bind_ga3c(None, a16) == -6                               # CAV_ERR_BAD_HANDLE
+    assert L.cav_k_ga3c(None, None, None) == -6
+    assert L.cav_env_schedule(None, None, None, None) == -6

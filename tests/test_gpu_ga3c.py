@@ -207,3 +207,28 @@ def test_facade_with_ga3c_policy(golden):
         assert all(a.is_at_goal for a in env.agents) and not any(a.in_collision for a in env.agents)
     finally:
         envs_pkg.set_config(old)
+
+
+def test_bind_and_phase_errors(golden):
+    """cav_k_ga3c without a network, a misaligned blob, an observation without pref_speed: status codes, no crash."""
+    from gpu_common import GpuRunner
+    N = 3
+    c = to_cav_config(make_config(N, evaluate=True), 8, N, precision="f64")
+    r = GpuRunner(c)
+    L = r.cav.L
+    assert L.cav_k_ga3c(r.cav._h, None, None) == -4 and b"cav_bind_ga3c" in L.cav_last_error(r.cav._h)   # NOT_BOUND
+    blob = torch.zeros(abi.CAV_GA3C_BLOB_FLOATS + 4, dtype=torch.float32, device="cuda")
+    assert L.cav_bind_ga3c(r.cav._h, blob.data_ptr() + 4) == -3                                          # MISALIGNED
+    r.cav.bind_ga3c(golden["blob"])
+    assert r.cav.L.cav_workspace_bytes(r.cav._h) >= (8 * N + 1) * 4
+    r.cav.bind_ga3c(None)  # detach
+    assert L.cav_k_ga3c(r.cav._h, None, None) == -4
+    with pytest.raises(abi.CavoidError):
+        r.cav.bind_ga3c(np.zeros(17, np.float32))
+    r.cav.close()
+    c2 = to_cav_config(make_config(N, evaluate=True, states_in_obs=["num_other_agents", "dist_to_goal", "other_agents_states"]),
+                       8, N, precision="f64")
+    r2 = GpuRunner(c2)
+    rc = r2.cav.L.cav_bind_ga3c(r2.cav._h, torch.from_numpy(golden["blob"]).cuda().data_ptr())
+    assert rc == -1 and b"pref_speed" in r2.cav.L.cav_last_error(r2.cav._h)                              # BAD_CONFIG
+    r2.cav.close()
