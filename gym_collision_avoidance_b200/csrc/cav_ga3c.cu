@@ -273,7 +273,9 @@ __global__ void __launch_bounds__(ga::NT, 1)
         }
         if (action_index) action_index[row] = best;
         if (MODE == 1) {
-            // network.py:7-16: full speed x 5 headings, half speed x 3, zero speed x 3; GA3CCADRLPolicy.py:80-84
+            // network.py:7-16: full speed x 5 headings, half speed x 3, zero speed x 3; GA3CCADRLPolicy.py:80-84.  The speed
+            // factor is 1, 0.5 or 0, so rounding pref_speed to float32 before the product equals the reference's float64
+            // product rounded into its float32 all_actions array (env.py:305-307)
             const double pi6 = 3.14159265358979323846 / 6, pi12 = 3.14159265358979323846 / 12;
             double sp, dh;
             if (best < 5) {

@@ -135,7 +135,8 @@ static void SFX(policy_env)(const cav_config_t *cfg, const cav_buffers_t *b, con
             cavo_ga3c_forward(g_ga3c_blob, X, 1, NULL, &best);
             double sp, dh;
             ga3c_action(best, &sp, &dh);
-            /* obs['pref_speed'] is a float32 entry of the observation dict (config.py:93-170 dtype) */
+            /* pref_speed * raw_action[0] lands in the float32 all_actions array (env.py:305-307); raw_action[0] is 1, 0.5 or
+             * 0, so rounding pref_speed to float32 first (the observation column may already be float32) gives the same value */
             a0 = (REAL)((double)(float)orow[cfg->obs_offset[CAV_OBS_PREF_SPEED]] * sp);
             a1 = (REAL)dh;
         } else if (pol == CAV_POLICY_RVO) { /* RVOPolicy.py:50-122 */
