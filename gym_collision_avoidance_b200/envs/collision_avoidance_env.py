@@ -181,6 +181,7 @@ class CollisionAvoidanceEnv(object):
                                   seed=int(np.random.randint(0, 2 ** 31 - 1)) if C.RVO_COLLAB_COEFF < 0 else 0)
         self._c = c
         self._cav = Cavoid(c, self.device)
+        self._ga3c_bound = None
         if C.USE_STATIC_MAP:
             self.map = Map(16, 16, 0.1, self.static_map_filename, static_map=self.static_map_array)
             self._cav.state.set_static_map(self.map.bits())
@@ -226,7 +227,9 @@ class CollisionAvoidanceEnv(object):
             # initialised from different checkpoints cannot share a device network)
             if ga3c.weight_blob is None:
                 raise abi.CavoidError("GA3CCADRLPolicy: call agent.policy.initialize_network() before env.set_agents / reset")
-            self._cav.bind_ga3c(ga3c.weight_blob)
+            if getattr(self, "_ga3c_bound", None) is not ga3c.weight_blob:  # upload the 683 KB once, not at every reset
+                self._cav.bind_ga3c(ga3c.weight_blob)
+                self._ga3c_bound = ga3c.weight_blob
         self._cav.state.load_host(hs, cols=None if full else self._AGENT_COLS)
 
     def _download(self):
