@@ -190,3 +190,105 @@ def test_oracle_step_with_ga3c_agents(golden, prec, obs_f32):
         assert len(seen) >= 2, "the agents must have turned to pass each other"
     finally:
         cav_oracle.set_ga3c(None)
+
+
+def _varint(v):
+    out = bytearray()
+    while True:
+        b = v & 0x7f
+        v >>= 7
+        out.append(b | (0x80 if v else 0))
+        if not v:
+            return bytes(out)
+
+
+def _pb(field, wire, payload):
+    key = _varint((field << 3) | wire)
+    if wire == 0:
+        return key + _varint(payload)
+    if wire == 2:
+        return key + _varint(len(payload)) + payload
+    return key + payload  # fixed32 / fixed64
+
+
+def _write_bundle(prefix, tensors, corrupt=None):
+    """A minimal single-shard TF tensor bundle (uncompressed one-block SSTable index + raw data), written by hand so that
+    the reader is tested wherever the reference's checkpoints are absent."""
+    import struct
+    data = b""
+    entries = [(b"", b"")]  # BundleHeaderProto under the empty key (contents irrelevant to the reader)
+    for name in sorted(tensors):
+        arr = np.asarray(tensors[name])
+        raw = arr.tobytes()
+        crc = tf1_files._masked_crc(raw)
+        if corrupt == name:
+            raw = raw[:-1] + bytes([raw[-1] ^ 0xFF])
+        shape = b"".join(_pb(2, 2, _pb(1, 0, int(d))) for d in arr.shape)
+        dt = {np.dtype("float32"): 1, np.dtype("int32"): 3}[arr.dtype]
+        entry = _pb(1, 0, dt) + _pb(2, 2, shape) + _pb(4, 0, len(data)) + _pb(5, 0, len(raw)) + _pb(6, 5, struct.pack("<I", crc))
+        entries.append((name.encode(), entry))
+        data += raw
+
+    def block(kvs):
+        body, prev = b"", b""
+        for k, v in kvs:
+            shared = 0
+            while shared < min(len(prev), len(k)) and prev[shared] == k[shared]:
+                shared += 1
+            body += _varint(shared) + _varint(len(k) - shared) + _varint(len(v)) + k[shared:] + v
+            prev = k
+        return body + struct.pack("<II", 0, 1)  # one restart point at offset 0, num_restarts = 1
+    blocks = b""
+    dblk = block(entries)
+    d_off, blocks = len(blocks), blocks + dblk + b"\x00" + b"\x00" * 4  # trailer: no compression + (unchecked) block crc
+    mblk = block([])
+    m_off, blocks = len(blocks), blocks + mblk + b"\x00" + b"\x00" * 4
+    iblk = block([(b"\xff", _varint(d_off) + _varint(len(dblk)))])
+    i_off, blocks = len(blocks), blocks + iblk + b"\x00" + b"\x00" * 4
+    foot = _varint(m_off) + _varint(len(mblk)) + _varint(i_off) + _varint(len(iblk))
+    foot += b"\x00" * (40 - len(foot)) + struct.pack("<Q", 0xdb4775248b80fb57)
+    with open(prefix + ".index", "wb") as fh:
+        fh.write(blocks + foot)
+    with open(prefix + ".data-00000-of-00001", "wb") as fh:
+        fh.write(data)
+
+
+def test_bundle_reader_on_a_hand_written_bundle(tmp_path):
+    """Prefix-compressed keys, the footer's block handles, dtype / shape / offset / size fields and the CRC check of the
+    tensor-bundle reader, on a bundle built by this test."""
+    rng = np.random.RandomState(4)
+    tensors = {"layer1/bias:0": rng.randn(256).astype(np.float32), "layer1/kernel:0": rng.randn(68, 256).astype(np.float32),
+               "layer2/kernel:0": rng.randn(4, 3, 2).astype(np.float32), "step:0": np.array(123, np.int32)}
+    p = str(tmp_path / "net")
+    _write_bundle(p, tensors)
+    got = tf1_files.read_checkpoint(p)
+    assert set(got) == set(tensors)
+    for k, v in tensors.items():
+        assert got[k].dtype == v.dtype and got[k].shape == v.shape and np.array_equal(got[k], v)
+    _write_bundle(p, tensors, corrupt="layer1/kernel:0")
+    with pytest.raises(ValueError, match="CRC"):
+        tf1_files.read_checkpoint(p)
+    assert np.array_equal(tf1_files.read_checkpoint(p, verify=False)["layer1/bias:0"], tensors["layer1/bias:0"])
+
+
+def test_meta_graph_reader_on_a_hand_written_graph(tmp_path):
+    """NodeDef name / op / inputs / attrs (shape, tensor with packed floats, tensor_content, scalar int) from protobuf bytes."""
+    import struct
+    shape = _pb(2, 2, _pb(1, 0, (1 << 64) - 1)) + _pb(2, 2, _pb(1, 0, 138))               # [-1, 138]
+    ph = _pb(1, 2, b"X") + _pb(2, 2, b"Placeholder") + _pb(5, 2, _pb(1, 2, b"shape") + _pb(2, 2, _pb(7, 2, shape)))
+    tconst = _pb(1, 0, 1) + _pb(2, 2, _pb(2, 2, _pb(1, 0, 3))) + _pb(5, 2, struct.pack("<3f", 1.0, 5.0, 3.14))
+    const = _pb(1, 2, b"Const") + _pb(2, 2, b"Const") + _pb(5, 2, _pb(1, 2, b"value") + _pb(2, 2, _pb(8, 2, tconst)))
+    tcont = _pb(1, 0, 3) + _pb(2, 2, _pb(2, 2, _pb(1, 0, 2))) + _pb(4, 2, struct.pack("<2i", 0, 5))
+    stack = _pb(1, 2, b"s/stack") + _pb(2, 2, b"Const") + _pb(5, 2, _pb(1, 2, b"value") + _pb(2, 2, _pb(8, 2, tcont)))
+    sub = _pb(1, 2, b"sub") + _pb(2, 2, b"Sub") + _pb(3, 2, b"X") + _pb(3, 2, b"Const") + _pb(3, 2, b"^ctl") + \
+        _pb(5, 2, _pb(1, 2, b"N") + _pb(2, 2, _pb(3, 0, 4)))
+    graph = b"".join(_pb(1, 2, n) for n in (ph, const, stack, sub))
+    meta = _pb(1, 2, b"ignored meta_info_def") + _pb(2, 2, graph)
+    path = tmp_path / "g.meta"
+    path.write_bytes(meta)
+    nodes, order = tf1_files.read_meta_graph(str(path))
+    assert order == ["X", "Const", "s/stack", "sub"]
+    assert nodes["X"]["op"] == "Placeholder" and nodes["X"]["attrs"]["shape"] == ("shape", [-1, 138])
+    assert np.allclose(nodes["Const"]["attrs"]["value"], [1.0, 5.0, 3.14]) and nodes["Const"]["attrs"]["value"].dtype == np.float32
+    assert list(nodes["s/stack"]["attrs"]["value"]) == [0, 5]
+    assert nodes["sub"]["inputs"] == ["X", "Const", "^ctl"] and nodes["sub"]["attrs"]["N"] == 4
