@@ -356,6 +356,77 @@ CAV_HDI int orca_lines_n(int n, int ego, const float4 *s_f4, const float *s_frad
                          [&](int k) { return (int)((order >> (4 * k)) & 15ull); }, lines);
 }
 
+// Neighbour order for n <= 16 agents in MORE than one kd-tree leaf (n > 10): the reference's list is ascending distSq with
+// exact ties in insertion order = the order in which the kd-tree query visits the agents (Agent.cpp:424-448,
+// KdTree.cpp:266-298), so the visiting rank is the tie-break field of the key: (distSq bits : rank : index) through the
+// same sorting network.  rank[o * rstride] = position of agent o in THIS ego's traversal (nullptr: single leaf, the rank is
+// the index).
+template <int NO>
+CAV_HDI unsigned long long orca_order_nk(int n, int ego, const float4 *s_f4, float rangeSq, bool any, const uint8_t *rank,
+                                         int rstride, int &nn) {
+    static_assert(NO <= 15, "4-bit packed order");
+    const float4 me = s_f4[ego];
+    unsigned long long key[NO > 0 ? NO : 1];
+    nn = 0;
+#pragma unroll
+    for (int j = 0; j < NO; ++j) {
+        const int o = j + (j >= ego ? 1 : 0);
+        key[j] = ~0ull;
+        if (any && o < n) {
+            const float4 ot = s_f4[o];
+            const float dx = me.x - ot.x, dy = me.y - ot.y;
+            const float distSq = fdot(dx, dy, dx, dy);
+            if (distSq < rangeSq) {
+                const unsigned r = rank ? (unsigned)rank[o * rstride] : (unsigned)o;
+                key[j] = ((unsigned long long)float_bits(distSq) << 32) | (unsigned long long)(r << 4) | (unsigned)o;
+                ++nn;
+            }
+        }
+    }
+    sort_network<NO>([&](int i, int j) {
+        const unsigned long long ka = key[i], kb = key[j];
+        const bool sw = kb < ka;
+        key[i] = sw ? kb : ka;
+        key[j] = sw ? ka : kb;
+    });
+    unsigned long long order = 0ull;
+#pragma unroll
+    for (int k = 0; k < NO; ++k) order |= (unsigned long long)(key[k] & 15ull) << (4 * k);
+    return order;
+}
+
+// this ego's kd-tree visiting ranks (one byte per agent, rank[o * rstride])
+CAV_HDI void kd_visit_ranks(const KdTree &kd, float px, float py, uint8_t *rank, int rstride) {
+    int r = 0;
+    kd_traverse(kd, px, py, [&](int o) { rank[o * rstride] = (uint8_t)r++; });
+}
+
+// compile-time slot count 11 .. 16 with the kd-tree order (rank == nullptr: one leaf); half-planes only, as orca_lines_n
+template <int NO>
+CAV_HDI int orca_lines_nk(int n, int ego, const float4 *s_f4, const float *s_frad, float &prefx, float &prefy,
+                          float timeHorizon, float timeStep, float collab, float neighborDist, int maxNeighbors,
+                          const uint8_t *rank, int rstride, SmemLines lines) {
+    int nn;
+    const unsigned long long order = orca_order_nk<NO>(n, ego, s_f4, neighborDist * neighborDist,
+                                                       maxNeighbors > 0 && collab != 0.0f, rank, rstride, nn);
+    if (nn > maxNeighbors) nn = maxNeighbors;
+    return orca_lines_v2(nn, ego, s_f4, s_frad, prefx, prefy, 1.0f / timeHorizon, 1.0f / timeStep, collab,
+                         [&](int k) { return (int)((order >> (4 * k)) & 15ull); }, lines);
+}
+
+// ... and with the linear programs (the host tests' entry)
+template <int NO, typename Proj>
+CAV_HDI void orca_v2_nk(int n, int ego, const float4 *s_f4, const float *s_frad, float prefx, float prefy, float maxSpeed,
+                        float timeHorizon, float timeStep, float collab, float neighborDist, int maxNeighbors,
+                        const uint8_t *rank, int rstride, SmemLines lines, Proj proj, float &nvx, float &nvy) {
+    int nn;
+    const unsigned long long order = orca_order_nk<NO>(n, ego, s_f4, neighborDist * neighborDist,
+                                                       maxNeighbors > 0 && collab != 0.0f, rank, rstride, nn);
+    if (nn > maxNeighbors) nn = maxNeighbors;
+    orca_solve_v2(nn, ego, s_f4, s_frad, prefx, prefy, maxSpeed, 1.0f / timeHorizon, 1.0f / timeStep, collab,
+                  [&](int k) { return (int)((order >> (4 * k)) & 15ull); }, lines, proj, nvx, nvy);
+}
+
 // insertion of the neighbours in kd-tree visiting order (index order when kd == nullptr) into this thread's key slots
 CAV_HDI int orca_neighbors_rt(int n, int ego, const float4 *s_f4, float collab, float neighborDist, int maxNeighbors,
                               unsigned long long *keys, int kstride, const KdTree *kd) {

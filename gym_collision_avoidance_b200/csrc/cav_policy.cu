@@ -31,8 +31,10 @@
 //     k_env_order sorts each launch range by decreasing cost (one CTA per range: 1024-bucket counting sort in shared
 //     memory), and position q of the next step's launch processes environment order[q].  Environments are independent:
 //     the order changes which warp computes an environment, never what it computes.
-// NT > 0: compile-time agent count (2..10: sorting network in registers, no kd-tree needed: single leaf).
-// NT == 0: run-time agent count 11..32 (insertion sort through shared memory in kd-tree order).
+// NT in 2..10: compile-time agent count, sorting network in registers, no kd-tree needed (single leaf).
+// NT in 11..16: compile-time agent count, the same network with each neighbour's kd-tree VISITING RANK as the tie-break
+//   field of its key (the lane walks the tree once and notes the ranks, one byte per agent) -- CAV_PM_CTK.
+// NT == 0: run-time agent count 17..32 (insertion sort through shared memory in kd-tree order).
 #include "cav_orca_core.cuh"
 #include "cav_tpa_common.cuh"
 
@@ -48,6 +50,10 @@ namespace cav {
 #define CAV_PM_MINB 12
 #endif
 
+#ifndef CAV_PM_CTK
+#define CAV_PM_CTK 1  // compile-time instantiations for 11 .. 16 agents (kd-tree rank in a register sorting network); 0: run-time-n path
+#endif
+
 struct PmLayout {  // per-warp shared-memory slice (bytes)
     int N, EPW, LW, NO;
     int off_rad, off_lines, off_keys, off_box, off_meta, off_perm, warp_bytes;
@@ -55,7 +61,7 @@ struct PmLayout {  // per-warp shared-memory slice (bytes)
 
 __host__ __device__ constexpr int pm_r16(int x) { return (x + 15) & ~15; }
 
-__host__ __device__ constexpr PmLayout pm_layout(int N, bool generic) {
+__host__ __device__ constexpr PmLayout pm_layout(int N, int mode) {
     PmLayout L{};
     L.N = N;
     L.EPW = 32 / N;
@@ -70,8 +76,9 @@ __host__ __device__ constexpr PmLayout pm_layout(int N, bool generic) {
     L.off_box = o;
     L.off_meta = o;
     L.off_perm = o;
-    if (generic) {
-        o += pm_r16(8 * L.NO * L.LW);
+    if (mode != 0) {
+        // mode 1: 64-bit insertion-sort keys [NO][LW]; mode 2: one byte of kd-tree visiting rank per (agent, lane) [N][32]
+        o += mode == 1 ? pm_r16(8 * L.NO * L.LW) : pm_r16(32 * N);
         L.off_box = o;
         o += 16 * L.EPW * (2 * N - 1);
         L.off_meta = o;
@@ -105,14 +112,18 @@ template <typename T, int NT>
 __global__ void __launch_bounds__(32 * CAV_PM_WARPS, CAV_PM_MINB)
     k_policy_move_v2(TpaBuffers b, KParams<T> p, const float *__restrict__ ext, uint8_t *__restrict__ kd_order, int phases,
                      T dt, int tile0, int ntiles, PmLayout rl, EnvSchedule sched) {
-    constexpr bool CT = NT > 0;
-    constexpr PmLayout cl = pm_layout(CT ? NT : 32, false);
-    const int N = CT ? NT : rl.N;
-    const int EPW = CT ? cl.EPW : rl.EPW;
-    const int LW = CT ? cl.LW : rl.LW;
-    const int NO = CT ? cl.NO : rl.NO;
-    const int off_rad = CT ? cl.off_rad : rl.off_rad, off_lines = CT ? cl.off_lines : rl.off_lines;
-    const int warp_bytes = CT ? cl.warp_bytes : rl.warp_bytes;
+    constexpr bool CN = NT > 0;                 // compile-time agent count
+    constexpr bool CT = NT > 0 && NT <= CAV_KD_MAX_LEAF;  // ... in one kd-tree leaf: the neighbour order needs no tree
+    constexpr bool CTK = NT > CAV_KD_MAX_LEAF;  // ... 11 .. 16: kd-tree visiting ranks break distance ties
+    constexpr PmLayout cl = pm_layout(CN ? NT : 32, CTK ? 2 : 0);
+    const int N = CN ? NT : rl.N;
+    const int EPW = CN ? cl.EPW : rl.EPW;
+    const int LW = CN ? cl.LW : rl.LW;
+    const int NO = CN ? cl.NO : rl.NO;
+    const int off_rad = CN ? cl.off_rad : rl.off_rad, off_lines = CN ? cl.off_lines : rl.off_lines;
+    const int warp_bytes = CN ? cl.warp_bytes : rl.warp_bytes;
+    const int off_keys = CN ? cl.off_keys : rl.off_keys, off_box = CN ? cl.off_box : rl.off_box;
+    const int off_meta = CN ? cl.off_meta : rl.off_meta, off_perm = CN ? cl.off_perm : rl.off_perm;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x;
@@ -169,9 +180,9 @@ __global__ void __launch_bounds__(32 * CAV_PM_WARPS, CAV_PM_MINB)
             const unsigned env_bits = (N >= 32 ? 0xffffffffu : ((1u << N) - 1u)) << eb;
             use_kd = have && n > CAV_KD_MAX_LEAF && (rvo_mask & env_bits) != 0u && kd_order != nullptr;
             const int slots = 2 * N - 1;
-            kd.box = reinterpret_cast<float4 *>(sp + rl.off_box) + el * slots;
-            kd.meta = reinterpret_cast<KdMeta *>(sp + rl.off_meta) + el * slots;
-            kd.perm = reinterpret_cast<uint8_t *>(sp + rl.off_perm) + eb;
+            kd.box = reinterpret_cast<float4 *>(sp + off_box) + el * slots;
+            kd.meta = reinterpret_cast<KdMeta *>(sp + off_meta) + el * slots;
+            kd.perm = reinterpret_cast<uint8_t *>(sp + off_perm) + eb;
             if (use_kd && a < n) kd.perm[a] = kd_order[gi];
             __syncwarp();
             if (use_kd && a == 0) kd_build(s_f4 + eb, n, kd);
@@ -202,8 +213,15 @@ __global__ void __launch_bounds__(32 * CAV_PM_WARPS, CAV_PM_MINB)
                 nl = orca_lines_n<(CT ? NT - 1 : 1)>(n, a, s_f4 + eb, s_frad + eb, prefx, prefy, p.rvo_inv_time_horizon_num,
                                                      p.rvo_time_step, ego_collab, p.rvo_neighbor_dist, p.rvo_max_neighbors,
                                                      SmemLines{s_lines + lane, LW});
+            } else if (CTK) {
+                // this ego's kd-tree visiting ranks, one byte per agent in the lane's column of [N][32]
+                uint8_t *s_rank = reinterpret_cast<uint8_t *>(sp + off_keys) + lane;
+                if (use_kd) kd_visit_ranks(kd, s_f4[lane].x, s_f4[lane].y, s_rank, 32);
+                nl = orca_lines_nk<(CTK ? NT - 1 : 1)>(n, a, s_f4 + eb, s_frad + eb, prefx, prefy, p.rvo_inv_time_horizon_num,
+                                                       p.rvo_time_step, ego_collab, p.rvo_neighbor_dist, p.rvo_max_neighbors,
+                                                       use_kd ? s_rank : nullptr, 32, SmemLines{s_lines + lane, LW});
             } else {
-                unsigned long long *s_keys = reinterpret_cast<unsigned long long *>(sp + rl.off_keys);
+                unsigned long long *s_keys = reinterpret_cast<unsigned long long *>(sp + off_keys);
                 nl = orca_lines_rt(n, a, s_f4 + eb, s_frad + eb, prefx, prefy, p.rvo_inv_time_horizon_num, p.rvo_time_step,
                                    ego_collab, p.rvo_neighbor_dist, p.rvo_max_neighbors, s_keys + lane, LW,
                                    use_kd ? &kd : nullptr, SmemLines{s_lines + lane, LW});
@@ -218,7 +236,7 @@ __global__ void __launch_bounds__(32 * CAV_PM_WARPS, CAV_PM_MINB)
 #else
                 work += 64;
 #endif
-                Line projbuf[CT ? (NT > 2 ? NT - 1 : 2) : 31];
+                Line projbuf[CN ? (NT > 2 ? NT - 1 : 2) : 31];
                 lp3_flat(SmemLines{s_lines + lane, LW}, nl, lp_fail, maxSpeed, LocalLines{projbuf}, nvx, nvy);
             }
             // Agent::update (Agent.cpp:470-475) in float, then RVOPolicy.py:96-111 in `real`
@@ -343,7 +361,7 @@ cudaError_t run_env_order(const EnvSchedule &sched, const int *at, int nranges, 
 template <typename T, int NT>
 static cudaError_t launch_v2(const cav_buffers_t &bufs, const KParams<T> &p, const float *ext, int phases, double dt,
                              int sm_count, cudaStream_t st, int env0, int env1, const EnvSchedule &sched) {
-    const PmLayout L = pm_layout(p.N, NT == 0);
+    const PmLayout L = pm_layout(p.N, NT == 0 ? 1 : (NT > CAV_KD_MAX_LEAF ? 2 : 0));
     const int epb = CAV_PM_WARPS * L.EPW;
     if (env1 < 0 || env1 > p.E) env1 = p.E;
     const int tile0 = env0 / epb;
@@ -362,7 +380,7 @@ static cudaError_t launch_v2(const cav_buffers_t &bufs, const KParams<T> &p, con
 }
 
 // every N in [2, 32]; cudaErrorNotSupported otherwise (N = 1 and N > 32 take the sub-warp-group kernel)
-int policy_move_v2_tile_envs(int N) { return CAV_PM_WARPS * pm_layout(N, N > 10).EPW; }
+int policy_move_v2_tile_envs(int N) { return CAV_PM_WARPS * pm_layout(N, N > 10 ? 1 : 0).EPW; }
 
 template <typename T>
 cudaError_t run_policy_move_v2(const cav_buffers_t &bufs, const KParams<T> &p, const float *ext, int phases, double dt,
@@ -379,6 +397,14 @@ cudaError_t run_policy_move_v2(const cav_buffers_t &bufs, const KParams<T> &p, c
         CAV_CASE(8)
         CAV_CASE(9)
         CAV_CASE(10)
+#if CAV_PM_CTK
+        CAV_CASE(11)
+        CAV_CASE(12)
+        CAV_CASE(13)
+        CAV_CASE(14)
+        CAV_CASE(15)
+        CAV_CASE(16)
+#endif
 #undef CAV_CASE
         default: break;
     }

@@ -114,16 +114,18 @@ def test_f32_vs_oracle_f32(N, mapping, monkeypatch):
 
 
 @pytest.mark.parametrize("mapping", ["tpa", "group"])
-def test_ragged_envs_and_mixed_policies(mapping, monkeypatch):
-    """Environments with fewer agents than slots (num_active), mixed policies incl. external/learning actions."""
+@pytest.mark.parametrize("N", [8, 13])
+def test_ragged_envs_and_mixed_policies(mapping, N, monkeypatch):
+    """Environments with fewer agents than slots (num_active), mixed policies incl. external/learning actions.  N = 13:
+    environments with more than ten active agents order their neighbours through the kd-tree, the others are one leaf."""
     from gpu_common import GpuRunner, to_dev
     monkeypatch.setenv("CAV_TPA_MAX_N", "32" if mapping == "tpa" else "0")
-    N, E = 8, 64
+    E = 64
     cfg = make_config(N, evaluate=False)
     c = to_cav_config(cfg, E, N, precision="f64", track_aux=True)
     rng = np.random.RandomState(5)
     na = rng.randint(2, N + 1, size=E).astype(np.int32)
-    pols = ["learning", "RVO", "noncoop", "static", "external", "RVO", "noncoop", "RVO"]
+    pols = (["learning", "RVO", "noncoop", "static", "external", "RVO", "noncoop", "RVO"] + ["RVO"] * 8)[:N]
     bank = _bank(E, N, seed=9, policies=pols, dense=True, num_active=na)
     hs = HostState(c)
     orc = Oracle(c)

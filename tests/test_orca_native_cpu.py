@@ -33,6 +33,8 @@ def host(tmp_path_factory):
     L.host_orca_solve_kd.argtypes = [ctypes.c_int, ctypes.c_int, fp, fp, fp] + [ctypes.c_float] * 7 + \
         [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, fp, fp]
     L.host_orca_solve_kd.restype = ctypes.c_int
+    L.host_orca_solve_kd_ct.argtypes = L.host_orca_solve_kd.argtypes
+    L.host_orca_solve_kd_ct.restype = ctypes.c_int
     return L
 
 
@@ -108,7 +110,8 @@ def test_finite_neighbor_dist_and_max_neighbors_match_reference(host):
 
 
 @pytest.mark.parametrize("n,kind", [(12, "circle"), (16, "circle"), (20, "circle"), (20, "lattice"), (33, "lattice"),
-                                    (64, "lattice"), (11, "stack"), (24, "circle_finite")])
+                                    (64, "lattice"), (11, "stack"), (24, "circle_finite"), (13, "lattice"), (16, "lattice"),
+                                    (14, "circle_finite"), (15, "stack")])
 def test_device_kdtree_source_tie_order_bit_exact_vs_reference_rvo2(host, n, kind):
     """cav_kdtree.cuh (the kernels' kd-tree: build over the persistent permutation + visiting order) and the generic
     solver's insertion in that order, on scenes made of exact float32 distance ties, stepped for 60 doSteps against ONE
@@ -154,6 +157,14 @@ def test_device_kdtree_source_tie_order_bit_exact_vs_reference_rvo2(host, n, kin
             assert rc == 0
             got = np.array([ovx.value, ovy.value], np.float32)
             assert got.tobytes() == all_ref[ego].tobytes(), (kind, step, ego, got, all_ref[ego], perm.tolist())
+            if 11 <= n <= 16:  # the compile-time solver (visiting rank as the tie-break field of a sorting-network key)
+                cvx, cvy = ctypes.c_float(), ctypes.c_float()
+                rc = host.host_orca_solve_kd_ct(n, ego, _fp(pos), _fp(vel), _fp(rad), msp[ego], pref[ego, 0], pref[ego, 1],
+                                                th, dt, np.float32(0.5), nd, 64, perm.ctypes.data, 0, ctypes.byref(cvx),
+                                                ctypes.byref(cvy))
+                assert rc == 0
+                got = np.array([cvx.value, cvy.value], np.float32)
+                assert got.tobytes() == all_ref[ego].tobytes(), ("ct", kind, step, ego, got, all_ref[ego], perm.tolist())
         vel = all_ref
         pos = (pos + vel * dt).astype(np.float32)
     R.rvo2ref_delete(sim)
